@@ -1,0 +1,152 @@
+"""Data loaders.
+
+Real datasets follow the reference's recipes (src/dataset/dataloader.py):
+  * CIFAR10  — RandomCrop(32, pad 4) + HFlip + Normalize; per-label ``random.sample`` of
+    ``distribution[label]`` indices; shuffle; test batch 100  (:61-92)
+  * MNIST    — ToTensor + Normalize (variants)
+  * AGNEWS   — CSV + BertTokenizer('bert-base-cased'), max_len 128  (:16-59)
+  * SPEECHCOMMANDS — 10-class subset, NumPy MFCC 40x98  (:95-122)
+They need files under ``./data`` (no network here).  When the files are missing, or
+``synthetic=True`` / ``SLB200_SYNTHETIC=1``, a ``SyntheticDataset`` with the same tensor
+shapes, dtypes and per-label counts is used instead (what ``bench.py`` uses).
+"""
+from __future__ import annotations
+
+import os
+import random
+from collections import defaultdict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Dataset, Subset
+
+# name -> (sample shape, dtype, num classes, test batch size)
+DATASET_SHAPES: Dict[str, Tuple[Tuple[int, ...], torch.dtype, int, int]] = {
+    "CIFAR10": ((3, 32, 32), torch.float32, 10, 100),
+    "MNIST": ((1, 28, 28), torch.float32, 10, 100),
+    "AGNEWS": ((128,), torch.long, 4, 20),
+    "EMOTION": ((128,), torch.long, 6, 20),
+    "SPEECHCOMMANDS": ((40, 98), torch.float32, 10, 20),
+}
+
+
+class SyntheticDataset(Dataset):
+    """Deterministic random samples with exact per-label counts.  Samples are generated once
+    into a pinned-able tensor (class-dependent mean so that a model can actually learn)."""
+
+    def __init__(self, data_name: str, distribution: Sequence[int], seed: int = 0, vocab: int = 28996):
+        shape, dtype, ncls, _ = DATASET_SHAPES[data_name.upper()]
+        labels: List[int] = []
+        for lbl, cnt in enumerate(distribution):
+            labels += [lbl % ncls] * int(cnt)
+        g = torch.Generator().manual_seed(seed)
+        n = len(labels)
+        self.labels = torch.tensor(labels, dtype=torch.long)
+        if dtype == torch.long:
+            self.data = torch.randint(1, vocab, (n,) + shape, generator=g)
+            self.data[:, 0] = 101
+            self.data[:, 1] = 1000 + self.labels          # a learnable signal
+        else:
+            self.data = torch.randn((n,) + shape, generator=g)
+            self.data += (self.labels.float().view(-1, *([1] * len(shape))) - (ncls - 1) / 2) * 0.25
+        self.as_dict = dtype == torch.long
+
+    def __len__(self):
+        return self.labels.numel()
+
+    def __getitem__(self, i):
+        if self.as_dict:
+            return {"input_ids": self.data[i], "attention_mask": torch.ones_like(self.data[i]),
+                    "labels": self.labels[i]}
+        return self.data[i], self.labels[i]
+
+
+def synthetic_loader(data_name: str, batch_size: int, distribution: Sequence[int], train: bool = True,
+                     seed: int = 0) -> DataLoader:
+    ds = SyntheticDataset(data_name, distribution, seed=seed)
+    return DataLoader(ds, batch_size=batch_size, shuffle=train, drop_last=False)
+
+
+def _select_by_label(labels: Sequence[int], distribution: Sequence[int]) -> List[int]:
+    by_label = defaultdict(list)
+    for idx, l in enumerate(labels):
+        by_label[int(l)].append(idx)
+    picked: List[int] = []
+    for label, count in enumerate(distribution):
+        pool = by_label.get(label, [])
+        picked.extend(random.sample(pool, min(int(count), len(pool))))
+    return picked
+
+
+def _cifar10(batch_size, distribution, train, root="./data"):
+    import torchvision
+    import torchvision.transforms as T
+    norm = T.Normalize((0.4914, 0.4822, 0.4465), (0.2023, 0.1994, 0.2010))
+    if train:
+        tf = T.Compose([T.RandomCrop(32, padding=4), T.RandomHorizontalFlip(), T.ToTensor(), norm])
+        ds = torchvision.datasets.CIFAR10(root=root, train=True, download=False, transform=tf)
+        return DataLoader(Subset(ds, _select_by_label(ds.targets, distribution)), batch_size=batch_size, shuffle=True)
+    ds = torchvision.datasets.CIFAR10(root=root, train=False, download=False, transform=T.Compose([T.ToTensor(), norm]))
+    return DataLoader(ds, batch_size=100, shuffle=False, num_workers=1)
+
+
+def _mnist(batch_size, distribution, train, root="./data"):
+    import torchvision
+    import torchvision.transforms as T
+    tf = T.Compose([T.ToTensor(), T.Normalize((0.1307,), (0.3081,))])
+    ds = torchvision.datasets.MNIST(root=root, train=train, download=False, transform=tf)
+    if train:
+        return DataLoader(Subset(ds, _select_by_label(ds.targets.tolist(), distribution)), batch_size=batch_size, shuffle=True)
+    return DataLoader(ds, batch_size=100, shuffle=False)
+
+
+def _agnews(batch_size, distribution, train, root="./data"):
+    import pandas as pd
+    from transformers import BertTokenizer
+    from .text import TokenizedTextDataset
+    tok = BertTokenizer.from_pretrained("bert-base-cased")
+    df = pd.read_csv(os.path.join(root, "AGNEWS_TRAIN.csv" if train else "AGNEWS_TEST.csv"))
+    dist = distribution if train else [500, 500, 500, 500]
+    idx = _select_by_label(df["label"].tolist(), dist)
+    texts = [df["text"].iloc[i] for i in idx]
+    labels = [int(df["label"].iloc[i]) for i in idx]
+    ds = TokenizedTextDataset(texts, labels, tok, max_length=128)
+    return DataLoader(ds, batch_size=batch_size if train else 20, shuffle=train)
+
+
+def _speechcommands(batch_size, distribution, train, root="./data"):
+    from .speechcommands import CLASSES, SpeechCommandsDataset
+    ds = SpeechCommandsDataset(root=root, subset="training" if train else "testing")
+    if not train:
+        return DataLoader(ds, batch_size=20, shuffle=False)
+    if distribution is None:
+        return DataLoader(ds, batch_size=batch_size, shuffle=True)
+    labels = [CLASSES.index(name) for _, name in ds.samples]
+    return DataLoader(Subset(ds, _select_by_label(labels, distribution)), batch_size=batch_size, shuffle=True)
+
+
+_REAL = {"CIFAR10": _cifar10, "MNIST": _mnist, "AGNEWS": _agnews, "SPEECHCOMMANDS": _speechcommands}
+_PRESENT = {"CIFAR10": "cifar-10-batches-py", "MNIST": "MNIST", "AGNEWS": "AGNEWS_TRAIN.csv",
+            "SPEECHCOMMANDS": "SpeechCommands"}
+
+
+def real_data_available(data_name: str, root: str = "./data") -> bool:
+    marker = _PRESENT.get(data_name.upper())
+    return bool(marker) and os.path.exists(os.path.join(root, marker))
+
+
+def data_loader(data_name: Optional[str] = None, batch_size: Optional[int] = None,
+                distribution: Optional[Sequence[int]] = None, train: bool = True,
+                synthetic: Optional[bool] = None, root: str = "./data", seed: int = 0) -> DataLoader:
+    name = str(data_name).upper()
+    if name not in DATASET_SHAPES:
+        raise ValueError(f"Dataset {data_name} not supported.")
+    if synthetic is None:
+        synthetic = os.environ.get("SLB200_SYNTHETIC", "0") == "1" or not real_data_available(name, root)
+    if synthetic or name not in _REAL:
+        shape, dtype, ncls, test_bs = DATASET_SHAPES[name]
+        if distribution is None or len(distribution) == 0:
+            distribution = [max(1, (100 if not train else 500) // ncls)] * ncls
+        return synthetic_loader(name, batch_size if train else test_bs, distribution, train=train, seed=seed)
+    return _REAL[name](batch_size, distribution, train, root)

@@ -1,0 +1,166 @@
+"""Stage executors.
+
+``StageExecutor`` is the contract between the trainer loops and whatever runs a stage:
+  * ``TorchExecutor``  — reference math through ``torch.nn``/autograd on any device.  Used on
+    CPU (tests, plumbing config #1), for model families that do not yet have a native
+    plan, and as the numerics oracle.
+  * ``B200Executor``   — (``b200_executor.py``) VGG-family stages compiled to hand-written
+    sm_100a kernels + CUDA graphs; selected automatically on CUDA.
+
+Reference semantics preserved:
+  * non-last stages *recompute* the forward with current weights when the gradient comes
+    back (src/train/VGG16.py:89-92) unless ``recompute=False`` (activation stashing);
+  * one optimizer step per microbatch; SGD(lr, momentum) for VGG-like CNNs
+    (src/train/VGG16.py:62,139), AdamW(lr, weight-decay) for BERT/KWT/ViT
+    (src/train/BERT.py:69, src/train/KWT.py:62);
+  * optional ``clip-grad-norm`` on the last stage (other/Vanilla_SL/src/Scheduler.py:204-205).
+The NaN check is kept on-device and read once per epoch (reference reads ``loss.item()``
+every step, quirk C7).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from ..models import SplitModel
+
+_ADAMW_MODELS = ("BERT", "KWT", "VIT")
+
+
+def make_optimizer(model: nn.Module, model_name: str, learning: dict) -> torch.optim.Optimizer:
+    params = [p for p in model.parameters() if p.requires_grad]
+    lr = float(learning.get("learning-rate", 0.01))
+    if model_name.upper() in _ADAMW_MODELS:
+        return torch.optim.AdamW(params, lr=lr, weight_decay=float(learning.get("weight-decay", 0.01)))
+    return torch.optim.SGD(params, lr=lr, momentum=float(learning.get("momentum", 0.0)))
+
+
+class StageExecutor:
+    """Interface; see module docstring."""
+
+    device: Any
+    is_first: bool
+    is_last: bool
+
+    def forward_only(self, data_id, x) -> torch.Tensor: ...
+    def backward(self, data_id, grad) -> Optional[torch.Tensor]: ...
+    def forward_backward_last(self, x, labels) -> torch.Tensor: ...
+    def state_dict(self) -> Dict[str, torch.Tensor]: ...
+    def load_state_dict(self, sd) -> None: ...
+    def nan_detected(self) -> bool: ...
+    def in_flight(self) -> int: ...
+    def last_loss(self) -> Optional[float]: ...
+
+
+class TorchExecutor(StageExecutor):
+    def __init__(self, model: SplitModel, model_name: str, learning: dict, device="cpu", is_first=False,
+                 is_last=False, recompute: bool = True, clip_grad_norm: float = 0.0):
+        self.model = model.to(device)
+        self.model_name = model_name
+        self.device = device
+        self.is_first, self.is_last = is_first, is_last
+        self.recompute = recompute
+        self.clip = float(clip_grad_norm or 0.0)
+        self.opt = make_optimizer(self.model, model_name, learning)
+        self.criterion = nn.CrossEntropyLoss()
+        self._store: Dict[Any, Any] = {}
+        self._nan = torch.zeros((), dtype=torch.bool, device=device)
+        self._loss = None
+        self.model.train()
+
+    # -- helpers -------------------------------------------------------------
+    def _call(self, x):
+        if isinstance(x, dict):
+            return self.model(input_ids=x["input_ids"]) if self.is_first else self.model(x)
+        if self.model_name.upper() == "BERT" and self.is_first:
+            return self.model(input_ids=x)
+        return self.model(x)
+
+    def _prep_input(self, x):
+        if isinstance(x, dict):
+            return {k: v.to(self.device) for k, v in x.items() if k != "labels"}
+        x = x.to(self.device)
+        if not self.is_first and x.is_floating_point():
+            x = x.float().detach().requires_grad_(True)
+        return x
+
+    # -- StageExecutor -----------------------------------------------------------
+    def forward_only(self, data_id, x) -> torch.Tensor:
+        self.model.train()
+        x = self._prep_input(x)
+        if self.recompute:
+            with torch.no_grad():
+                out = self._call(x)
+            self._store[data_id] = (x, None)
+        else:
+            out = self._call(x)
+            self._store[data_id] = (x, out)
+        return out.detach()
+
+    def backward(self, data_id, grad) -> Optional[torch.Tensor]:
+        self.model.train()
+        x, out = self._store.pop(data_id)
+        self.opt.zero_grad(set_to_none=True)
+        if out is None:                       # faithful mode: recompute with *current* weights
+            out = self._call(x)
+        out.backward(gradient=grad.to(self.device).to(out.dtype))
+        self.opt.step()
+        if isinstance(x, torch.Tensor) and x.requires_grad:
+            return x.grad
+        return None
+
+    def forward_backward_last(self, x, labels) -> Optional[torch.Tensor]:
+        self.model.train()
+        x = self._prep_input(x)
+        labels = labels.to(self.device)
+        self.opt.zero_grad(set_to_none=True)
+        out = self._call(x)
+        loss = self.criterion(out, labels)
+        self._nan |= torch.isnan(loss.detach())
+        self._loss = loss.detach()
+        loss.backward()
+        if self.clip > 0:
+            nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
+        self.opt.step()
+        if isinstance(x, torch.Tensor) and x.requires_grad:
+            return x.grad
+        return None
+
+    def state_dict(self):
+        return {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+
+    def load_state_dict(self, sd):
+        self.model.load_state_dict(sd)
+
+    def nan_detected(self) -> bool:
+        return bool(self._nan.item())
+
+    def reset_epoch(self):
+        self._nan.zero_()
+        self._store.clear()
+
+    def in_flight(self) -> int:
+        return len(self._store)
+
+    def last_loss(self):
+        return None if self._loss is None else float(self._loss.item())
+
+
+def make_executor(model: SplitModel, model_name: str, learning: dict, device, is_first: bool, is_last: bool,
+                  b200_opts: Optional[dict] = None) -> StageExecutor:
+    """Pick the executor: native sm_100a plan on CUDA for supported tables, torch otherwise."""
+    opts = b200_opts or {}
+    kind = opts.get("executor", "auto")
+    dev = torch.device(device)
+    clip = float(learning.get("clip-grad-norm", 0.0) or 0.0) if is_last else 0.0
+    if kind in ("auto", "b200") and dev.type == "cuda":
+        from .b200_executor import B200Executor, supports
+        if supports(model):
+            return B200Executor(model, model_name, learning, device=dev, is_first=is_first, is_last=is_last,
+                                recompute=bool(opts.get("recompute", True)))
+        if kind == "b200":
+            raise RuntimeError(f"no native sm_100a plan for {type(model).__name__}")
+    return TorchExecutor(model, model_name, learning, device=dev, is_first=is_first, is_last=is_last,
+                         recompute=bool(opts.get("recompute", True)), clip_grad_norm=clip)

@@ -1,0 +1,59 @@
+import glob
+
+import pytest
+import yaml
+
+from split_learning_b200.config import load_config, normalize
+from split_learning_b200.plan import rank_assignment, resolve_range, stage_layers
+
+
+@pytest.mark.parametrize("path", ["/root/reference/config.yaml"] + sorted(glob.glob("/root/reference/other/*/config.yaml")))
+def test_reference_configs_load_and_roundtrip(path):
+    cfg = load_config(path)
+    again = normalize(cfg.to_dict())
+    assert again.to_dict() == cfg.to_dict()
+    assert cfg.learning["batch-size"] > 0 and "control-count" in cfg.learning
+
+
+def test_variant_keys():
+    flex = load_config("/root/reference/other/FLEX/config.yaml")
+    assert flex.cluster_mode and flex.num_cluster == 3 and flex.cluster_cut_layers == [[7], [7], [4]]
+    assert (flex.t_g, flex.t_c, flex.select_ratio) == (4, 2, 0.5)
+    two = load_config("/root/reference/other/2LS/config.yaml")
+    assert two.cluster_cut_layers == [[2]] * 3 and two.infor_cluster == [[2, 1]] * 3 and two.warnings
+    dcsl = load_config("/root/reference/other/DCSL/config.yaml")
+    assert dcsl.local_round == 1 and dcsl.no_cluster_cut_layers == [7]
+    van = load_config("/root/reference/other/Vanilla_SL/config.yaml")
+    assert van.limited_time == {"enable": False, "epoch": 10, "time": 10.0}
+    assert van.learning["clip-grad-norm"] == 0.0
+
+
+def test_readme_era_schema():
+    raw = {"server": {"clients": [2, 2], "no-cluster": {"cut-layers": [14]}, "model": "VGG16",
+                      "data-distribution": {"non-iid": True, "non-iid-rate": 0.5, "num-sample": 100, "num-label": 10}},
+           "learning": {"batch-size": 8}}
+    cfg = normalize(raw)
+    assert cfg.no_cluster_cut_layers == [14] and cfg.non_iid_rate == 0.5
+    assert cfg.learning["control-count"] == 3          # defaults filled in
+
+
+def test_validation_errors():
+    with pytest.raises(ValueError):
+        normalize({"server": {"clients": [1, 1, 1], "manual": {"cluster-mode": False, "no-cluster": {"cut-layers": [7]}}}})
+    with pytest.raises(ValueError):
+        normalize({"server": {"clients": [1, 1, 1], "manual": {"cluster-mode": False, "no-cluster": {"cut-layers": [10, 5]}}}})
+
+
+def test_stage_layers_matches_reference_arithmetic():
+    # src/Server.py:222-228
+    assert stage_layers(1, 2, [7]) == [0, 7]
+    assert stage_layers(2, 2, [7]) == [7, -1]
+    assert [stage_layers(i, 3, [5, 10]) for i in (1, 2, 3)] == [[0, 5], [5, 10], [10, -1]]
+    assert resolve_range([0, 0], 52) == (0, 52)
+    assert resolve_range([7, -1], 52) == (7, 52)
+
+
+def test_rank_assignment():
+    assert rank_assignment([1, 1]) == [(1, 0, 0), (2, 0, 0)]
+    r = rank_assignment([4, 4], [[2, 2], [2, 2]])
+    assert len(r) == 8 and r[0] == (1, 0, 0) and r[2] == (2, 0, 0) and r[4] == (1, 1, 0)

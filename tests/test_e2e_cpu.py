@@ -1,0 +1,119 @@
+"""BASELINE config #1: VGG16/CIFAR10 2-layer split cut=[7], 1 client/layer, CPU world_size=2
+— the full REGISTER→START→READY→SYN→NOTIFY→PAUSE→UPDATE→STOP cycle with no GPU."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+import yaml
+
+from split_learning_b200.checkpoint import load_checkpoint
+from split_learning_b200.config import normalize
+from split_learning_b200.models import VGG16_CIFAR10
+from split_learning_b200.runner import run_inproc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _raw(tmp, clients=(1, 1), cut=(7,), rounds=1, samples=64, **server):
+    raw = yaml.safe_load(open("/root/reference/config.yaml")) if os.path.exists("/root/reference/config.yaml") \
+        else yaml.safe_load(open(os.path.join(ROOT, "config.yaml")))
+    raw["server"].update({"clients": list(clients), "global-round": rounds, "validation": True})
+    raw["server"]["manual"]["no-cluster"]["cut-layers"] = list(cut)
+    raw["server"]["data-distribution"]["num-sample"] = samples
+    raw["server"].update(server)
+    raw["log_path"] = str(tmp)
+    raw["learning"]["batch-size"] = 8
+    raw["b200"] = {"synthetic-data": True, "watchdog-seconds": 60}
+    return raw
+
+
+def test_two_stage_inproc(tmp_path):
+    srv = run_inproc(normalize(_raw(tmp_path, rounds=2)), workdir=str(tmp_path), timeout=300)
+    assert [h["ok"] for h in srv.history] == [True, True]
+    assert srv.topology.cut_layers() == [[7]] and srv.topology.infor_cluster() == [[1, 1]]
+    sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    m = VGG16_CIFAR10()
+    m.load_state_dict(sd)                       # flat full-model layout, 97 entries
+    assert len(sd) == 97
+    # BN counters advanced: stage 1 recomputes forward (2 per microbatch), stage 2 once
+    nb = 6 * 8 // 8 if False else None
+    assert sd["layer2.num_batches_tracked"].item() == 2 * sd["layer9.num_batches_tracked"].item() > 0
+
+
+def test_three_stage_two_first_clients(tmp_path):
+    srv = run_inproc(normalize(_raw(tmp_path, clients=(2, 1, 1), cut=(5, 10))), workdir=str(tmp_path), timeout=300)
+    assert srv.history[0]["ok"] and srv.topology.infor_cluster() == [[2, 1, 1]]
+    assert len(load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))) == 97
+
+
+def test_cluster_mode(tmp_path):
+    raw = _raw(tmp_path, clients=(2, 2))
+    raw["server"]["manual"] = {"cluster-mode": True, "no-cluster": {"cut-layers": [7]},
+                               "cluster": {"num-cluster": 2, "cut-layers": [[7], [14]], "infor-cluster": [[1, 1], [1, 1]]}}
+    srv = run_inproc(normalize(raw), workdir=str(tmp_path), timeout=300)
+    assert srv.history[0]["ok"] and srv.topology.cut_layers() == [[7], [14]]
+    assert len(load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))) == 97
+
+
+def test_resume_from_checkpoint(tmp_path):
+    run_inproc(normalize(_raw(tmp_path)), workdir=str(tmp_path), timeout=300)
+    first = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    raw = _raw(tmp_path)
+    raw["learning"]["learning-rate"] = 0.0         # resumed weights must come back unchanged
+    raw["learning"]["momentum"] = 0.0
+    run_inproc(normalize(raw), workdir=str(tmp_path), timeout=300)
+    second = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    assert torch.equal(first["layer52.weight"], second["layer52.weight"])
+    assert torch.equal(first["layer1.weight"], second["layer1.weight"])
+
+
+def test_watchdog_instead_of_deadlock(tmp_path):
+    """Kill-a-stage fault test: with no last stage the first stage must time out, not hang."""
+    from split_learning_b200.client import RpcClient
+    from split_learning_b200.server import Server
+    from split_learning_b200.transport import InProcBroker
+    import threading
+    raw = _raw(tmp_path)
+    raw["b200"]["watchdog-seconds"] = 1.0
+    cfg = normalize(raw)
+    broker = InProcBroker()
+    srv = Server(cfg, broker, workdir=str(tmp_path))
+    threading.Thread(target=lambda: srv.start(idle_timeout=20), daemon=True).start()
+    ghost = RpcClient("ghost", 2, broker, b200_opts=cfg.b200)
+    ghost.register({"speed": 1})                  # registers, then never serves its queue
+
+    def ghost_ack():                              # acknowledges START so SYN is released, then dies
+        m = broker.get_obj("reply_ghost", 20)
+        ghost.on_start(m)
+    threading.Thread(target=ghost_ack, daemon=True).start()
+    c1 = RpcClient("c1", 1, broker, b200_opts=cfg.b200)
+    c1.register({"speed": 1})
+    with pytest.raises(TimeoutError):
+        c1.wait_response(idle_timeout=30)
+    srv.done = True
+
+
+@pytest.mark.slow
+def test_world_size_2_processes_tcp(tmp_path):
+    """One OS process per role over the loopback TCP broker (server.py / client.py CLIs)."""
+    cfg_path = tmp_path / "config.yaml"
+    raw = _raw(tmp_path)
+    raw["b200"]["port"] = 29911
+    yaml.safe_dump(raw, open(cfg_path, "w"))
+    env = dict(os.environ, PYTHONPATH=ROOT, SLB200_QUIET="1")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "server.py"), "--config", str(cfg_path)],
+                              cwd=tmp_path, env=env)]
+    for layer in (1, 2):
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "client.py"), "--layer_id", str(layer),
+                                       "--device", "cpu", "--config", str(cfg_path)], cwd=tmp_path, env=env))
+    try:
+        for p in procs:
+            assert p.wait(timeout=300) == 0
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    assert (tmp_path / "VGG16_CIFAR10.pth").exists()
