@@ -1,0 +1,752 @@
+// Memory-bound kernels of the VGG-family stages:
+// BatchNorm(train)+ReLU+MaxPool forward/backward on NHWC bf16, the first-layer direct conv
+// (Cin <= 4), Linear finalisation (bias/ReLU/dropout), fused CE forward+backward, fused
+// flat optimisers (SGD-momentum, AdamW), the FedAvg weighted n-ary reduction over (peer)
+// pointers, and the mailbox flag primitives.  All vectorised to 16-byte accesses.
+#include "sm100.cuh"
+
+namespace slb {
+
+struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+// "last block done" publication of a mailbox flag: every block fences its (possibly peer) stores,
+// the last one to arrive releases the flag system-wide and re-arms the ticket counter.
+// The flag value is a per-slot sequence number kept in device memory (`seq`), so the same
+// captured CUDA graph publishes 1, 2, 3, ... on successive replays.
+__device__ __forceinline__ void publish_flag(uint32_t* ticket, uint32_t* flag, uint32_t* seq, uint32_t* hint) {
+  if (flag == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    __threadfence_system();
+    const uint32_t t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x * gridDim.y - 1) {
+      *ticket = 0;
+      const uint32_t value = *seq + 1;
+      *seq = value;
+      __threadfence_system();
+      st_release_sys(flag, value);
+      if (hint != nullptr) st_release_sys(hint, value);
+    }
+  }
+}
+
+// ============================================================================ zero / flags
+__global__ void zero_kernel(float4* p, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Spin until *flag >= expected (acquire, system scope).  `expect_ctr` (nullable): device counter; the
+// kernel waits for *expect_ctr + 1 and stores it back (graph-replay friendly).  `status` (nullable)
+// receives 1 on timeout so a dead producer turns into an error instead of a hung GPU.
+__global__ void wait_flag_kernel(const uint32_t* flag, uint32_t expected, uint32_t* expect_ctr, unsigned long long max_spins,
+                                 int* status) {
+  if (expect_ctr) expected = *expect_ctr + 1;
+  unsigned long long spins = 0;
+  while (ld_acquire_sys(flag) < expected) {
+    __nanosleep(64);
+    if (++spins > max_spins) {
+      if (status) *status = 1;
+      return;
+    }
+  }
+  if (expect_ctr) *expect_ctr = expected;
+}
+__global__ void set_flag_kernel(uint32_t* flag, uint32_t value, uint32_t* seq, uint32_t* hint) {
+  if (seq) { value = *seq + 1; *seq = value; }
+  __threadfence_system();
+  st_release_sys(flag, value);
+  if (hint) st_release_sys(hint, value);
+}
+__global__ void counter_inc_kernel(uint32_t* c) { *c += 1; }
+
+// ============================================================================ BN + ReLU + MaxPool forward
+struct BnFwdParams {
+  const __nv_bfloat16* y;   // [P][C] conv output (pre-BN)
+  const float* sum;         // [C]
+  const float* sumsq;       // [C]
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked;
+  float* save_mean;         // [C]
+  float* save_invstd;       // [C]
+  __nv_bfloat16* out;       // [P or P/4][C]   (may be a peer pointer: cut-edge mailbox slot)
+  int P, C, H, W;
+  int relu, pool;
+  float momentum, eps;
+  int update_running;
+  int identity;             // 1: no normalisation (orphan ReLU/MaxPool at the head of a stage)
+  uint32_t* ticket;
+  uint32_t* flag;
+  uint32_t* seq;
+  uint32_t* hint;
+};
+
+__global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const BnFwdParams p) {
+  extern __shared__ float s_aff[];     // scale[C], shift[C]
+  float* s_scale = s_aff;
+  float* s_shift = s_aff + p.C;
+  const float invP = 1.f / static_cast<float>(p.P);
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    if (p.identity) { s_scale[c] = 1.f; s_shift[c] = 0.f; continue; }
+    const float mean = p.sum[c] * invP;
+    const float var = fmaxf(p.sumsq[c] * invP - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + p.eps);
+    const float g = p.gamma[c];
+    s_scale[c] = g * invstd;
+    s_shift[c] = p.beta[c] - mean * g * invstd;
+    if (blockIdx.x == 0) {
+      p.save_mean[c] = mean;
+      p.save_invstd[c] = invstd;
+      if (p.update_running) {
+        const float unbiased = p.P > 1 ? var * static_cast<float>(p.P) / static_cast<float>(p.P - 1) : var;
+        p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
+        p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * unbiased;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.update_running && !p.identity && p.num_batches_tracked) *p.num_batches_tracked += 1;
+  __syncthreads();
+
+  const int cg = p.C >> 3;                                  // 8-channel groups
+  const int OW = p.pool ? p.W >> 1 : p.W, OH = p.pool ? p.H >> 1 : p.H;
+  const long long outP = p.pool ? static_cast<long long>(p.P) >> 2 : p.P;
+  const long long total = outP * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    const long long op = i / cg;
+    float sc[8], sh[8], r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = s_scale[g * 8 + j]; sh[j] = s_shift[g * 8 + j]; }
+    if (!p.pool) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(p.y + op * p.C + g * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(f[j], sc[j], sh[j]);
+        r[j] = p.relu ? fmaxf(z, 0.f) : z;
+      }
+    } else {
+      const int ow = static_cast<int>(op % OW);
+      const long long t = op / OW;
+      const int oh = static_cast<int>(t % OH);
+      const long long b = t / OH;
+      const long long base = ((b * p.H + 2 * oh) * p.W + 2 * ow);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long ip = base + (q >> 1) * p.W + (q & 1);
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(p.y + ip * p.C + g * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float z = fmaf(f[j], sc[j], sh[j]);
+          if (p.relu) z = fmaxf(z, 0.f);
+          r[j] = fmaxf(r[j], z);
+        }
+      }
+    }
+    *reinterpret_cast<bf16x8*>(p.out + op * p.C + g * 8) = pack8(r);
+  }
+  publish_flag(p.ticket, p.flag, p.seq, p.hint);
+}
+
+// ============================================================================ BN + ReLU + MaxPool backward
+struct BnBwdParams {
+  const __nv_bfloat16* dout;   // [P or P/4][C] gradient w.r.t. the (pooled) activation  (may be a mailbox slot)
+  const __nv_bfloat16* y;      // [P][C] saved conv output
+  const float* gamma;
+  const float* beta;
+  const float* save_mean;
+  const float* save_invstd;
+  float* dgamma;               // [C] (zeroed by caller; accumulated)
+  float* dbeta;                // [C]
+  __nv_bfloat16* dy;           // [P][C] gradient w.r.t. conv output
+  int P, C, H, W;
+  int relu, pool;
+  int identity;
+};
+
+// dz for the 1 (no pool) or 4 (pool) input pixels of output position `op`, 8 channels.
+template <bool POOL>
+__device__ __forceinline__ void bn_dz(const BnBwdParams& p, long long op, int g, const float (&sc)[8], const float (&sh)[8],
+                                      float (&yv)[POOL ? 4 : 1][8], float (&dz)[POOL ? 4 : 1][8], long long (&ip)[POOL ? 4 : 1]) {
+  float d[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(p.dout + op * p.C + g * 8), d);
+  if constexpr (!POOL) {
+    ip[0] = op;
+    unpack8(*reinterpret_cast<const bf16x8*>(p.y + op * p.C + g * 8), yv[0]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(yv[0][j], sc[j], sh[j]);
+      dz[0][j] = (p.relu && z <= 0.f) ? 0.f : d[j];
+    }
+  } else {
+    const int OW = p.W >> 1, OH = p.H >> 1;
+    const int ow = static_cast<int>(op % OW);
+    const long long t = op / OW;
+    const int oh = static_cast<int>(t % OH);
+    const long long b = t / OH;
+    const long long base = ((b * p.H + 2 * oh) * p.W + 2 * ow);
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ip[q] = base + (q >> 1) * p.W + (q & 1);
+      unpack8(*reinterpret_cast<const bf16x8*>(p.y + ip[q] * p.C + g * 8), yv[q]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float z = fmaf(yv[q][j], sc[j], sh[j]);
+        if (p.relu) z = fmaxf(z, 0.f);
+        if (z > best[j]) { best[j] = z; arg[j] = q; }   // first maximum wins, like torch
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dz[q][j] = (arg[j] == q && !(p.relu && best[j] <= 0.f)) ? d[j] : 0.f;
+  }
+}
+
+// pass 1: dgamma / dbeta.  blockDim = (C/8, 256/(C/8)); grid-stride over output positions.
+template <bool POOL>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
+  constexpr int NP = POOL ? 4 : 1;
+  const int g = threadIdx.x;
+  float sc[8], sh[8], mean[8], istd[8], ag[8], ab[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    mean[j] = p.save_mean[c];
+    istd[j] = p.save_invstd[c];
+    sc[j] = p.gamma[c] * istd[j];
+    sh[j] = p.beta[c] - mean[j] * sc[j];
+    ag[j] = ab[j] = 0.f;
+  }
+  const long long outP = POOL ? static_cast<long long>(p.P) >> 2 : p.P;
+  for (long long op = blockIdx.x * (long long)blockDim.y + threadIdx.y; op < outP; op += (long long)gridDim.x * blockDim.y) {
+    float yv[NP][8], dz[NP][8];
+    long long ip[NP];
+    bn_dz<POOL>(p, op, g, sc, sh, yv, dz, ip);
+#pragma unroll
+    for (int q = 0; q < NP; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ab[j] += dz[q][j];
+        ag[j] += dz[q][j] * (yv[q][j] - mean[j]) * istd[j];
+      }
+  }
+  extern __shared__ float s_red[];            // [2][C]
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * p.C; i += blockDim.x * blockDim.y) s_red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_red[g * 8 + j], ag[j]);
+    atomicAdd(&s_red[p.C + g * 8 + j], ab[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < p.C; i += blockDim.x * blockDim.y) {
+    atomicAdd(p.dgamma + i, s_red[i]);
+    atomicAdd(p.dbeta + i, s_red[p.C + i]);
+  }
+}
+
+// pass 2: dy = gamma*invstd*(dz - dbeta/P - xhat*dgamma/P)
+template <bool POOL>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
+  constexpr int NP = POOL ? 4 : 1;
+  const int g = threadIdx.x;
+  const float invP = 1.f / static_cast<float>(p.P);
+  float sc[8], sh[8], mean[8], istd[8], k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    if (p.identity) { mean[j] = 0.f; istd[j] = 1.f; sc[j] = 1.f; sh[j] = 0.f; k1[j] = 0.f; k2[j] = 0.f; continue; }
+    mean[j] = p.save_mean[c];
+    istd[j] = p.save_invstd[c];
+    sc[j] = p.gamma[c] * istd[j];
+    sh[j] = p.beta[c] - mean[j] * sc[j];
+    k1[j] = p.dbeta[c] * invP;
+    k2[j] = p.dgamma[c] * invP;
+  }
+  const long long outP = POOL ? static_cast<long long>(p.P) >> 2 : p.P;
+  for (long long op = blockIdx.x * (long long)blockDim.y + threadIdx.y; op < outP; op += (long long)gridDim.x * blockDim.y) {
+    float yv[NP][8], dz[NP][8];
+    long long ip[NP];
+    bn_dz<POOL>(p, op, g, sc, sh, yv, dz, ip);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = (yv[q][j] - mean[j]) * istd[j];
+        r[j] = sc[j] * (dz[q][j] - k1[j] - xhat * k2[j]);
+      }
+      *reinterpret_cast<bf16x8*>(p.dy + ip[q] * p.C + g * 8) = pack8(r);
+    }
+  }
+}
+
+// Column sums / sums of squares of a bf16 [P][C] matrix (BN statistics fallback, bias gradients).
+__global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* y, float* sum, float* sumsq, long long P, int C) {
+  const int g = threadIdx.x;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  for (long long r = blockIdx.x * (long long)blockDim.y + threadIdx.y; r < P; r += (long long)gridDim.x * blockDim.y) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(y + r * C + g * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] += f[j]; b[j] += f[j] * f[j]; }
+  }
+  extern __shared__ float s_red[];
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * C; i += blockDim.x * blockDim.y) s_red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_red[g * 8 + j], a[j]);
+    atomicAdd(&s_red[C + g * 8 + j], b[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < C; i += blockDim.x * blockDim.y) {
+    atomicAdd(sum + i, s_red[i]);
+    if (sumsq) atomicAdd(sumsq + i, s_red[C + i]);
+  }
+}
+
+// ============================================================================ first-layer direct conv (Cin <= 4)
+// x: fp32 NCHW [B][Cin][H][W]; w: fp32 [Cout][3][3][Cin]; y: bf16 NHWC [B][H][W][Cout] (pre-BN) + BN statistics.
+template <int CIN>
+__global__ void __launch_bounds__(256) conv3x3_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, __nv_bfloat16* y,
+                                                               float* sum, float* sumsq, int B, int H, int W, int Cout) {
+  extern __shared__ float s_w[];                 // [Cout][9*CIN] + bias[Cout] + stats[2*Cout]
+  float* s_b = s_w + Cout * 9 * CIN;
+  float* s_st = s_b + Cout;
+  for (int i = threadIdx.x; i < Cout * 9 * CIN; i += blockDim.x) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) { s_b[i] = bias ? bias[i] : 0.f; s_st[i] = 0.f; s_st[Cout + i] = 0.f; }
+  __syncthreads();
+  const int groups = Cout >> 4;                  // 16 output channels per thread
+  const long long total = (long long)B * H * W * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    const long long pix = i / groups;
+    const int ww = static_cast<int>(pix % W);
+    const int hh = static_cast<int>((pix / W) % H);
+    const long long b = pix / ((long long)W * H);
+    float patch[9 * CIN];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int ih = hh + t / 3 - 1, iw = ww + t % 3 - 1;
+      const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) patch[t * CIN + c] = ok ? __ldg(x + ((b * CIN + c) * H + ih) * W + iw) : 0.f;
+    }
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+      const float* wr = s_w + (g * 16 + o) * 9 * CIN;
+      float a = s_b[g * 16 + o];
+#pragma unroll
+      for (int k = 0; k < 9 * CIN; ++k) a = fmaf(patch[k], wr[k], a);
+      acc[o] = a;
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(y + pix * Cout + g * 16);
+    o4[0] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+    o4[1] = make_uint4(pack_bf16x2(acc[8], acc[9]), pack_bf16x2(acc[10], acc[11]), pack_bf16x2(acc[12], acc[13]), pack_bf16x2(acc[14], acc[15]));
+    if (sum) {
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        const float r = __bfloat162float(__float2bfloat16(acc[o]));
+        atomicAdd(&s_st[g * 16 + o], r);
+        atomicAdd(&s_st[Cout + g * 16 + o], r * r);
+      }
+    }
+  }
+  if (sum) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) {
+      atomicAdd(sum + i, s_st[i]);
+      atomicAdd(sumsq + i, s_st[Cout + i]);
+    }
+  }
+}
+
+// dw[Cout][9*CIN] += sum_pix dy[pix][Cout] * patch[pix][9*CIN]    (block = 128 pixels)
+template <int CIN>
+__global__ void __launch_bounds__(256) conv3x3_small_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                                 float* dw, int B, int H, int W, int Cout) {
+  constexpr int KK = 9 * CIN;
+  extern __shared__ float s_buf[];               // patch[128][KK] + dy[128][Cout]
+  float* s_patch = s_buf;
+  float* s_dy = s_buf + 128 * KK;
+  const long long P = (long long)B * H * W;
+  const long long pix0 = blockIdx.x * 128LL;
+  for (int i = threadIdx.x; i < 128 * KK; i += blockDim.x) {
+    const int lp = i / KK, k = i - lp * KK;
+    const long long pix = pix0 + lp;
+    float v = 0.f;
+    if (pix < P) {
+      const int t = k / CIN, c = k - t * CIN;
+      const int ww = static_cast<int>(pix % W), hh = static_cast<int>((pix / W) % H);
+      const long long b = pix / ((long long)W * H);
+      const int ih = hh + t / 3 - 1, iw = ww + t % 3 - 1;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[((b * CIN + c) * H + ih) * W + iw];
+    }
+    s_patch[i] = v;
+  }
+  for (int i = threadIdx.x; i < 128 * Cout; i += blockDim.x) {
+    const long long pix = pix0 + i / Cout;
+    s_dy[i] = pix < P ? __bfloat162float(dy[pix * Cout + (i % Cout)]) : 0.f;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < Cout * KK; o += blockDim.x) {
+    const int co = o / KK, k = o - co * KK;
+    float a = 0.f;
+#pragma unroll 8
+    for (int lp = 0; lp < 128; ++lp) a = fmaf(s_dy[lp * Cout + co], s_patch[lp * KK + k], a);
+    atomicAdd(dw + o, a);
+  }
+}
+
+// ============================================================================ Linear finalisation
+__device__ __forceinline__ uint32_t hash_u32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return h;
+}
+// out[b][n] = dropout(relu(acc[b][n] + bias[n]))  -> bf16 (ld = ldo) ; also keeps fp32 logits when out_f32 != null
+__global__ void linear_finalize_kernel(const float* acc, const float* bias, __nv_bfloat16* out, float* out_f32, uint8_t* mask,
+                                       int B, int N, int ldo, int relu, float drop_p, uint32_t seed, const uint32_t* step_ptr) {
+  const uint32_t step = step_ptr ? *step_ptr : 0u;
+  const long long total = (long long)B * N;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t thresh = static_cast<uint32_t>(drop_p * 4294967296.0);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = static_cast<int>(i % N), b = static_cast<int>(i / N);
+    float v = acc[i] + (bias ? bias[n] : 0.f);
+    if (relu) v = fmaxf(v, 0.f);
+    if (drop_p > 0.f) {
+      const bool keep = hash_u32(seed, step, static_cast<uint32_t>(i)) >= thresh;
+      mask[i] = keep ? 1 : 0;
+      v = keep ? v * keep_scale : 0.f;
+    }
+    if (out) out[(long long)b * ldo + n] = __float2bfloat16(v);
+    if (out_f32) out_f32[i] = v;
+  }
+}
+// dz[b][n] = dy[b][n] * dropmask * (relu ? y>0 : 1)  (bf16, ld = ldz) ; db[n] = sum_b dz[b][n] (bf16-rounded values)
+__global__ void linear_bwd_prep_kernel(const float* dacc, const __nv_bfloat16* yout, const uint8_t* mask, __nv_bfloat16* dz,
+                                       float* dbias, int B, int N, int ldy, int ldz, int relu, float drop_p) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float g = dacc[(long long)b * N + n];
+    if (drop_p > 0.f) g = mask[(long long)b * N + n] ? g * keep_scale : 0.f;
+    if (relu && !(__bfloat162float(yout[(long long)b * ldy + n]) > 0.f)) g = 0.f;
+    const __nv_bfloat16 r = __float2bfloat16(g);
+    dz[(long long)b * ldz + n] = r;
+    s += __bfloat162float(r);
+  }
+  if (dbias) dbias[n] = s;
+}
+// bf16 dropout on a dense activation (VGG layer 46) and its backward
+__global__ void dropout_fwd_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* mask, long long n, float p, uint32_t seed,
+                                   const uint32_t* step_ptr) {
+  const uint32_t step = step_ptr ? *step_ptr : 0u;
+  const float ks = 1.f / (1.f - p);
+  const uint32_t thresh = static_cast<uint32_t>(p * 4294967296.0);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const bool keep = hash_u32(seed, step, static_cast<uint32_t>(i)) >= thresh;
+    mask[i] = keep ? 1 : 0;
+    y[i] = __float2bfloat16(keep ? __bfloat162float(x[i]) * ks : 0.f);
+  }
+}
+__global__ void dropout_bwd_kernel(const float* dacc, const uint8_t* mask, __nv_bfloat16* dx, long long n, float p) {
+  const float ks = 1.f / (1.f - p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = __float2bfloat16((mask == nullptr || mask[i]) ? dacc[i] * (mask ? ks : 1.f) : 0.f);
+}
+
+// ============================================================================ cross-entropy forward + backward
+// one warp per sample: loss_sum += -log softmax[label] / B; dlogits = (softmax - onehot) / B  (fp32, ld = ldd)
+__global__ void ce_fwd_bwd_kernel(const float* logits, const long long* labels, float* dlogits, float* loss_sum,
+                                  int* nan_flag, int B, int C, int ldd) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const float* row = logits + (long long)warp * C;
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = 0.f;
+  for (int c = lane; c < C; c += 32) se += __expf(row[c] - mx);
+  for (int o = 16; o; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+  const int lab = static_cast<int>(labels[warp]);
+  const float lse = mx + __logf(se);
+  const float invB = 1.f / static_cast<float>(B);
+  for (int c = lane; c < ldd; c += 32) {
+    float g = 0.f;
+    if (c < C) g = (__expf(row[c] - lse) - (c == lab ? 1.f : 0.f)) * invB;
+    dlogits[(long long)warp * ldd + c] = g;
+  }
+  if (lane == 0) {
+    const float loss = lse - row[lab];
+    atomicAdd(loss_sum, loss * invB);
+    if (loss != loss) *nan_flag = 1;
+  }
+}
+
+// ============================================================================ optimisers (flat)
+// v = mu*v + g ; p -= lr*v ; g = 0 ; optional bf16 shadow copy of p  (torch.optim.SGD, no dampening/nesterov/wd)
+__global__ void sgd_momentum_kernel(float4* p, float4* g, float4* m, uint2* p_bf16, long long n4, float lr, float mu, int first_step) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 gi = g[i];
+    float4 mi = m[i], pi = p[i];
+    if (first_step) { mi = gi; }            // torch initialises the buffer with the first gradient
+    else { mi.x = fmaf(mu, mi.x, gi.x); mi.y = fmaf(mu, mi.y, gi.y); mi.z = fmaf(mu, mi.z, gi.z); mi.w = fmaf(mu, mi.w, gi.w); }
+    pi.x -= lr * mi.x; pi.y -= lr * mi.y; pi.z -= lr * mi.z; pi.w -= lr * mi.w;
+    m[i] = mi;
+    p[i] = pi;
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p_bf16) p_bf16[i] = make_uint2(pack_bf16x2(pi.x, pi.y), pack_bf16x2(pi.z, pi.w));
+  }
+}
+__global__ void adamw_kernel(float4* p, float4* g, float4* m, float4* v, uint2* p_bf16, long long n4, float lr, float b1, float b2,
+                             float eps, float wd, float bc1, float bc2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 gi = g[i];
+    float4 mi = m[i], vi = v[i], pi = p[i];
+    float* pp = reinterpret_cast<float*>(&pi);
+    float* mm = reinterpret_cast<float*>(&mi);
+    float* vv = reinterpret_cast<float*>(&vi);
+    const float* gg = reinterpret_cast<const float*>(&gi);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      pp[k] *= (1.f - lr * wd);
+      mm[k] = b1 * mm[k] + (1.f - b1) * gg[k];
+      vv[k] = b2 * vv[k] + (1.f - b2) * gg[k] * gg[k];
+      pp[k] -= lr * (mm[k] / bc1) / (sqrtf(vv[k] / bc2) + eps);
+    }
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p_bf16) p_bf16[i] = make_uint2(pack_bf16x2(pi.x, pi.y), pack_bf16x2(pi.z, pi.w));
+  }
+}
+__global__ void cast_f32_bf16_kernel(const float4* x, uint2* y, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    y[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// ============================================================================ FedAvg n-ary weighted reduction
+// out[i] = sum_r coef[r] * nan_to_num(src[r][i]) ; src pointers may be peer (NVLink) addresses.  
+struct FedAvgParams {
+  const float* src[16];
+  float coef[16];
+  int nsrc;
+};
+__global__ void __launch_bounds__(512) fedavg_kernel(float4* out, uint2* out_bf16, const FedAvgParams p, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int r = 0; r < p.nsrc; ++r) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p.src[r]) + i);
+      const float c = p.coef[r];
+      acc.x += c * (v.x == v.x ? v.x : 0.f);
+      acc.y += c * (v.y == v.y ? v.y : 0.f);
+      acc.z += c * (v.z == v.z ? v.z : 0.f);
+      acc.w += c * (v.w == v.w ? v.w : 0.f);
+    }
+    out[i] = acc;
+    if (out_bf16) out_bf16[i] = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+  }
+}
+
+static inline int grid_for(long long work, int block, int max_blocks = 148 * 8) {
+  long long g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return static_cast<int>(g);
+}
+static inline int last_err() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -static_cast<int>(e) - 2000;
+}
+
+}  // namespace slb
+using namespace slb;
+
+extern "C" {
+
+int slb_zero(void* p, long long bytes, cudaStream_t st) {
+  if (bytes % 16) return -1;
+  zero_kernel<<<grid_for(bytes / 16, 256), 256, 0, st>>>(reinterpret_cast<float4*>(p), bytes / 16);
+  return last_err();
+}
+int slb_wait_flag(const uint32_t* flag, uint32_t expected, uint32_t* expect_ctr, unsigned long long max_spins, int* status,
+                  cudaStream_t st) {
+  wait_flag_kernel<<<1, 1, 0, st>>>(flag, expected, expect_ctr, max_spins, status);
+  return last_err();
+}
+int slb_set_flag(uint32_t* flag, uint32_t value, uint32_t* seq, uint32_t* hint, cudaStream_t st) {
+  set_flag_kernel<<<1, 1, 0, st>>>(flag, value, seq, hint);
+  return last_err();
+}
+int slb_counter_inc(uint32_t* c, cudaStream_t st) {
+  counter_inc_kernel<<<1, 1, 0, st>>>(c);
+  return last_err();
+}
+
+int slb_bn_relu_pool_fwd(const void* y, const float* sum, const float* sumsq, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, long long* nbt, float* save_mean, float* save_invstd,
+                         void* out, int P, int C, int H, int W, int relu, int pool, float momentum, float eps,
+                         int update_running, int identity, uint32_t* ticket, uint32_t* flag, uint32_t* seq, uint32_t* hint,
+                         cudaStream_t st) {
+  if (C % 8) return -1;
+  BnFwdParams p = {reinterpret_cast<const __nv_bfloat16*>(y), sum, sumsq, gamma, beta, running_mean, running_var, nbt,
+                   save_mean, save_invstd, reinterpret_cast<__nv_bfloat16*>(out), P, C, H, W, relu, pool, momentum, eps,
+                   update_running, identity, ticket, flag, seq, hint};
+  const long long work = (pool ? (long long)P / 4 : P) * (C / 8);
+  bn_relu_pool_fwd_kernel<<<grid_for(work, 256, 148 * 4), 256, 2 * C * sizeof(float), st>>>(p);
+  return last_err();
+}
+
+int slb_bn_relu_pool_bwd(const void* dout, const void* y, const float* gamma, const float* beta, const float* save_mean,
+                         const float* save_invstd, float* dgamma, float* dbeta, void* dy, int P, int C, int H, int W, int relu,
+                         int pool, int identity, cudaStream_t st) {
+  if (C % 8 || C > 2048) return -1;
+  BnBwdParams p = {reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(y), gamma, beta,
+                   save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dy), P, C, H, W, relu, pool, identity};
+  const int tx = C / 8;
+  const int ty = tx >= 256 ? 1 : 256 / tx;
+  dim3 block(tx, ty);
+  const long long outP = pool ? (long long)P / 4 : P;
+  const int grid = grid_for(outP, ty, 148 * 2);
+  if (pool) {
+    if (!identity) bn_bwd_reduce_kernel<true><<<grid, block, 2 * C * sizeof(float), st>>>(p);
+    bn_bwd_apply_kernel<true><<<grid, block, 0, st>>>(p);
+  } else {
+    if (!identity) bn_bwd_reduce_kernel<false><<<grid, block, 2 * C * sizeof(float), st>>>(p);
+    bn_bwd_apply_kernel<false><<<grid, block, 0, st>>>(p);
+  }
+  return last_err();
+}
+
+int slb_col_stats(const void* y, float* sum, float* sumsq, long long P, int C, cudaStream_t st) {
+  if (C % 8) return -1;
+  const int tx = C / 8, ty = tx >= 256 ? 1 : 256 / tx;
+  col_stats_kernel<<<grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(y), sum, sumsq, P, C);
+  return last_err();
+}
+
+int slb_conv3x3_small_fwd(const float* x, const float* w, const float* bias, void* y, float* sum, float* sumsq, int B, int Cin,
+                          int H, int W, int Cout, cudaStream_t st) {
+  if (Cout % 16) return -1;
+  const size_t smem = (size_t)(Cout * 9 * Cin + 3 * Cout) * sizeof(float);
+  const long long work = (long long)B * H * W * (Cout / 16);
+  const int grid = grid_for(work, 256, 148 * 4);
+  __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
+  if (Cin == 3) conv3x3_small_fwd_kernel<3><<<grid, 256, smem, st>>>(x, w, bias, yy, sum, sumsq, B, H, W, Cout);
+  else if (Cin == 1) conv3x3_small_fwd_kernel<1><<<grid, 256, smem, st>>>(x, w, bias, yy, sum, sumsq, B, H, W, Cout);
+  else return -2;
+  return last_err();
+}
+int slb_conv3x3_small_wgrad(const float* x, const void* dy, float* dw, int B, int Cin, int H, int W, int Cout, cudaStream_t st) {
+  const size_t smem = (size_t)(128 * 9 * Cin + 128 * Cout) * sizeof(float);
+  const int grid = static_cast<int>(((long long)B * H * W + 127) / 128);
+  const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(dy);
+  if (Cin == 3) {
+    static bool done3 = false;
+    if (!done3) { cudaFuncSetAttribute(conv3x3_small_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done3 = true; }
+    conv3x3_small_wgrad_kernel<3><<<grid, 256, smem, st>>>(x, d, dw, B, H, W, Cout);
+  } else if (Cin == 1) {
+    static bool done1 = false;
+    if (!done1) { cudaFuncSetAttribute(conv3x3_small_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done1 = true; }
+    conv3x3_small_wgrad_kernel<1><<<grid, 256, smem, st>>>(x, d, dw, B, H, W, Cout);
+  } else return -2;
+  return last_err();
+}
+
+int slb_linear_finalize(const float* acc, const float* bias, void* out, float* out_f32, uint8_t* mask, int B, int N, int ldo,
+                        int relu, float drop_p, uint32_t seed, const uint32_t* step_ptr, cudaStream_t st) {
+  linear_finalize_kernel<<<grid_for((long long)B * N, 256), 256, 0, st>>>(acc, bias, reinterpret_cast<__nv_bfloat16*>(out), out_f32,
+                                                                         mask, B, N, ldo, relu, drop_p, seed, step_ptr);
+  return last_err();
+}
+int slb_linear_bwd_prep(const float* dacc, const void* yout, const uint8_t* mask, void* dz, float* dbias, int B, int N, int ldy,
+                        int ldz, int relu, float drop_p, cudaStream_t st) {
+  linear_bwd_prep_kernel<<<(N + 127) / 128, 128, 0, st>>>(dacc, reinterpret_cast<const __nv_bfloat16*>(yout), mask,
+                                                         reinterpret_cast<__nv_bfloat16*>(dz), dbias, B, N, ldy, ldz, relu, drop_p);
+  return last_err();
+}
+int slb_dropout_fwd(const void* x, void* y, uint8_t* mask, long long n, float p, uint32_t seed, const uint32_t* step_ptr,
+                    cudaStream_t st) {
+  dropout_fwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+                                                      mask, n, p, seed, step_ptr);
+  return last_err();
+}
+int slb_dropout_bwd(const float* dacc, const uint8_t* mask, void* dx, long long n, float p, cudaStream_t st) {
+  dropout_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dacc, mask, reinterpret_cast<__nv_bfloat16*>(dx), n, p);
+  return last_err();
+}
+int slb_ce_fwd_bwd(const float* logits, const long long* labels, float* dlogits, float* loss_sum, int* nan_flag, int B, int C,
+                   int ldd, cudaStream_t st) {
+  ce_fwd_bwd_kernel<<<(B * 32 + 127) / 128, 128, 0, st>>>(logits, labels, dlogits, loss_sum, nan_flag, B, C, ldd);
+  return last_err();
+}
+int slb_sgd_momentum(float* p, float* g, float* m, void* p_bf16, long long n, float lr, float mu, int first_step, cudaStream_t st) {
+  if (n % 4) return -1;
+  sgd_momentum_kernel<<<grid_for(n / 4, 256, 148 * 16), 256, 0, st>>>(reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
+                                                                     reinterpret_cast<float4*>(m), reinterpret_cast<uint2*>(p_bf16),
+                                                                     n / 4, lr, mu, first_step);
+  return last_err();
+}
+int slb_adamw(float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float b1, float b2, float eps, float wd,
+              float bc1, float bc2, cudaStream_t st) {
+  if (n % 4) return -1;
+  adamw_kernel<<<grid_for(n / 4, 256, 148 * 16), 256, 0, st>>>(reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
+                                                              reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+                                                              reinterpret_cast<uint2*>(p_bf16), n / 4, lr, b1, b2, eps, wd, bc1, bc2);
+  return last_err();
+}
+int slb_cast_f32_bf16(const float* x, void* y, long long n, cudaStream_t st) {
+  if (n % 4) return -1;
+  cast_f32_bf16_kernel<<<grid_for(n / 4, 256, 148 * 16), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y), n / 4);
+  return last_err();
+}
+// srcs: host array of nsrc device pointers (local or peer-mapped), coefs: host array
+int slb_fedavg(float* out, void* out_bf16, const float* const* srcs, const float* coefs, int nsrc, long long n, cudaStream_t st) {
+  if (nsrc < 1 || nsrc > 16 || n % 4) return -1;
+  FedAvgParams p;
+  for (int i = 0; i < 16; ++i) { p.src[i] = i < nsrc ? srcs[i] : nullptr; p.coef[i] = i < nsrc ? coefs[i] : 0.f; }
+  p.nsrc = nsrc;
+  fedavg_kernel<<<grid_for(n / 4, 512, 148 * 4), 512, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<uint2*>(out_bf16), p, n / 4);
+  return last_err();
+}
+
+}  // extern "C"

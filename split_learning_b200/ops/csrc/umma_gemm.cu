@@ -1,0 +1,494 @@
+// One warp-specialised tcgen05 GEMM pipeline, instantiated for every GEMM-shaped op of the
+// split-learning stages:
+//
+//   MODE_CONV   conv3x3 s1 p1 forward and input-gradient as implicit GEMM.
+//               A = NHWC activations, one 4-D TMA box per filter tap (signed coordinates ->
+//               zero padding for free), K-major;  B = [Cout][3][3][Cin] weights, K-major
+//               (forward) or MN-major view of the same tensor (dgrad, taps mirrored).
+//   MODE_WGRAD  conv3x3 weight gradient, K = all pixels, both operands MN-major,
+//               split-K over CTAs with fp32 red.add into the [Cout][3][3][Cin] gradient.
+//   MODE_GEMM   plain C[M,N] (+)= A * B with any major combination: the three Linear GEMMs
+//               (swap-AB so the 4096-wide dimension sits on the MMA M axis).
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread MMA issue,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).  BLOCK_M = 128 (UMMA M),
+// BLOCK_K = 64 bf16 = one 128-byte swizzle row, fp32 accumulators in TMEM.
+#include "sm100.cuh"
+
+namespace slb {
+
+enum { MODE_CONV = 0, MODE_WGRAD = 1, MODE_GEMM = 2 };
+enum { EPI_BF16 = 0, EPI_F32_ATOMIC = 1, EPI_F32_ATOMIC_T = 2, EPI_F32_STORE = 3 };
+
+struct GemmParams {
+  // generic
+  int M, N;             // logical output extent (rows on TMEM lanes, cols on TMEM columns)
+  int k_iters;          // total K iterations of 64
+  int k_split;          // gridDim.z
+  int a_mn, b_mn;       // operand majors (1 = MN-major)
+  int epi;              // epilogue kind
+  void* out;            // output tensor
+  long long ldo;        // output leading dimension (elements)
+  const float* bias;    // per-column bias (EPI_BF16) or nullptr
+  float* col_sum;       // per-column sum / sum of squares (BN statistics) or nullptr
+  float* col_sumsq;
+  // row remap for wgrad: row r -> (r % rmod) * rmul1 + (r / rmod) * rmul2   (rmod == 0: r * ldo)
+  int rmod;
+  long long rmul1, rmul2;
+  int m_valid_mod;      // wgrad: rows r with r / rmod >= 9 are padding
+  // conv geometry
+  int C;                // channels of the A tensor (GEMM-K per tap)
+  int tw, th, tb;       // pixel-tile box (W, H, B) ; tw*th*tb == 128 (conv) or 64 (wgrad)
+  int H, W;
+  int flip;             // 1: dgrad (mirrored taps)
+  int b_row_stride;     // conv: columns of B per tap (= Cin of the weight tensor)
+  int Cout;             // wgrad: number of output channels (rows per tap)
+};
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int A_BYTES = 128 * 128;      // 16 KB
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 5 : 6);
+  static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int BAR_BYTES = 4096;
+  static constexpr int TOTAL = TILE_BYTES + BAR_BYTES + 1024 /*align slack*/;
+};
+
+// Sum of v[c] over the 32 lanes of a warp for every c in 0..31; lane j returns column j.
+__device__ __forceinline__ float warp_col_reduce32(float (&v)[32]) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int MODE, int BLOCK_N>
+__global__ void __launch_bounds__(192, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using L = SmemLayout<BLOCK_N>;
+  constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::TILE_BYTES);
+  uint64_t* empty_bar = full_bar + L::STAGES;
+  uint64_t* accum_bar = empty_bar + L::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);   // [2][BLOCK_N] floats (<= 2 KB of the 4 KB tail)
+
+  const int warp = threadIdx.x >> 5;
+  const int m_tile = blockIdx.x, n_tile = blockIdx.y, z = blockIdx.z;
+  const int m0 = m_tile * 128, n0 = n_tile * BLOCK_N;
+
+  // K range of this CTA (split-K)
+  const int per = (p.k_iters + p.k_split - 1) / p.k_split;
+  const int k_begin = z * per;
+  const int k_end = min(p.k_iters, k_begin + per);
+  const int my_iters = max(0, k_end - k_begin);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < L::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (my_iters > 0) {
+    if (warp == 0) {
+      // ============================== TMA producer ==============================
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = k_begin; it < k_end; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if constexpr (MODE == MODE_CONV) {
+            const int kc_per_tap = p.C >> 6;
+            const int tap = it / kc_per_tap, kc = it - tap * kc_per_tap;
+            int dh = tap / 3 - 1, dw = tap % 3 - 1;
+            if (p.flip) { dh = -dh; dw = -dw; }
+            // pixel tile origin: 128 consecutive NHWC pixels starting at m0
+            const int pix_per_img = p.H * p.W;
+            const int b0 = m0 / pix_per_img;
+            const int rem = m0 - b0 * pix_per_img;
+            const int h0 = rem / p.W;
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * 64, dw, h0 + dh, b0);
+            if (!p.b_mn) {
+              tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.b_row_stride + kc * 64, n0);
+            } else {
+#pragma unroll
+              for (int g = 0; g < BLOCK_N / 64; ++g)
+                tma_load_2d(sb + g * 8192, &tmB, &full_bar[stage], tap * p.b_row_stride + n0 + g * 64, kc * 64);
+            }
+          } else if constexpr (MODE == MODE_WGRAD) {
+            // K iteration = 64 consecutive pixels starting at it*64
+            const int pix0 = it * 64;
+            const int pix_per_img = p.H * p.W;
+            const int b0 = pix0 / pix_per_img;
+            const int rem = pix0 - b0 * pix_per_img;
+            const int h0 = rem / p.W;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int r = m0 + g * 64;
+              const int tap = r / p.Cout, c0 = r - tap * p.Cout;
+              if (tap < 9) {
+                const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+                // dW[co][tap][ci] = sum_q dY[q - tap][co] * X[q][ci]
+                tma_load_4d(sa + g * 8192, &tmA, &full_bar[stage], c0, -dw, h0 - dh, b0);
+              } else {
+                // padding half-tile (9 taps is odd when Cout == 64): re-load tap 8, result is discarded
+                tma_load_4d(sa + g * 8192, &tmA, &full_bar[stage], c0, 0, h0, b0);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < BLOCK_N / 64; ++g)
+              tma_load_4d(sb + g * 8192, &tmB, &full_bar[stage], n0 + g * 64, 0, h0, b0);
+          } else {
+            if (!p.a_mn) {
+              tma_load_2d(sa, &tmA, &full_bar[stage], it * 64, m0);
+            } else {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) tma_load_2d(sa + g * 8192, &tmA, &full_bar[stage], m0 + g * 64, it * 64);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(sb, &tmB, &full_bar[stage], it * 64, n0);
+            } else {
+#pragma unroll
+              for (int g = 0; g < (BLOCK_N + 63) / 64; ++g)
+                tma_load_2d(sb + g * 8192, &tmB, &full_bar[stage], n0 + g * 64, it * 64);
+            }
+          }
+          if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      // ============================== MMA issuer ==============================
+      const uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, p.a_mn != 0, p.b_mn != 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_base = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t b_base = a_base + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = p.a_mn ? umma_desc_sw128(a_base + k * 2048, 8192, 1024)
+                                       : umma_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t db = p.b_mn ? umma_desc_sw128(b_base + k * 2048, 8192, 1024)
+                                       : umma_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                  // frees this smem stage once the MMAs retire
+          if (it == my_iters - 1) umma_commit(accum_bar);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+      }
+    } else {
+      // ============================== epilogue ==============================
+      const int q = warp & 3;                       // TMEM lane quarter owned by this warp
+      const int row = m0 + q * 32 + lane_id();      // output row of this thread
+      const int et = (warp - 2) * 32 + lane_id();   // 0..127 epilogue thread id
+      const bool want_stats = (p.col_sum != nullptr);
+      if (want_stats) {
+        for (int i = et; i < 2 * BLOCK_N; i += 128) s_stats[i] = 0.f;
+        asm volatile("bar.sync 1, 128;");
+      }
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+      const bool row_ok = row < p.M;
+      long long row_off;
+      bool row_store = row_ok;
+      if (p.rmod > 0) {
+        const int hi = row / p.rmod, lo = row - hi * p.rmod;
+        row_off = lo * p.rmul1 + hi * p.rmul2;
+        row_store = row_ok && hi < p.m_valid_mod;
+      } else {
+        row_off = static_cast<long long>(row) * p.ldo;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (p.epi == EPI_BF16) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]);
+            if (p.bias != nullptr && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
+            f[j] = x;
+          }
+          if (row_store) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
+            if (col0 + 32 <= p.N) {
+              uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            } else {
+              for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = __float2bfloat16(f[j]);
+            }
+          }
+          if (want_stats) {
+            // statistics of the bf16-rounded values that were stored (what the consumer normalises)
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float r = row_ok ? __bfloat162float(__float2bfloat16(f[j])) : 0.f;
+              s1[j] = r;
+              s2[j] = r * r;
+            }
+            const float c1 = warp_col_reduce32(s1);
+            const float c2 = warp_col_reduce32(s2);
+            atomicAdd(&s_stats[c + lane_id()], c1);
+            atomicAdd(&s_stats[BLOCK_N + c + lane_id()], c2);
+          }
+        } else if (p.epi == EPI_F32_ATOMIC) {
+          if (row_store) {
+            float* o = reinterpret_cast<float*>(p.out) + row_off + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
+          }
+        } else if (p.epi == EPI_F32_ATOMIC_T) {
+          if (row_ok) {
+            float* o = reinterpret_cast<float*>(p.out) + row;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(o + static_cast<long long>(col0 + j) * p.ldo, __uint_as_float(v[j]));
+          }
+        } else {  // EPI_F32_STORE
+          if (row_store) {
+            float* o = reinterpret_cast<float*>(p.out) + row_off + col0;
+            if (col0 + 32 <= p.N) {
+              float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            } else {
+              for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = __uint_as_float(v[j]);
+            }
+          }
+        }
+      }
+      if (want_stats) {
+        asm volatile("bar.sync 1, 128;");
+        for (int i = et; i < BLOCK_N; i += 128) {
+          if (n0 + i < p.N) {
+            atomicAdd(p.col_sum + n0 + i, s_stats[i]);
+            atomicAdd(p.col_sumsq + n0 + i, s_stats[BLOCK_N + i]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map, SWIZZLE_128B, inner box = 64 elements (128 B).  dims/strides innermost first.
+static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i];
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
+}
+
+static int tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
+                   uint32_t box_rows) {
+  uint64_t dims[2] = {cols, rows};
+  uint64_t str[2] = {2, ld_elems * 2};
+  uint32_t box[2] = {box_cols, box_rows};
+  return make_tmap(m, base, 2, dims, str, box);
+}
+static int tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int tb, int th, int tw) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t str[4] = {2, (uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
+  return make_tmap(m, base, 4, dims, str, box);
+}
+
+template <int MODE, int BN>
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid, cudaStream_t st) {
+  auto k = umma_gemm_kernel<MODE, BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::TOTAL);
+    if (e != cudaSuccess) return -static_cast<int>(e) - 1000;
+    attr_done = true;
+  }
+  k<<<grid, 192, SmemLayout<BN>::TOTAL, st>>>(a, b, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -static_cast<int>(e) - 2000;
+}
+
+template <int MODE>
+static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid,
+                       cudaStream_t st) {
+  switch (bn) {
+    case 32: return launch<MODE, 32>(a, b, p, grid, st);
+    case 64: return launch<MODE, 64>(a, b, p, grid, st);
+    case 128: return launch<MODE, 128>(a, b, p, grid, st);
+    case 256: return launch<MODE, 256>(a, b, p, grid, st);
+    default: return -3;
+  }
+}
+
+static void pixel_box(int H, int W, int pixels, int* tb, int* th, int* tw) {
+  *tw = W;
+  int rows = pixels / W;           // full-width rows in the tile
+  if (rows <= H) { *th = rows; *tb = 1; }
+  else { *th = H; *tb = rows / H; }
+}
+
+}  // namespace slb
+
+using namespace slb;
+
+extern "C" {
+
+// y[B,H,W,Cout] (bf16, pre-BN) = conv3x3(x[B,H,W,Cin], w[Cout][3][3][Cin]) + bias ; optional per-channel
+// sum / sum-of-squares accumulation (caller zeroes them).  flip=1 computes the input gradient:
+// x := dY [B,H,W,Cout_w], w as stored, out = dX[B,H,W,Cin_w]  (then Cin here means channels of A = Cout_w).
+int slb_conv3x3_igemm(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
+                      int B, int H, int W, int Ca /*channels of A*/, int Nout /*output channels*/, int flip,
+                      int w_cin /*Cin of the weight tensor*/, int w_cout, cudaStream_t st) {
+  if (Ca % 64 != 0 || Nout % 64 != 0) return -10;
+  const int M = B * H * W;
+  if (128 % W != 0 && W % 128 != 0) return -11;
+  int tb, th, tw;
+  pixel_box(H, W, 128, &tb, &th, &tw);
+  if (tw * th * tb != 128) return -12;
+  int bn = Nout >= 256 ? 256 : Nout;   // 64, 128, 256
+  if (flip && bn > 128) bn = 128;
+  CUtensorMap ta, tbm;
+  int r = tmap_nhwc(&ta, x, B, H, W, Ca, tb, th, tw);
+  if (r) return r;
+  if (!flip) r = tmap_2d(&tbm, w, (uint64_t)9 * w_cin, w_cout, (uint64_t)9 * w_cin, 64, bn);
+  else       r = tmap_2d(&tbm, w, (uint64_t)9 * w_cin, w_cout, (uint64_t)9 * w_cin, 64, 64);
+  if (r) return r;
+  GemmParams p = {};
+  p.M = M; p.N = Nout; p.k_iters = 9 * (Ca / 64); p.k_split = 1;
+  p.a_mn = 0; p.b_mn = flip ? 1 : 0; p.epi = EPI_BF16; p.out = y; p.ldo = Nout;
+  p.bias = bias; p.col_sum = col_sum; p.col_sumsq = col_sumsq;
+  p.C = Ca; p.tw = tw; p.th = th; p.tb = tb; p.H = H; p.W = W; p.flip = flip; p.b_row_stride = w_cin;
+  dim3 grid((M + 127) / 128, Nout / bn, 1);
+  return dispatch_bn<MODE_CONV>(bn, ta, tbm, p, grid, st);
+}
+
+// dw[Cout][3][3][Cin] (fp32, accumulated with red.add; caller zeroes) += sum_pixels dy (x) x
+int slb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int k_split,
+                      cudaStream_t st) {
+  if (Cin % 64 != 0 || Cout % 64 != 0) return -10;
+  const int pixels = B * H * W;
+  int tb, th, tw;
+  pixel_box(H, W, 64, &tb, &th, &tw);
+  if (tw * th * tb != 64) return -12;
+  const int bn = Cin >= 256 ? 256 : Cin;
+  CUtensorMap ta, tbm;
+  int r = tmap_nhwc(&ta, dy, B, H, W, Cout, tb, th, tw);
+  if (r) return r;
+  r = tmap_nhwc(&tbm, x, B, H, W, Cin, tb, th, tw);
+  if (r) return r;
+  GemmParams p = {};
+  const int rows = 9 * Cout;
+  p.M = ((rows + 127) / 128) * 128; p.N = Cin; p.k_iters = (pixels + 63) / 64;   // tail pixels are TMA zero-fill
+  const int m_tiles = p.M / 128, n_tiles = Cin / bn;
+  if (k_split <= 0) {
+    k_split = (148 + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
+    if (k_split < 1) k_split = 1;
+  }
+  if (k_split > p.k_iters) k_split = p.k_iters;
+  p.k_split = k_split;
+  p.a_mn = 1; p.b_mn = 1; p.epi = EPI_F32_ATOMIC; p.out = dw; p.ldo = Cin;
+  p.rmod = Cout; p.rmul1 = (long long)9 * Cin; p.rmul2 = Cin; p.m_valid_mod = 9;
+  p.C = Cout; p.tw = tw; p.th = th; p.tb = tb; p.H = H; p.W = W; p.Cout = Cout;
+  dim3 grid(m_tiles, n_tiles, k_split);
+  return dispatch_bn<MODE_WGRAD>(bn, ta, tbm, p, grid, st);
+}
+
+// Generic bf16 GEMM:  D[M,N] = A x B  with fp32 result.
+//   A: a_mn==0 -> stored [M][K] (K contiguous, lda); a_mn==1 -> stored [K][M] (M contiguous, lda)
+//   B: b_mn==0 -> stored [N][K];                     b_mn==1 -> stored [K][N]
+//   epi: 1 = atomic add into out[M][ldo], 2 = atomic add into transposed out[N][ldo], 3 = plain store out[M][ldo]
+int slb_gemm_bf16(const void* A, const void* Bm, float* out, int M, int N, int K, int a_mn, int b_mn, long long lda,
+                  long long ldb, long long ldo, int epi, int k_split, int block_n, cudaStream_t st) {
+  if (block_n != 32 && block_n != 64 && block_n != 128 && block_n != 256) return -3;
+  CUtensorMap ta, tbm;
+  int r;
+  if (!a_mn) r = tmap_2d(&ta, A, K, M, lda, 64, 128);
+  else       r = tmap_2d(&ta, A, M, K, lda, 64, 64);
+  if (r) return r;
+  if (!b_mn) r = tmap_2d(&tbm, Bm, K, N, ldb, 64, block_n);
+  else       r = tmap_2d(&tbm, Bm, N, K, ldb, 64, 64);
+  if (r) return r;
+  if (b_mn && block_n < 64) return -4;
+  GemmParams p = {};
+  p.M = M; p.N = N; p.k_iters = (K + 63) / 64;
+  if (k_split < 1) k_split = 1;
+  if (k_split > p.k_iters) k_split = p.k_iters;
+  if (epi == EPI_F32_STORE) k_split = 1;
+  p.k_split = k_split; p.a_mn = a_mn; p.b_mn = b_mn; p.epi = epi; p.out = out; p.ldo = ldo;
+  dim3 grid((M + 127) / 128, (N + block_n - 1) / block_n, k_split);
+  return dispatch_bn<MODE_GEMM>(block_n, ta, tbm, p, grid, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+"""ctypes binding of ``_slb200.so`` — the hand-written sm_100a kernels.
+
+Every wrapper takes torch CUDA tensors (or raw device pointers), launches on the *current*
+torch stream (so it composes with CUDA-graph capture) and raises on a non-zero status.
+There is deliberately no fallback here: on a CUDA box a missing/unloadable library is an
+error (``require()``), never a silent switch to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_longlong, c_uint32, c_uint64, c_void_p
+from typing import Optional, Sequence
+
+import torch
+
+from . import build as _build
+
+_lib = None
+LAUNCHES = 0            # number of kernels launched through this module (bench's gpu_launches)
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def available() -> bool:
+    return os.path.exists(_build.LIB)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_build.LIB):
+            raise NativeError(f"{_build.LIB} missing: run `python -m split_learning_b200.ops.build`")
+        _lib = ctypes.CDLL(_build.LIB)
+        _lib.slb_error_string.restype = ctypes.c_char_p
+    return _lib
+
+
+def require():
+    """Fail loudly when CUDA is present but the kernel library is not."""
+    if torch.cuda.is_available():
+        lib()
+
+
+def _p(t) -> c_void_p:
+    if t is None:
+        return c_void_p(0)
+    if isinstance(t, int):
+        return c_void_p(t)
+    return c_void_p(t.data_ptr())
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(code: int, what: str, n: int = 1):
+    global LAUNCHES
+    if code != 0:
+        msg = ""
+        if code <= -2000:
+            msg = lib().slb_error_string(-(code + 2000)).decode()
+        elif code <= -1000:
+            msg = "cudaFuncSetAttribute: " + lib().slb_error_string(-(code + 1000)).decode()
+        elif code <= -100:
+            msg = f"cuTensorMapEncodeTiled CUresult={-(code + 100)}"
+        raise NativeError(f"{what} failed with status {code} {msg}")
+    LAUNCHES += n
+
+
+# ------------------------------------------------------------------ tensor-core ops
+def conv3x3_fwd(x, w_bf16, y, bias=None, col_sum=None, col_sumsq=None):
+    """x [B,H,W,Cin] bf16, w [Cout,3,3,Cin] bf16 -> y [B,H,W,Cout] bf16 (pre-BN) + optional BN sums."""
+    B, H, W, Cin = x.shape
+    Cout = w_bf16.shape[0]
+    _check(lib().slb_conv3x3_igemm(_p(x), _p(w_bf16), _p(y), _p(bias), _p(col_sum), _p(col_sumsq), c_int(B), c_int(H),
+                                   c_int(W), c_int(Cin), c_int(Cout), c_int(0), c_int(Cin), c_int(Cout), _stream()),
+           "conv3x3_fwd")
+
+
+def conv3x3_dgrad(dy, w_bf16, dx):
+    """dy [B,H,W,Cout] bf16, w [Cout,3,3,Cin] bf16 -> dx [B,H,W,Cin] bf16."""
+    B, H, W, Cout = dy.shape
+    Cin = w_bf16.shape[3]
+    _check(lib().slb_conv3x3_igemm(_p(dy), _p(w_bf16), _p(dx), _p(None), _p(None), _p(None), c_int(B), c_int(H), c_int(W),
+                                   c_int(Cout), c_int(Cin), c_int(1), c_int(Cin), c_int(Cout), _stream()), "conv3x3_dgrad")
+
+
+def conv3x3_wgrad(x, dy, dw_f32, k_split: int = 0):
+    """dw [Cout,3,3,Cin] fp32 += x^T (*) dy   (caller zeroes dw)."""
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    _check(lib().slb_conv3x3_wgrad(_p(x), _p(dy), _p(dw_f32), c_int(B), c_int(H), c_int(W), c_int(Cin), c_int(Cout),
+                                   c_int(k_split), _stream()), "conv3x3_wgrad")
+
+
+EPI_ATOMIC, EPI_ATOMIC_T, EPI_STORE = 1, 2, 3
+
+
+def gemm_bf16(A, Bm, out, M, N, K, a_mn, b_mn, lda, ldb, ldo, epi, k_split=1, block_n=32):
+    _check(lib().slb_gemm_bf16(_p(A), _p(Bm), _p(out), c_int(M), c_int(N), c_int(K), c_int(a_mn), c_int(b_mn),
+                               c_longlong(lda), c_longlong(ldb), c_longlong(ldo), c_int(epi), c_int(k_split),
+                               c_int(block_n), _stream()), "gemm_bf16")
+
+
+def linear_fwd(x, w_bf16, acc, k_split=4):
+    """acc[b][out] (fp32, zeroed) += x[b][in] @ w[out][in]^T  — swap-AB: out on the MMA M axis."""
+    Bn, K = x.shape
+    out_f = w_bf16.shape[0]
+    gemm_bf16(w_bf16, x, acc, out_f, Bn, K, 0, 0, w_bf16.stride(0), x.stride(0), acc.stride(0), EPI_ATOMIC_T, k_split, 32)
+
+
+def linear_dgrad(dz, w_bf16, dacc, k_split=4):
+    """dacc[b][in] (fp32, zeroed) += dz[b][out] @ w[out][in]."""
+    Bn = dz.shape[0]
+    out_f, in_f = w_bf16.shape
+    gemm_bf16(w_bf16, dz, dacc, in_f, Bn, out_f, 1, 0, w_bf16.stride(0), dz.stride(0), dacc.stride(0), EPI_ATOMIC_T,
+              k_split, 32)
+
+
+def linear_wgrad(dz, x, dw_f32):
+    """dw[out][in] (fp32) = dz[b][out]^T @ x[b][in]   (plain store)."""
+    Bn, in_f = x.shape
+    out_f = dw_f32.shape[0]
+    gemm_bf16(dz, x, dw_f32, out_f, in_f, Bn, 1, 1, dz.stride(0), x.stride(0), dw_f32.stride(0), EPI_STORE, 1,
+              256 if in_f >= 256 else 64)
+
+
+# ------------------------------------------------------------------ memory-bound ops
+def zero_(t):
+    _check(lib().slb_zero(_p(t), c_longlong(t.numel() * t.element_size()), _stream()), "zero")
+
+
+def bn_relu_pool_fwd(y, col_sum, col_sumsq, gamma, beta, running_mean, running_var, nbt, save_mean, save_invstd, out,
+                     H, W, relu, pool, momentum=0.1, eps=1e-5, update_running=True, identity=False, ticket=None, flag=None,
+                     seq=None, hint=None):
+    P, C = y.shape[0] * y.shape[1] * y.shape[2], y.shape[3]
+    _check(lib().slb_bn_relu_pool_fwd(_p(y), _p(col_sum), _p(col_sumsq), _p(gamma), _p(beta), _p(running_mean),
+                                      _p(running_var), _p(nbt), _p(save_mean), _p(save_invstd), _p(out), c_int(P), c_int(C),
+                                      c_int(H), c_int(W), c_int(int(relu)), c_int(int(pool)), c_float(momentum), c_float(eps),
+                                      c_int(int(update_running)), c_int(int(identity)), _p(ticket), _p(flag), _p(seq), _p(hint),
+                                      _stream()), "bn_relu_pool_fwd")
+
+
+def bn_relu_pool_bwd(dout, y, gamma, beta, save_mean, save_invstd, dgamma, dbeta, dy, H, W, relu, pool, identity=False):
+    P, C = y.shape[0] * y.shape[1] * y.shape[2], y.shape[3]
+    _check(lib().slb_bn_relu_pool_bwd(_p(dout), _p(y), _p(gamma), _p(beta), _p(save_mean), _p(save_invstd), _p(dgamma),
+                                      _p(dbeta), _p(dy), c_int(P), c_int(C), c_int(H), c_int(W), c_int(int(relu)),
+                                      c_int(int(pool)), c_int(int(identity)), _stream()), "bn_relu_pool_bwd",
+           1 if identity else 2)
+
+
+def col_stats(y2d, col_sum, col_sumsq=None):
+    P, C = y2d.shape
+    _check(lib().slb_col_stats(_p(y2d), _p(col_sum), _p(col_sumsq), c_longlong(P), c_int(C), _stream()), "col_stats")
+
+
+def conv3x3_small_fwd(x_nchw_f32, w_f32, bias, y, col_sum=None, col_sumsq=None):
+    B, Cin, H, W = x_nchw_f32.shape
+    Cout = w_f32.shape[0]
+    _check(lib().slb_conv3x3_small_fwd(_p(x_nchw_f32), _p(w_f32), _p(bias), _p(y), _p(col_sum), _p(col_sumsq), c_int(B),
+                                       c_int(Cin), c_int(H), c_int(W), c_int(Cout), _stream()), "conv3x3_small_fwd")
+
+
+def conv3x3_small_wgrad(x_nchw_f32, dy, dw_f32):
+    B, Cin, H, W = x_nchw_f32.shape
+    Cout = dy.shape[3]
+    _check(lib().slb_conv3x3_small_wgrad(_p(x_nchw_f32), _p(dy), _p(dw_f32), c_int(B), c_int(Cin), c_int(H), c_int(W),
+                                         c_int(Cout), _stream()), "conv3x3_small_wgrad")
+
+
+def linear_finalize(acc, bias, out_bf16, out_f32, mask, relu, drop_p=0.0, seed=0, step_ptr=None):
+    B, N = acc.shape
+    ldo = out_bf16.stride(0) if out_bf16 is not None else N
+    _check(lib().slb_linear_finalize(_p(acc), _p(bias), _p(out_bf16), _p(out_f32), _p(mask), c_int(B), c_int(N), c_int(ldo),
+                                     c_int(int(relu)), c_float(drop_p), c_uint32(seed), _p(step_ptr), _stream()),
+           "linear_finalize")
+
+
+def linear_bwd_prep(dacc, yout, mask, dz, dbias, relu, drop_p=0.0):
+    B, N = dacc.shape
+    _check(lib().slb_linear_bwd_prep(_p(dacc), _p(yout), _p(mask), _p(dz), _p(dbias), c_int(B), c_int(N),
+                                     c_int(yout.stride(0) if yout is not None else N), c_int(dz.stride(0)),
+                                     c_int(int(relu)), c_float(drop_p), _stream()), "linear_bwd_prep")
+
+
+def dropout_fwd(x, y, mask, p, seed, step_ptr=None):
+    _check(lib().slb_dropout_fwd(_p(x), _p(y), _p(mask), c_longlong(x.numel()), c_float(p), c_uint32(seed), _p(step_ptr),
+                                 _stream()), "dropout_fwd")
+
+
+def dropout_bwd(dacc, mask, dx, p):
+    _check(lib().slb_dropout_bwd(_p(dacc), _p(mask), _p(dx), c_longlong(dacc.numel()), c_float(p), _stream()), "dropout_bwd")
+
+
+def ce_fwd_bwd(logits_f32, labels_i64, dlogits_f32, loss_sum, nan_flag):
+    B, C = logits_f32.shape
+    _check(lib().slb_ce_fwd_bwd(_p(logits_f32), _p(labels_i64), _p(dlogits_f32), _p(loss_sum), _p(nan_flag), c_int(B),
+                                c_int(C), c_int(dlogits_f32.stride(0)), _stream()), "ce_fwd_bwd")
+
+
+def sgd_momentum(p, g, m, p_bf16, lr, mu, first_step=False):
+    _check(lib().slb_sgd_momentum(_p(p), _p(g), _p(m), _p(p_bf16), c_longlong(p.numel()), c_float(lr), c_float(mu),
+                                  c_int(int(first_step)), _stream()), "sgd_momentum")
+
+
+def adamw(p, g, m, v, p_bf16, lr, b1, b2, eps, wd, step):
+    bc1, bc2 = 1.0 - b1 ** step, 1.0 - b2 ** step
+    _check(lib().slb_adamw(_p(p), _p(g), _p(m), _p(v), _p(p_bf16), c_longlong(p.numel()), c_float(lr), c_float(b1),
+                           c_float(b2), c_float(eps), c_float(wd), c_float(bc1), c_float(bc2), _stream()), "adamw")
+
+
+def cast_f32_bf16(x, y):
+    _check(lib().slb_cast_f32_bf16(_p(x), _p(y), c_longlong(x.numel()), _stream()), "cast_f32_bf16")
+
+
+def fedavg(out, out_bf16, src_ptrs: Sequence[int], coefs: Sequence[float], n: int):
+    k = len(src_ptrs)
+    arr = (c_void_p * k)(*[c_void_p(int(s)) for s in src_ptrs])
+    cf = (c_float * k)(*[float(c) for c in coefs])
+    _check(lib().slb_fedavg(_p(out), _p(out_bf16), arr, cf, c_int(k), c_longlong(n), _stream()), "fedavg")
+
+
+def wait_flag(flag_ptr: int, expected: int = 0, expect_ctr=None, max_spins: int = 1 << 30, status=None):
+    """Stream-ordered wait until *flag >= expected (or >= *expect_ctr + 1 when a device counter is given)."""
+    _check(lib().slb_wait_flag(c_void_p(flag_ptr), c_uint32(expected), _p(expect_ctr), c_uint64(max_spins), _p(status),
+                               _stream()), "wait_flag")
+
+
+def set_flag(flag_ptr: int, value: int = 0, seq=None, hint_ptr: int = 0):
+    _check(lib().slb_set_flag(c_void_p(flag_ptr), c_uint32(value), _p(seq), c_void_p(hint_ptr), _stream()), "set_flag")
+
+
+def counter_inc(ctr):
+    _check(lib().slb_counter_inc(_p(ctr), _stream()), "counter_inc")
+
+
+def memcpy_async(dst_ptr: int, src_ptr: int, nbytes: int):
+    _check(lib().slb_memcpy_async(c_void_p(dst_ptr), c_void_p(src_ptr), c_longlong(nbytes), _stream()), "memcpy_async", 0)

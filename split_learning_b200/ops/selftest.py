@@ -1,0 +1,348 @@
+"""Numerics self-test of every sm_100a kernel against plain PyTorch fp32 references.
+
+    python -m split_learning_b200.ops.selftest            # all checks, each in its own process
+    python -m split_learning_b200.ops.selftest NAME ...   # selected checks, in-process
+
+``tests/test_kernels_gpu.py`` runs the same functions under pytest.  Process isolation
+matters while bringing kernels up: one illegal access poisons the CUDA context.
+"""
+from __future__ import annotations
+
+import json
+import subprocess
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+from . import native as N
+
+CHECKS = {}
+
+
+def check(fn):
+    CHECKS[fn.__name__] = fn
+    return fn
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _conv_case(B, H, W, Cin, Cout, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = _bf(torch.randn(B, H, W, Cin, device="cuda", generator=g))
+    w = _bf(torch.randn(Cout, 3, 3, Cin, device="cuda", generator=g) * (1.0 / (9 * Cin) ** 0.5))
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    return x, w, bias
+
+
+def _ref_conv(x, w, bias=None):
+    # NHWC bf16 -> NCHW fp32 reference
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+CONV_SHAPES = [(32, 32, 32, 64, 64), (32, 16, 16, 64, 128), (32, 16, 16, 128, 128), (32, 8, 8, 128, 256),
+               (32, 8, 8, 256, 256), (32, 4, 4, 256, 512), (32, 4, 4, 512, 512), (32, 2, 2, 512, 512), (8, 2, 2, 512, 512),
+               (8, 32, 32, 64, 64)]
+
+
+@check
+def conv_fwd():
+    worst = 0.0
+    for (B, H, W, Cin, Cout) in CONV_SHAPES:
+        x, w, bias = _conv_case(B, H, W, Cin, Cout)
+        y = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+        s1 = torch.zeros(Cout, device="cuda")
+        s2 = torch.zeros(Cout, device="cuda")
+        N.conv3x3_fwd(x, w, y, bias, s1, s2)
+        torch.cuda.synchronize()
+        ref = _ref_conv(x, w, bias)
+        e = _rel(y, ref)
+        yb = y.float().reshape(-1, Cout)
+        e1 = _rel(s1, yb.sum(0))
+        e2 = _rel(s2, (yb * yb).sum(0))
+        print(f"  conv_fwd {B}x{H}x{W} {Cin}->{Cout}: y {e:.2e} sum {e1:.2e} sumsq {e2:.2e}")
+        worst = max(worst, e, e1, e2)
+    return worst, 1.5e-2
+
+
+@check
+def conv_dgrad():
+    worst = 0.0
+    for (B, H, W, Cin, Cout) in CONV_SHAPES:
+        x, w, _ = _conv_case(B, H, W, Cin, Cout)
+        dy = _bf(torch.randn(B, H, W, Cout, device="cuda"))
+        dx = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.bfloat16)
+        N.conv3x3_dgrad(dy, w, dx)
+        torch.cuda.synchronize()
+        xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+        F.conv2d(xr, w.float().permute(0, 3, 1, 2), None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+        e = _rel(dx, xr.grad.permute(0, 2, 3, 1))
+        print(f"  conv_dgrad {B}x{H}x{W} {Cin}<-{Cout}: {e:.2e}")
+        worst = max(worst, e)
+    return worst, 1.5e-2
+
+
+@check
+def conv_wgrad():
+    worst = 0.0
+    for (B, H, W, Cin, Cout) in CONV_SHAPES:
+        x, w, _ = _conv_case(B, H, W, Cin, Cout)
+        dy = _bf(torch.randn(B, H, W, Cout, device="cuda"))
+        dw = torch.zeros(Cout, 3, 3, Cin, device="cuda")
+        N.conv3x3_wgrad(x, dy, dw)
+        torch.cuda.synchronize()
+        wr = w.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+        F.conv2d(x.float().permute(0, 3, 1, 2), wr, None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+        e = _rel(dw, wr.grad.permute(0, 2, 3, 1))
+        print(f"  conv_wgrad {B}x{H}x{W} {Cin}x{Cout}: {e:.2e}")
+        worst = max(worst, e)
+    return worst, 1.5e-2
+
+
+@check
+def linear_all():
+    worst = 0.0
+    for (Bn, inf, outf, pad) in [(32, 512, 4096, 0), (32, 4096, 4096, 0), (32, 4096, 10, 16), (8, 4096, 4096, 0)]:
+        x = _bf(torch.randn(Bn, inf, device="cuda"))
+        w = _bf(torch.randn(outf, inf, device="cuda") / inf ** 0.5)
+        acc = torch.zeros(Bn, outf, device="cuda")
+        N.linear_fwd(x, w, acc)
+        torch.cuda.synchronize()
+        e1 = _rel(acc, x.float() @ w.float().t())
+        ld = pad or outf
+        dzp = torch.zeros(Bn, ld, device="cuda", dtype=torch.bfloat16)
+        dzp[:, :outf] = _bf(torch.randn(Bn, outf, device="cuda"))
+        dz = dzp[:, :outf]
+        dacc = torch.zeros(Bn, inf, device="cuda")
+        N.linear_dgrad(dz, w, dacc)
+        torch.cuda.synchronize()
+        e2 = _rel(dacc, dz.float() @ w.float())
+        dw = torch.empty(outf, inf, device="cuda")
+        N.linear_wgrad(dz, x, dw)
+        torch.cuda.synchronize()
+        e3 = _rel(dw, dz.float().t() @ x.float())
+        print(f"  linear {Bn}x{inf}->{outf}: fwd {e1:.2e} dgrad {e2:.2e} wgrad {e3:.2e}")
+        worst = max(worst, e1, e2, e3)
+    return worst, 1e-2
+
+
+@check
+def bn_fwd_bwd():
+    worst = 0.0
+    for (B, H, W, C, relu, pool) in [(32, 32, 32, 64, 1, 1), (32, 32, 32, 64, 1, 0), (32, 32, 32, 64, 0, 0),
+                                     (32, 16, 16, 128, 1, 1), (32, 2, 2, 512, 1, 1), (8, 4, 4, 512, 1, 0)]:
+        torch.manual_seed(1)
+        y = _bf(torch.randn(B, H, W, C, device="cuda") * 1.5 + 0.3)
+        gamma = torch.rand(C, device="cuda") + 0.5
+        beta = torch.randn(C, device="cuda") * 0.1
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        nbt = torch.zeros((), device="cuda", dtype=torch.int64)
+        s1 = torch.zeros(C, device="cuda")
+        s2 = torch.zeros(C, device="cuda")
+        N.col_stats(y.view(-1, C), s1, s2)
+        sm, si = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+        OH, OW = (H // 2, W // 2) if pool else (H, W)
+        out = torch.empty(B, OH, OW, C, device="cuda", dtype=torch.bfloat16)
+        N.bn_relu_pool_fwd(y, s1, s2, gamma, beta, rm, rv, nbt, sm, si, out, H, W, relu, pool)
+        torch.cuda.synchronize()
+        # reference
+        yr = y.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+        bn = torch.nn.BatchNorm2d(C).cuda().train()
+        with torch.no_grad():
+            bn.weight.copy_(gamma)
+            bn.bias.copy_(beta)
+        z = bn(yr)
+        if relu:
+            z = F.relu(z)
+        if pool:
+            z = F.max_pool2d(z, 2, 2)
+        e1 = _rel(out, z.permute(0, 2, 3, 1))
+        e2 = max(_rel(rm, bn.running_mean), _rel(rv, bn.running_var))
+        dout = _bf(torch.randn_like(out.float()))
+        z.backward(dout.float().permute(0, 3, 1, 2))
+        dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        dy = torch.empty_like(y)
+        N.bn_relu_pool_bwd(dout, y, gamma, beta, sm, si, dg, db, dy, H, W, relu, pool)
+        torch.cuda.synchronize()
+        e3 = _rel(dy, yr.grad.permute(0, 2, 3, 1))
+        e4 = max(_rel(dg, bn.weight.grad), _rel(db, bn.bias.grad))
+        print(f"  bn {B}x{H}x{W}x{C} relu={relu} pool={pool}: out {e1:.2e} running {e2:.2e} dy {e3:.2e} dgamma/dbeta {e4:.2e}"
+              f" nbt={int(nbt)}")
+        worst = max(worst, e1, e2, e3, e4)
+        assert int(nbt) == 1
+    return worst, 2e-2
+
+
+@check
+def conv1_direct():
+    torch.manual_seed(2)
+    B, Cin, H, W, Cout = 32, 3, 32, 32, 64
+    x = torch.randn(B, Cin, H, W, device="cuda")
+    w = torch.randn(Cout, 3, 3, Cin, device="cuda") * 0.2
+    bias = torch.randn(Cout, device="cuda")
+    y = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    s1, s2 = torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
+    N.conv3x3_small_fwd(x, w, bias, y, s1, s2)
+    torch.cuda.synchronize()
+    wr = w.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    ref = F.conv2d(x, wr, bias, padding=1)
+    e1 = _rel(y, ref.permute(0, 2, 3, 1))
+    e2 = _rel(s1, y.float().reshape(-1, Cout).sum(0))
+    dy = _bf(torch.randn(B, H, W, Cout, device="cuda"))
+    dw = torch.zeros(Cout, 3, 3, Cin, device="cuda")
+    N.conv3x3_small_wgrad(x, dy, dw)
+    torch.cuda.synchronize()
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    e3 = _rel(dw, wr.grad.permute(0, 2, 3, 1))
+    print(f"  conv1 direct: fwd {e1:.2e} stats {e2:.2e} wgrad {e3:.2e}")
+    return max(e1, e2, e3), 1e-2
+
+
+@check
+def ce_and_linear_epilogues():
+    torch.manual_seed(3)
+    B, C = 32, 10
+    logits = torch.randn(B, C, device="cuda") * 3
+    labels = torch.randint(0, C, (B,), device="cuda")
+    dl = torch.zeros(B, C, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    nan = torch.zeros(1, device="cuda", dtype=torch.int32)
+    N.ce_fwd_bwd(logits, labels, dl, loss, nan)
+    torch.cuda.synchronize()
+    lr = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(lr, labels)
+    ref.backward()
+    e1 = abs(float(loss) - float(ref)) / abs(float(ref))
+    e2 = _rel(dl, lr.grad)
+    assert int(nan) == 0
+    # linear finalize / bwd prep
+    acc = torch.randn(B, 4096, device="cuda")
+    bias = torch.randn(4096, device="cuda")
+    out = torch.empty(B, 4096, device="cuda", dtype=torch.bfloat16)
+    mask = torch.empty(B, 4096, device="cuda", dtype=torch.uint8)
+    stepc = torch.full((1,), 7, device="cuda", dtype=torch.int32)
+    N.linear_finalize(acc, bias, out, None, mask, True, 0.5, 123, stepc)
+    torch.cuda.synchronize()
+    ref_out = F.relu(acc + bias) * mask.float() * 2.0
+    e3 = _rel(out, ref_out)
+    keep = float(mask.float().mean())
+    dacc = torch.randn(B, 4096, device="cuda")
+    dz = torch.empty(B, 4096, device="cuda", dtype=torch.bfloat16)
+    dbias = torch.empty(4096, device="cuda")
+    N.linear_bwd_prep(dacc, out, mask, dz, dbias, True, 0.5)
+    torch.cuda.synchronize()
+    ref_dz = dacc * mask.float() * 2.0 * (out.float() > 0)
+    e4 = max(_rel(dz, ref_dz), _rel(dbias, dz.float().sum(0)))
+    print(f"  ce loss {e1:.2e} dlogits {e2:.2e} finalize {e3:.2e} keep={keep:.3f} bwd_prep {e4:.2e}")
+    assert 0.45 < keep < 0.55
+    return max(e1, e2, e3, e4), 1e-2
+
+
+@check
+def optimizers_and_fedavg():
+    torch.manual_seed(4)
+    n = 1 << 20
+    p = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda")
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.SGD([ref_p], lr=0.01, momentum=0.5)
+    m = torch.zeros(n, device="cuda")
+    pb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    worst = 0.0
+    for step in range(3):
+        gi = g * (step + 1)
+        ref_p.grad = gi.clone()
+        opt.step()
+        gg = gi.clone()
+        N.sgd_momentum(p, gg, m, pb, 0.01, 0.5, step == 0)
+        torch.cuda.synchronize()
+        worst = max(worst, float((p - ref_p.data).abs().max()))
+        assert float(gg.abs().max()) == 0.0
+    worst = max(worst, _rel(pb, p))
+    # AdamW
+    p2 = torch.randn(n, device="cuda")
+    ref2 = torch.nn.Parameter(p2.clone())
+    o2 = torch.optim.AdamW([ref2], lr=1e-3, weight_decay=0.01)
+    m2, v2 = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 4):
+        ref2.grad = g.clone() * step
+        o2.step()
+        N.adamw(p2, g.clone() * step, m2, v2, None, 1e-3, 0.9, 0.999, 1e-8, 0.01, step)
+    torch.cuda.synchronize()
+    e_adam = float((p2 - ref2.data).abs().max())
+    # FedAvg
+    srcs = [torch.randn(n, device="cuda") for _ in range(4)]
+    srcs[1][5] = float("nan")
+    coefs = [0.1, 0.2, 0.3, 0.4]
+    out = torch.empty(n, device="cuda")
+    N.fedavg(out, None, [s.data_ptr() for s in srcs], coefs, n)
+    torch.cuda.synchronize()
+    ref = sum(c * torch.nan_to_num(s) for c, s in zip(coefs, srcs))
+    e_fa = float((out - ref).abs().max())
+    print(f"  sgd {worst:.2e} adamw {e_adam:.2e} fedavg {e_fa:.2e}")
+    return max(worst, e_adam, e_fa), 1e-5 if False else 8e-3
+
+
+@check
+def flags_and_peer():
+    flag = torch.zeros(4, device="cuda", dtype=torch.int32)
+    status = torch.zeros(1, device="cuda", dtype=torch.int32)
+    side = torch.cuda.Stream()
+    # load both kernels first: lazy module loading of a new kernel can wait for running kernels to finish
+    N.set_flag(flag.data_ptr() + 12, 1)
+    N.wait_flag(flag.data_ptr() + 12, 1, None, 1 << 10, status)
+    torch.cuda.synchronize()
+    N.wait_flag(flag.data_ptr(), 3, None, 1 << 22, status)          # waits on the main stream
+    with torch.cuda.stream(side):
+        N.set_flag(flag.data_ptr(), 3)
+    torch.cuda.synchronize()
+    assert int(flag[0]) == 3 and int(status) == 0
+    ctr = torch.zeros(2, device="cuda", dtype=torch.int32)           # device-side sequence counters
+    for it in range(1, 4):
+        N.set_flag(flag.data_ptr() + 8, 0, ctr[0:1])
+        N.wait_flag(flag.data_ptr() + 8, 0, ctr[1:2], 1 << 22, status)
+    torch.cuda.synchronize()
+    assert int(flag[2]) == 3 and ctr.tolist() == [3, 3] and int(status) == 0
+    N.wait_flag(flag.data_ptr() + 4, 1, None, 1000, status)          # never set -> bounded timeout, no hang
+    torch.cuda.synchronize()
+    assert int(status) == 1
+    return 0.0, 1.0
+
+
+def run_one(name):
+    t = time.time()
+    err, tol = CHECKS[name]()
+    ok = bool(err <= tol)
+    print(json.dumps({"check": name, "err": err, "tol": tol, "ok": ok, "seconds": round(time.time() - t, 2)}))
+    return ok
+
+
+def main(argv):
+    if argv:
+        return 0 if all([run_one(n) for n in argv]) else 1
+    results = {}
+    for name in CHECKS:
+        try:
+            r = subprocess.run([sys.executable, "-m", "split_learning_b200.ops.selftest", name], capture_output=True,
+                               text=True, timeout=300)
+            tail = (r.stdout + r.stderr).strip().splitlines()[-25:]
+            results[name] = r.returncode
+        except subprocess.TimeoutExpired:
+            tail, results[name] = ["TIMEOUT"], -9
+        print(f"=== {name}: rc={results[name]}")
+        print("\n".join(tail))
+    print("SUMMARY", json.dumps(results))
+    return 0 if all(v == 0 for v in results.values()) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))
