@@ -1,0 +1,141 @@
+"""Cut-edge mailboxes in consumer HBM (the device data plane).
+
+One ``Mailbox`` = a ring of ``depth`` (= control-count) slots that lives in the *consumer's*
+memory.  The producer's final kernel of a pass stores the payload tiles straight into the
+slot — a local pointer when both stages share a GPU, an NVLink-peer pointer (CUDA IPC
+mapping) when they do not — and its last CTA publishes ``flag[slot] = seq`` with
+``st.release.sys``; the consumer's graph starts with a one-thread ``ld.acquire.sys`` wait.
+No host code, NCCL call, pickle or D2H/H2D copy touches activations or gradients
+(reference path being replaced: src/train/VGG16.py:20-53).
+
+Slot reuse is safe without "empty" acknowledgements because at most ``depth`` microbatches
+are in flight (control-count): slot ``s`` is rewritten for microbatch ``i + depth`` only
+after the gradient of microbatch ``i`` came back.
+
+Layout of one exported allocation (all offsets 256-byte aligned):
+    payload[depth][bytes_per_slot] | labels[depth][B] int64 | flags[depth] u32 | header[16] u32
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from ..ops import native as N
+
+
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
+
+
+class _RawCuda:
+    """Expose a raw device pointer to torch through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def tensor_from_ptr(ptr: int, nbytes: int, device) -> torch.Tensor:
+    return torch.as_tensor(_RawCuda(ptr, nbytes), device=device)
+
+
+@dataclass
+class MailboxSpec:
+    depth: int
+    batch: int
+    payload_shape: Tuple[int, ...]      # per-microbatch tensor shape, bf16
+    with_labels: bool = True
+
+    @property
+    def payload_bytes(self) -> int:
+        n = 2
+        for d in self.payload_shape:
+            n *= d
+        return _align(n)
+
+    @property
+    def labels_off(self) -> int:
+        return self.depth * self.payload_bytes
+
+    @property
+    def flags_off(self) -> int:
+        return self.labels_off + _align(self.depth * self.batch * 8)
+
+    @property
+    def header_off(self) -> int:
+        return self.flags_off + 256
+
+    @property
+    def total_bytes(self) -> int:
+        return self.header_off + 256
+
+
+class Mailbox:
+    """View of a mailbox allocation (owner side or a peer-mapped producer side)."""
+
+    def __init__(self, spec: MailboxSpec, base: torch.Tensor, owner: bool, raw_ptr: Optional[int] = None):
+        self.spec, self.base, self.owner = spec, base, owner
+        self.raw_ptr = raw_ptr if raw_ptr is not None else base.data_ptr()
+        d = spec.depth
+        self.payload: List[torch.Tensor] = []
+        for s in range(d):
+            nb = 2
+            for x in spec.payload_shape:
+                nb *= x
+            t = base[s * spec.payload_bytes: s * spec.payload_bytes + nb].view(torch.bfloat16).view(spec.payload_shape)
+            self.payload.append(t)
+        lab = base[spec.labels_off: spec.labels_off + d * spec.batch * 8].view(torch.int64).view(d, spec.batch)
+        self.labels = [lab[s] for s in range(d)]
+        self.flags = base[spec.flags_off: spec.flags_off + 4 * d].view(torch.int32)
+        self.header = base[spec.header_off: spec.header_off + 64].view(torch.int32)
+
+    def flag_ptr(self, slot: int) -> int:
+        return self.raw_ptr + self.spec.flags_off + 4 * slot
+
+    # ---- allocation / export --------------------------------------------------------
+    @staticmethod
+    def allocate_local(spec: MailboxSpec, device) -> "Mailbox":
+        base = torch.zeros(spec.total_bytes, dtype=torch.uint8, device=device)
+        return Mailbox(spec, base, owner=True)
+
+    @staticmethod
+    def allocate_exportable(spec: MailboxSpec, device) -> Tuple["Mailbox", bytes]:
+        """cudaMalloc'ed (not caching-allocator) memory + its 64-byte IPC handle."""
+        lib = N.lib()
+        ptr = ctypes.c_void_p()
+        rc = lib.slb_malloc(ctypes.byref(ptr), ctypes.c_longlong(spec.total_bytes))
+        if rc != 0:
+            raise N.NativeError(f"slb_malloc failed: {rc}")
+        handle = (ctypes.c_uint8 * 64)()
+        rc = lib.slb_ipc_get_handle(ptr, handle)
+        if rc != 0:
+            raise N.NativeError(f"cudaIpcGetMemHandle failed: {rc}")
+        base = tensor_from_ptr(ptr.value, spec.total_bytes, device)
+        return Mailbox(spec, base, owner=True, raw_ptr=ptr.value), bytes(handle)
+
+    @staticmethod
+    def open_peer(spec: MailboxSpec, handle: bytes, device) -> "Mailbox":
+        lib = N.lib()
+        ptr = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+        rc = lib.slb_ipc_open(buf, ctypes.byref(ptr))
+        if rc != 0:
+            raise N.NativeError(f"cudaIpcOpenMemHandle failed: {rc}")
+        base = tensor_from_ptr(ptr.value, spec.total_bytes, device)
+        return Mailbox(spec, base, owner=False, raw_ptr=ptr.value)
+
+
+class EdgeCounters:
+    """Device-resident sequence counters of one end of an edge: ``seq[s]`` (next value the
+    producer publishes for slot s) or ``expect[s]`` (last value the consumer has consumed)."""
+
+    def __init__(self, depth: int, device):
+        self.ctr = torch.zeros(max(depth, 1) * 4, dtype=torch.int32, device=device)
+
+    def at(self, slot: int) -> torch.Tensor:
+        return self.ctr[slot * 4: slot * 4 + 1]
+
+    def reset(self) -> None:
+        self.ctr.zero_()

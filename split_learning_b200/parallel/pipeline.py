@@ -1,0 +1,213 @@
+"""Device-resident split pipeline: stage programs as CUDA graphs chained by mailbox flags.
+
+``DeviceStage`` binds a ``B200Executor`` to its edges:
+
+    first stage   F(slot): forward; the fused BN/ReLU/pool kernel of the cut block stores
+                           straight into the next stage's mailbox slot (+labels) and flags it
+                  B(slot): wait(grad flag) → recompute forward → backward → SGD
+    middle stage  F(slot): wait(act flag) → forward → store+flag downstream
+                  B(slot): wait(grad flag) → recompute → backward (cut-head dgrad stores dX
+                           into the upstream gradient mailbox) → flag → SGD
+    last stage    L(slot): wait(act flag) → forward → CE → backward (dgrad stores dX upstream)
+                           → flag → SGD
+
+Each program is captured once per slot; an epoch is a static 1F1B schedule (``control-count``
+forwards of warm-up, then gradient-first alternation — the steady state of the reference's
+loop, src/train/VGG16.py:76-119) that the host merely enqueues.  ``LocalPipeline`` runs all
+stages of one replica chain in a single process/stream (N = 1 GPU); the multi-process runner
+(``parallel/runner.py``) gives every stage its own GPU and wires the same objects to
+IPC-mapped peer mailboxes.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ..ops import native as N
+from ..train.b200_executor import B200Executor
+from .mailbox import EdgeCounters, Mailbox, MailboxSpec
+
+
+def act_spec(ex: B200Executor, batch: int, depth: int) -> MailboxSpec:
+    """Mailbox geometry of the activation edge *leaving* ``ex`` (== gradient edge entering it)."""
+    if ex.out_kind != "image":
+        raise NotImplementedError("device data plane supports cuts inside the convolutional trunk")
+    c, h, w = ex.out_shape
+    return MailboxSpec(depth, batch, (batch, h, w, c), with_labels=True)
+
+
+class DeviceStage:
+    def __init__(self, ex: B200Executor, batch: int, depth: int,
+                 fwd_in: Optional[Mailbox] = None, grad_in: Optional[Mailbox] = None,
+                 fwd_out: Optional[Mailbox] = None, grad_out: Optional[Mailbox] = None,
+                 stream: Optional[torch.cuda.Stream] = None, wait_spins: int = 1 << 28):
+        self.ex, self.B, self.depth = ex, batch, depth
+        self.fwd_in, self.grad_in, self.fwd_out, self.grad_out = fwd_in, grad_in, fwd_out, grad_out
+        self.stream = stream or ex.stream
+        self.plan = ex.plan(batch)
+        dev = ex.device
+        self.seq_fwd = EdgeCounters(depth, dev)       # values I publish downstream
+        self.seq_grad = EdgeCounters(depth, dev)      # values I publish upstream
+        self.exp_fwd = EdgeCounters(depth, dev)       # values I have consumed from upstream activations
+        self.exp_grad = EdgeCounters(depth, dev)      # values I have consumed from downstream gradients
+        self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.wait_spins = wait_spins
+        self.labels_slots = [torch.zeros(batch, dtype=torch.int64, device=dev) for _ in range(depth)]
+        if fwd_in is not None:                        # consume activations in place from my mailbox
+            self.plan.bind_inputs(fwd_in.payload)
+        elif self.plan.n_slots < depth:
+            raise RuntimeError("executor has fewer input slots than the pipeline depth")
+        self.graphs: Dict[Tuple[str, int], torch.cuda.CUDAGraph] = {}
+        self.use_graphs = ex.use_graphs
+        self._warmed: set = set()
+        self.launches_per: Dict[str, int] = {}
+
+    # ---- program bodies ----------------------------------------------------------------
+    def _F(self, slot: int) -> None:
+        if self.fwd_in is not None:
+            N.wait_flag(self.fwd_in.flag_ptr(slot), 0, self.exp_fwd.at(slot), self.wait_spins, self.status)
+            labels = self.fwd_in.labels[slot]
+        else:
+            labels = self.labels_slots[slot]
+        pub = None
+        out = None
+        if self.fwd_out is not None:
+            N.memcpy_async(self.fwd_out.labels[slot].data_ptr(), labels.data_ptr(), self.B * 8)
+            out = self.fwd_out.payload[slot]
+            pub = {"flag": self.fwd_out.flag_ptr(slot), "seq": self.seq_fwd.at(slot)}
+        self.plan._forward(slot, out_ptr_override=out, publish=pub)
+
+    def _B(self, slot: int) -> None:
+        N.wait_flag(self.grad_in.flag_ptr(slot), 0, self.exp_grad.at(slot), self.wait_spins, self.status)
+        if self.ex.recompute:
+            self.plan._forward(slot)                  # faithful recompute with current weights, no publish
+        gout = self.grad_out.payload[slot] if self.grad_out is not None else None
+        self.plan._backward(self.grad_in.payload[slot], grad_out_override=gout)
+        if self.grad_out is not None:
+            N.set_flag(self.grad_out.flag_ptr(slot), 0, self.seq_grad.at(slot))
+
+    def _L(self, slot: int) -> None:
+        labels = self.labels_slots[slot]
+        if self.fwd_in is not None:
+            N.wait_flag(self.fwd_in.flag_ptr(slot), 0, self.exp_fwd.at(slot), self.wait_spins, self.status)
+            labels = self.fwd_in.labels[slot]
+        gout = self.grad_out.payload[slot] if self.grad_out is not None else None
+        self.plan._last(slot, labels=labels, grad_out_override=gout)
+        if self.grad_out is not None:
+            N.set_flag(self.grad_out.flag_ptr(slot), 0, self.seq_grad.at(slot))
+
+    # ---- execution ----------------------------------------------------------------------
+    def _exec(self, kind: str, slot: int) -> None:
+        body = {"F": self._F, "B": self._B, "L": self._L}[kind]
+        key = (kind, slot)
+        with torch.cuda.stream(self.stream):
+            if not self.use_graphs:
+                body(slot)
+                return
+            g = self.graphs.get(key)
+            if g is None:
+                if kind not in self._warmed:          # first ever call of this program: eager (loads modules)
+                    before = N.LAUNCHES
+                    body(slot)
+                    self.launches_per[kind] = N.LAUNCHES - before
+                    self._warmed.add(kind)
+                    return
+                self.stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    body(slot)
+                self.graphs[key] = g
+            g.replay()
+
+    def forward(self, it: int) -> None:
+        self._exec("F", it % self.depth)
+
+    def backward(self, it: int) -> None:
+        self._exec("B", it % self.depth)
+
+    def last(self, it: int) -> None:
+        self._exec("L", it % self.depth)
+
+    def stage_input(self, it: int, x_host: torch.Tensor, y_host: torch.Tensor) -> None:
+        """First stage: H2D copy of a microbatch (pinned host memory) into input slot ``it % depth``."""
+        slot = it % self.depth
+        with torch.cuda.stream(self.stream):
+            self.plan.x_in[slot].copy_(x_host, non_blocking=True)
+            self.labels_slots[slot].copy_(y_host, non_blocking=True)
+
+    def check(self) -> None:
+        if int(self.status[0].item()) != 0:
+            raise TimeoutError("device pipeline: a mailbox flag never arrived (peer stage dead?)")
+
+    def reset_counters(self) -> None:
+        for c in (self.seq_fwd, self.seq_grad, self.exp_fwd, self.exp_grad):
+            c.reset()
+
+
+class LocalPipeline:
+    """All stages of one chain on one GPU / one stream (the N = 1 configuration).
+
+    The host enqueues a dependency-ordered schedule, so every flag wait is already satisfied
+    when its kernel runs; mailboxes are plain local allocations (producer pointer == consumer
+    pointer), i.e. exactly the multi-GPU kernels with ``peer = self``.
+    """
+
+    def __init__(self, executors: Sequence[B200Executor], batch: int, depth: int):
+        assert executors[0].is_first and executors[-1].is_last
+        self.depth, self.B = depth, batch
+        dev = executors[0].device
+        stream = executors[0].stream
+        self.stages: List[DeviceStage] = []
+        n = len(executors)
+        acts = [Mailbox.allocate_local(act_spec(executors[i], batch, depth), dev) for i in range(n - 1)]
+        grads = [Mailbox.allocate_local(act_spec(executors[i], batch, depth), dev) for i in range(n - 1)]
+        for i, ex in enumerate(executors):
+            self.stages.append(DeviceStage(
+                ex, batch, depth,
+                fwd_in=acts[i - 1] if i > 0 else None, grad_in=grads[i] if i < n - 1 else None,
+                fwd_out=acts[i] if i < n - 1 else None, grad_out=grads[i - 1] if i > 0 else None, stream=stream))
+        self.stream = stream
+        self.it_f = 0
+        self.it_b = 0
+
+    def feed(self, x_host: torch.Tensor, y_host: torch.Tensor) -> None:
+        self.stages[0].stage_input(self.it_f, x_host, y_host)
+
+    def step_forward(self) -> None:
+        """Forward microbatch ``it_f`` through every non-last stage, then the last stage's
+        fused forward/backward, i.e. everything that depends only on this microbatch's input."""
+        it = self.it_f
+        for st in self.stages[:-1]:
+            st.forward(it)
+        self.stages[-1].last(it)
+        self.it_f += 1
+
+    def step_backward(self) -> None:
+        it = self.it_b
+        for st in reversed(self.stages[:-1]):
+            st.backward(it)
+        self.it_b += 1
+
+    def run(self, batches, steps: Optional[int] = None) -> int:
+        """1F1B over an iterable of (x_host, y_host): warm-up ``depth`` forwards, then alternate."""
+        n = 0
+        for x, y in batches:
+            if self.it_f - self.it_b >= self.depth:
+                self.step_backward()
+            self.feed(x, y)
+            self.step_forward()
+            n += 1
+            if steps is not None and n >= steps:
+                break
+        while self.it_b < self.it_f:
+            self.step_backward()
+        return n
+
+    def loss(self) -> torch.Tensor:
+        return self.stages[-1].ex.loss_buf
+
+    def synchronize(self) -> None:
+        self.stream.synchronize()
+        for s in self.stages:
+            s.check()

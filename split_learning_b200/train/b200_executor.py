@@ -1,0 +1,623 @@
+"""Native sm_100a stage executor for VGG-family layer tables.
+
+A stage's ``LayerSpec`` slice is compiled into a static plan of fused blocks
+
+    ConvBlock   = [conv3x3] [BatchNorm2d(train)] [ReLU] [MaxPool2]     (tcgen05 implicit GEMM
+                  + fused BN-stat epilogue; BN/ReLU/pool apply kernel writes the block output —
+                  for the last block of a non-last stage that output pointer *is* the next
+                  stage's mailbox slot, local or NVLink-peer, and the kernel publishes the flag)
+    Dropout     = standalone dropout on a dense activation (VGG layer 46)
+    LinearBlock = Linear [ReLU] [Dropout]   (swap-AB tcgen05 GEMM, split-K, fused finalisation)
+
+over flat fp32 master / gradient / momentum buffers with a bf16 shadow copy refreshed by the
+fused SGD kernel.  Forward, backward(+recompute) and the optimizer step of one microbatch are
+captured once per batch size into CUDA graphs; the host only copies the input in and replays.
+
+Semantics follow the reference trainer (src/train/VGG16.py:61-190): SGD(lr, momentum) step per
+microbatch, recompute-forward with *current* weights on non-last stages (BN running stats
+advance twice, as in the reference), CE mean loss on the last stage, NaN flag kept on device.
+Conv weights are stored [Cout][3][3][Cin]; ``state_dict()`` converts to torch's layout so
+checkpoints stay loadable by the reference model classes.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+
+from ..models import SplitModel
+from ..ops import native as N
+from .executor import StageExecutor
+
+
+# ----------------------------------------------------------------------------- plan
+@dataclass
+class ConvBlock:
+    conv: Optional[int] = None       # layer indices (1-based) or None
+    bn: Optional[int] = None
+    relu: bool = False
+    pool: bool = False
+    cin: int = 0
+    cout: int = 0
+    H: int = 0
+    W: int = 0
+
+
+@dataclass
+class DropoutOp:
+    idx: int
+    p: float
+    n: int = 0
+
+
+@dataclass
+class LinearBlock:
+    lin: int
+    fin: int
+    fout: int
+    relu: bool = False
+    drop: float = 0.0
+
+
+def _input_shape(model: SplitModel) -> Tuple[str, Tuple[int, ...]]:
+    """Shape of the stage input (without batch): ('image', (C,H,W)) or ('flat', (F,))."""
+    x = model.example_input(1)
+    c, h, w = x.shape[1:]
+    kind = "image"
+    for i in range(1, model.start_layer + 1):
+        s = model.LAYERS[i - 1]
+        if s.kind == "conv3x3":
+            c = s.args[1]
+        elif s.kind == "maxpool2":
+            h, w = h // 2, w // 2
+        elif s.kind == "flatten":
+            kind, c = "flat", c * h * w
+        elif s.kind == "linear":
+            c = s.args[1]
+    return (kind, (c, h, w)) if kind == "image" else (kind, (c,))
+
+
+def supports(model: SplitModel) -> bool:
+    ok_kinds = {"conv3x3", "bn2d", "relu", "maxpool2", "flatten", "dropout", "linear"}
+    if not all(s.kind in ok_kinds for _, s in model.owned_specs()):
+        return False
+    try:
+        compile_plan(model)
+        return True
+    except (ValueError, NotImplementedError):
+        return False
+
+
+def compile_plan(model: SplitModel):
+    kind, shp = _input_shape(model)
+    specs = model.owned_specs()
+    blocks: List[Any] = []
+    if kind == "image":
+        c, h, w = shp
+    else:
+        c, h, w = shp[0], 1, 1
+    flat = kind == "flat"
+    i = 0
+    while i < len(specs):
+        idx, s = specs[i]
+        if s.kind in ("conv3x3", "bn2d", "relu", "maxpool2") and not flat:
+            b = ConvBlock(H=h, W=w, cin=c)
+            if s.kind == "conv3x3":
+                if s.args[0] != c:
+                    raise ValueError("channel mismatch")
+                b.conv, c = idx, s.args[1]
+                i += 1
+            if i < len(specs) and specs[i][1].kind == "bn2d":
+                b.bn = specs[i][0]
+                i += 1
+            if i < len(specs) and specs[i][1].kind == "relu":
+                b.relu = True
+                i += 1
+            if i < len(specs) and specs[i][1].kind == "maxpool2":
+                b.pool = True
+                h, w = h // 2, w // 2
+                i += 1
+            b.cout = c
+            if b.conv is not None and b.cin > 4 and (b.cin % 64 or b.cout % 64):
+                raise NotImplementedError("tcgen05 conv path needs channels % 64 == 0")
+            if b.conv is not None and b.bn is None and (b.relu or b.pool):
+                raise NotImplementedError("conv+ReLU/pool without BatchNorm has no native plan yet")
+            if b.conv is not None and b.bn is None and b.cin <= 4:
+                raise NotImplementedError("first-layer conv must be followed by BatchNorm in the same stage")
+            if b.W > 128 or (128 % b.W):
+                raise NotImplementedError("image width must divide 128")
+            blocks.append(b)
+        elif s.kind == "flatten":
+            if not flat and (h, w) != (1, 1):
+                raise NotImplementedError("flatten of a spatial map > 1x1 (NHWC/NCHW order differs)")
+            flat, c = True, c * h * w
+            i += 1
+        elif s.kind == "dropout" and flat:
+            blocks.append(DropoutOp(idx, float(s.args[0]), c))
+            i += 1
+        elif s.kind == "linear" and flat:
+            b = LinearBlock(idx, s.args[0], s.args[1])
+            if s.args[0] != c:
+                raise ValueError("feature mismatch")
+            c = s.args[1]
+            i += 1
+            if i < len(specs) and specs[i][1].kind == "relu":
+                b.relu = True
+                i += 1
+            if i < len(specs) and specs[i][1].kind == "dropout":
+                b.drop = float(specs[i][1].args[0])
+                i += 1
+            if b.fin % 64:
+                raise NotImplementedError("Linear in_features % 64")
+            blocks.append(b)
+        else:
+            raise NotImplementedError(f"layer {idx}: {s.kind} in this position")
+    out_shape = ("flat", (c,)) if flat else ("image", (c, h, w))
+    return (kind, shp), blocks, out_shape
+
+
+def _align(n: int, a: int = 128) -> int:
+    return (n + a - 1) // a * a
+
+
+# ----------------------------------------------------------------------------- executor
+class B200Executor(StageExecutor):
+    def __init__(self, model: SplitModel, model_name: str, learning: dict, device, is_first=False, is_last=False,
+                 recompute: bool = True, use_graphs: bool = True, seed: int = 1234):
+        N.require()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.model_cls = type(model)
+        self.start_layer, self.end_layer = model.start_layer, model.end_layer
+        self.model_name = model_name
+        self.is_first, self.is_last = is_first, is_last
+        self.recompute = recompute
+        self.use_graphs = use_graphs
+        self.lr = float(learning.get("learning-rate", 0.01))
+        self.mu = float(learning.get("momentum", 0.0))
+        self.seed = seed
+        (self.in_kind, self.in_shape), self.blocks, (self.out_kind, self.out_shape) = compile_plan(model)
+        self.num_classes = model.num_classes() if is_last else None
+        self._layout_params(model)
+        self.load_state_dict(model.state_dict())
+        self.plans: Dict[int, "_Plan"] = {}
+        self.step_ctr = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.nan_flag = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.loss_buf = torch.zeros(4, device=self.device)       # [0] = mean CE loss of the last microbatch
+        self._store: Dict[Any, Tuple[int, int]] = {}      # data_id -> (batch, slot)
+        self.slots = max(1, int(learning.get("control-count", 3))) if not is_last else 1
+        self.stream = torch.cuda.Stream(device=self.device)
+        # device data plane hooks (set by parallel.mailbox): where the stage output / input gradient go
+        self.out_target = None
+        self.grad_target = None
+
+    # ------------------------------------------------------------------ parameters
+    def _layout_params(self, model: SplitModel) -> None:
+        """Flat fp32 master layout; every tensor starts on a 128-element boundary."""
+        self.entries: Dict[str, Tuple[int, Tuple[int, ...]]] = {}   # key -> (offset, stored shape)
+        off = 0
+        for b in self.blocks:
+            if isinstance(b, ConvBlock):
+                if b.conv is not None:
+                    self.entries[f"layer{b.conv}.weight"] = (off, (b.cout, 3, 3, b.cin))
+                    off += _align(b.cout * 9 * b.cin)
+                    self.entries[f"layer{b.conv}.bias"] = (off, (b.cout,))
+                    off += _align(b.cout)
+                if b.bn is not None:
+                    self.entries[f"layer{b.bn}.weight"] = (off, (b.cout,))
+                    off += _align(b.cout)
+                    self.entries[f"layer{b.bn}.bias"] = (off, (b.cout,))
+                    off += _align(b.cout)
+            elif isinstance(b, LinearBlock):
+                self.entries[f"layer{b.lin}.weight"] = (off, (b.fout, b.fin))
+                off += _align(b.fout * b.fin)
+                self.entries[f"layer{b.lin}.bias"] = (off, (b.fout,))
+                off += _align(b.fout)
+        self.n_params = max(off, 128)
+        dev = self.device
+        self.P = torch.zeros(self.n_params, device=dev)
+        self.G = torch.zeros(self.n_params, device=dev)
+        self.M = torch.zeros(self.n_params, device=dev)
+        self.PB = torch.zeros(self.n_params, device=dev, dtype=torch.bfloat16)
+        self.bn_state: Dict[int, Dict[str, torch.Tensor]] = {}
+        for b in self.blocks:
+            if isinstance(b, ConvBlock) and b.bn is not None:
+                self.bn_state[b.bn] = {"running_mean": torch.zeros(b.cout, device=dev),
+                                       "running_var": torch.ones(b.cout, device=dev),
+                                       "num_batches_tracked": torch.zeros((), device=dev, dtype=torch.int64)}
+
+    def view(self, buf: torch.Tensor, key: str) -> torch.Tensor:
+        off, shape = self.entries[key]
+        return buf[off:off + math.prod(shape)].view(shape)
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        with torch.no_grad():
+            for key, (off, shape) in self.entries.items():
+                t = sd[key].to(self.device, torch.float32)
+                if len(shape) == 4:                      # torch [Cout,Cin,3,3] -> stored [Cout,3,3,Cin]
+                    t = t.permute(0, 2, 3, 1).contiguous()
+                self.P[off:off + t.numel()].copy_(t.reshape(-1))
+            for bn, st in self.bn_state.items():
+                for k in st:
+                    if f"layer{bn}.{k}" in sd:
+                        st[k].copy_(sd[f"layer{bn}.{k}"].to(self.device))
+            self.PB.copy_(self.P)
+        torch.cuda.synchronize(self.device)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        torch.cuda.synchronize(self.device)
+        tmpl = self.model_cls(self.start_layer, self.end_layer).state_dict()
+        out = {}
+        for key in tmpl:
+            if key in self.entries:
+                t = self.view(self.P, key).detach().clone()
+                if t.dim() == 4:
+                    t = t.permute(0, 3, 1, 2).contiguous()
+                out[key] = t
+            else:
+                layer, name = key.split(".", 1)
+                out[key] = self.bn_state[int(layer[5:])][name].detach().clone()
+        return out
+
+    # ------------------------------------------------------------------ plans
+    def plan(self, batch: int) -> "_Plan":
+        p = self.plans.get(batch)
+        if p is None:
+            p = self.plans[batch] = _Plan(self, batch)
+        return p
+
+    # ------------------------------------------------------------------ StageExecutor API (tensor in / tensor out)
+    def _to_internal(self, x: torch.Tensor) -> torch.Tensor:
+        x = x.to(self.device, non_blocking=True)
+        if self.is_first:
+            return x.float().contiguous()
+        if self.in_kind == "image":
+            if x.dim() == 4 and x.shape[1] == self.in_shape[0] and x.shape[-1] != self.in_shape[0]:
+                x = x.permute(0, 2, 3, 1)                # NCHW wire -> NHWC
+            return x.to(torch.bfloat16).contiguous()
+        return x.to(torch.bfloat16).contiguous()
+
+    def _from_internal_out(self, t: torch.Tensor) -> torch.Tensor:
+        if self.out_kind == "image":
+            return t.permute(0, 3, 1, 2).float().contiguous()       # NCHW fp32 on the compat wire
+        return t.float()
+
+    def forward_only(self, data_id, x) -> torch.Tensor:
+        xi = self._to_internal(x)
+        B = xi.shape[0]
+        pl = self.plan(B)
+        slot = pl.acquire_slot()
+        with torch.cuda.stream(self.stream):
+            pl.x_in[slot].copy_(xi, non_blocking=True)
+            pl.run_forward(slot)
+            out = self._from_internal_out(pl.final_out())
+        self.stream.synchronize()
+        self._store[data_id] = (B, slot)
+        return out
+
+    def backward(self, data_id, grad) -> Optional[torch.Tensor]:
+        B, slot = self._store.pop(data_id)
+        pl = self.plan(B)
+        g = grad.to(self.device)
+        if self.out_kind == "image" and g.dim() == 4 and g.shape[1] == self.out_shape[0] and g.shape[-1] != self.out_shape[0]:
+            g = g.permute(0, 2, 3, 1)
+        with torch.cuda.stream(self.stream):
+            pl.dout_in.copy_(g.to(torch.bfloat16), non_blocking=True)
+            pl.run_backward(slot)
+            res = None
+            if not self.is_first:
+                gi = pl.input_grad()
+                res = gi.permute(0, 3, 1, 2).float().contiguous() if self.in_kind == "image" else gi.float()
+        self.stream.synchronize()
+        pl.release_slot(slot)
+        return res
+
+    def forward_backward_last(self, x, labels) -> Optional[torch.Tensor]:
+        xi = self._to_internal(x)
+        B = xi.shape[0]
+        pl = self.plan(B)
+        with torch.cuda.stream(self.stream):
+            pl.x_in[0].copy_(xi, non_blocking=True)
+            pl.labels.copy_(labels.to(self.device), non_blocking=True)
+            pl.run_last()
+            res = None
+            if not self.is_first:
+                gi = pl.input_grad()
+                res = gi.permute(0, 3, 1, 2).float().contiguous() if self.in_kind == "image" else gi.float()
+        self.stream.synchronize()
+        return res
+
+    def nan_detected(self) -> bool:
+        return bool(int(self.nan_flag.item()))
+
+    def reset_epoch(self):
+        self.nan_flag.zero_()
+        self._store.clear()
+        for p in self.plans.values():
+            p.free = list(range(p.n_slots))
+
+    def in_flight(self) -> int:
+        return len(self._store)
+
+    def last_loss(self):
+        return float(self.loss_buf[0].item())
+
+
+# ----------------------------------------------------------------------------- per-batch-size plan
+class _Plan:
+    """Static buffers + captured graphs for one batch size."""
+
+    def __init__(self, ex: B200Executor, B: int):
+        self.ex, self.B = ex, B
+        dev = ex.device
+        bf = torch.bfloat16
+        self.n_slots = ex.slots if (ex.recompute or ex.is_last) else ex.slots
+        self.free = list(range(self.n_slots))
+        # ---- stage input slots
+        if ex.is_first:
+            c, h, w = ex.in_shape
+            self.x_in = [torch.zeros(B, c, h, w, device=dev) for _ in range(self.n_slots)]
+        elif ex.in_kind == "image":
+            c, h, w = ex.in_shape
+            self.x_in = [torch.zeros(B, h, w, c, device=dev, dtype=bf) for _ in range(self.n_slots)]
+        else:
+            self.x_in = [torch.zeros(B, ex.in_shape[0], device=dev, dtype=bf) for _ in range(self.n_slots)]
+        self.labels = torch.zeros(B, device=dev, dtype=torch.int64)
+        # ---- zero-scratch (BN sums, fp32 GEMM accumulators): one contiguous region, one zero kernel per pass
+        scratch = 0
+        self.soff: Dict[Tuple[int, str], Tuple[int, int]] = {}
+
+        def reserve(key, n):
+            nonlocal scratch
+            self.soff[key] = (scratch, n)
+            scratch += _align(n, 4)
+        for bi, b in enumerate(ex.blocks):
+            if isinstance(b, ConvBlock) and b.bn is not None:
+                reserve((bi, "sum"), b.cout)
+                reserve((bi, "sumsq"), b.cout)
+            elif isinstance(b, LinearBlock):
+                reserve((bi, "acc"), B * b.fout)
+                reserve((bi, "dacc_in"), B * b.fin)
+        self.scratch = torch.zeros(max(scratch, 4), device=dev)
+        # ---- activations
+        self.act: List[Dict[str, torch.Tensor]] = []
+        for bi, b in enumerate(ex.blocks):
+            d: Dict[str, torch.Tensor] = {}
+            if isinstance(b, ConvBlock):
+                OH, OW = (b.H // 2, b.W // 2) if b.pool else (b.H, b.W)
+                if b.conv is not None:
+                    d["y"] = torch.zeros(B, b.H, b.W, b.cout, device=dev, dtype=bf)
+                    d["dy"] = torch.zeros(B, b.H, b.W, b.cout, device=dev, dtype=bf)
+                d["out"] = d["y"] if (b.conv is not None and b.bn is None) else torch.zeros(B, OH, OW, b.cout, device=dev, dtype=bf)
+                d["save_mean"] = torch.zeros(b.cout, device=dev)
+                d["save_invstd"] = torch.ones(b.cout, device=dev)
+                d["dx"] = torch.zeros(B, b.H, b.W, b.cin, device=dev, dtype=bf) if (b.cin > 4 and b.conv is not None) else None
+                if b.conv is None:
+                    d["dx_orphan"] = torch.zeros(B, b.H, b.W, b.cout, device=dev, dtype=bf)
+                d["dout_bf16"] = torch.zeros(B, OH, OW, b.cout, device=dev, dtype=bf)
+            elif isinstance(b, DropoutOp):
+                d["out"] = torch.zeros(B, b.n, device=dev, dtype=bf)
+                d["mask"] = torch.zeros(B, b.n, device=dev, dtype=torch.uint8)
+                d["dx"] = torch.zeros(B, b.n, device=dev, dtype=bf)
+            else:
+                ld = _align(b.fout, 16)
+                d["out"] = torch.zeros(B, ld, device=dev, dtype=bf)[:, :b.fout]
+                d["dz"] = torch.zeros(B, ld, device=dev, dtype=bf)[:, :b.fout]
+                d["mask"] = torch.zeros(B, b.fout, device=dev, dtype=torch.uint8) if b.drop > 0 else None
+                d["logits"] = torch.zeros(B, b.fout, device=dev) if (bi == len(ex.blocks) - 1 and ex.is_last) else None
+                d["dx_bf16"] = torch.zeros(B, b.fin, device=dev, dtype=bf)
+            self.act.append(d)
+        # gradient w.r.t. the stage output (arrives from the next stage)
+        last = self.act[-1]["out"]
+        self.dout_in = torch.zeros(last.shape, device=dev, dtype=bf)
+        self.dlogits = torch.zeros(B, ex.num_classes, device=dev) if ex.is_last else None
+        self.ticket = torch.zeros(4, device=dev, dtype=torch.int32)
+        self.graphs: Dict[Tuple[str, int], torch.cuda.CUDAGraph] = {}
+        self._warm = False
+
+    # ---- helpers -----------------------------------------------------------------
+    def s(self, bi: int, name: str, shape=None) -> torch.Tensor:
+        off, n = self.soff[(bi, name)]
+        t = self.scratch[off:off + n]
+        return t.view(shape) if shape is not None else t
+
+    def acquire_slot(self) -> int:
+        if not self.free:
+            raise RuntimeError("more microbatches in flight than control-count slots")
+        return self.free.pop(0)
+
+    def release_slot(self, slot: int) -> None:
+        self.free.append(slot)
+
+    def final_out(self) -> torch.Tensor:
+        return self.act[-1]["out"]
+
+    def input_grad(self) -> torch.Tensor:
+        first = self.ex.blocks[0]
+        a = self.act[0]
+        if isinstance(first, ConvBlock):
+            return a["dx"] if first.conv is not None else a["dx_orphan"]
+        if isinstance(first, DropoutOp):
+            return a["dx"]
+        return a["dx_bf16"]
+
+    # ---- the kernel sequences ------------------------------------------------------
+    def _forward(self, slot: int, out_ptr_override: Optional[torch.Tensor] = None, publish=None) -> None:
+        ex = self.ex
+        N.zero_(self.scratch)
+        x: torch.Tensor = self.x_in[slot]
+        nb = len(ex.blocks)
+        for bi, b in enumerate(ex.blocks):
+            a = self.act[bi]
+            is_final = bi == nb - 1
+            if isinstance(b, ConvBlock):
+                a["in"] = x
+                plain = b.conv is not None and b.bn is None          # cut right after the conv (e.g. cut 4)
+                if plain:
+                    tgt = a["y"] if not (is_final and out_ptr_override is not None) else out_ptr_override
+                    N.conv3x3_fwd(x, ex.view(ex.PB, f"layer{b.conv}.weight"), tgt, ex.view(ex.P, f"layer{b.conv}.bias"))
+                    if is_final and publish is not None:
+                        N.set_flag(publish["flag"].data_ptr() if hasattr(publish["flag"], "data_ptr") else publish["flag"],
+                                   0, publish["seq"], publish.get("hint_ptr", 0))
+                    a["out"] = a["y"]
+                    a["y_eff"] = a["y"]
+                    x = tgt
+                    continue
+                if b.conv is not None:
+                    s1, s2 = self.s(bi, "sum"), self.s(bi, "sumsq")
+                    bias = ex.view(ex.P, f"layer{b.conv}.bias")
+                    if b.cin <= 4:
+                        N.conv3x3_small_fwd(x, ex.view(ex.P, f"layer{b.conv}.weight"), bias, a["y"], s1, s2)
+                    else:
+                        N.conv3x3_fwd(x, ex.view(ex.PB, f"layer{b.conv}.weight"), a["y"], bias, s1, s2)
+                    y = a["y"]
+                else:
+                    y = x
+                    if b.bn is not None:
+                        s1, s2 = self.s(bi, "sum"), self.s(bi, "sumsq")
+                        N.col_stats(y.reshape(-1, b.cout), s1, s2)
+                out = a["out"] if not (is_final and out_ptr_override is not None) else out_ptr_override
+                kw = {}
+                if is_final and publish is not None:
+                    kw = dict(ticket=self.ticket, flag=publish["flag"], seq=publish["seq"], hint=publish.get("hint"))
+                if b.bn is not None:
+                    st = ex.bn_state[b.bn]
+                    N.bn_relu_pool_fwd(y, self.s(bi, "sum"), self.s(bi, "sumsq"), ex.view(ex.P, f"layer{b.bn}.weight"),
+                                       ex.view(ex.P, f"layer{b.bn}.bias"), st["running_mean"], st["running_var"],
+                                       st["num_batches_tracked"], a["save_mean"], a["save_invstd"], out, b.H, b.W,
+                                       b.relu, b.pool, **kw)
+                else:
+                    N.bn_relu_pool_fwd(y, None, None, None, None, None, None, None, a["save_mean"], a["save_invstd"], out,
+                                       b.H, b.W, b.relu, b.pool, update_running=False, identity=True, **kw)
+                a["y_eff"] = y
+                x = a["out"] if out is a["out"] else out
+            elif isinstance(b, DropoutOp):
+                xin = x.reshape(self.B, -1)
+                a["in"] = xin
+                N.dropout_fwd(xin, a["out"], a["mask"], b.p, ex.seed + b.idx, ex.step_ctr)
+                x = a["out"]
+            else:
+                xin = x.reshape(self.B, -1)
+                a["in"] = xin
+                acc = self.s(bi, "acc", (self.B, b.fout))
+                w = ex.view(ex.PB, f"layer{b.lin}.weight")
+                N.linear_fwd(xin, w, acc, k_split=max(1, min(8, (b.fin // 64) // 8)))
+                N.linear_finalize(acc, ex.view(ex.P, f"layer{b.lin}.bias"), a["out"], a["logits"], a["mask"], b.relu,
+                                  b.drop, ex.seed + b.lin, ex.step_ctr)
+                x = a["out"]
+
+    def _backward(self, dout: torch.Tensor, grad_out_override: Optional[torch.Tensor] = None) -> None:
+        """dout: gradient w.r.t. the stage output (bf16) — or fp32 dlogits on the last stage."""
+        ex = self.ex
+        g: Any = dout
+        for bi in range(len(ex.blocks) - 1, -1, -1):
+            b, a = ex.blocks[bi], self.act[bi]
+            need_dx = not (bi == 0 and ex.is_first)
+            if isinstance(b, LinearBlock):
+                # g: fp32 [B, fout] accumulated gradient (dacc) or bf16 gradient from the wire
+                if g.dtype != torch.float32:
+                    g = g.float()                                   # compat path only (outside graphs)
+                N.linear_bwd_prep(g, a["out"], a["mask"], a["dz"], ex.view(ex.G, f"layer{b.lin}.bias"), b.relu, b.drop)
+                N.linear_wgrad(a["dz"], a["in"], ex.view(ex.G, f"layer{b.lin}.weight"))
+                if need_dx:
+                    dacc = self.s(bi, "dacc_in", (self.B, b.fin))
+                    N.linear_dgrad(a["dz"], ex.view(ex.PB, f"layer{b.lin}.weight"), dacc,
+                                   k_split=max(1, min(8, (b.fout // 64) // 8)))
+                    g = dacc
+                    if bi == 0:                                     # stage input gradient leaves as bf16
+                        N.dropout_bwd(dacc, None, a["dx_bf16"], 0.0)
+            elif isinstance(b, DropoutOp):
+                N.dropout_bwd(g, a["mask"], a["dx"], b.p)
+                g = a["dx"]
+            else:
+                if g.dtype == torch.float32:                        # from a Linear block straight into a conv block
+                    tmp = a["dout_bf16"]
+                    N.dropout_bwd(g, None, tmp, 0.0)
+                    g = tmp
+                g = g.reshape(a["out"].shape)
+                y = a["y_eff"]
+                if b.conv is not None:
+                    dy = a["dy"]
+                else:
+                    dy = a["dx_orphan"]
+                    if bi == 0 and grad_out_override is not None:
+                        dy = grad_out_override
+                if b.conv is not None and b.bn is None:
+                    dy = g.reshape(y.shape)
+                elif b.bn is not None:
+                    N.bn_relu_pool_bwd(g, y, ex.view(ex.P, f"layer{b.bn}.weight"), ex.view(ex.P, f"layer{b.bn}.bias"),
+                                       a["save_mean"], a["save_invstd"], ex.view(ex.G, f"layer{b.bn}.weight"),
+                                       ex.view(ex.G, f"layer{b.bn}.bias"), dy, b.H, b.W, b.relu, b.pool)
+                else:
+                    N.bn_relu_pool_bwd(g, y, None, None, a["save_mean"], a["save_invstd"], None, None, dy, b.H, b.W,
+                                       b.relu, b.pool, identity=True)
+                if b.conv is not None:
+                    N.col_stats(dy.reshape(-1, b.cout), ex.view(ex.G, f"layer{b.conv}.bias"), None)
+                    if b.cin <= 4:
+                        N.conv3x3_small_wgrad(a["in"], dy, ex.view(ex.G, f"layer{b.conv}.weight"))
+                    else:
+                        N.conv3x3_wgrad(a["in"], dy, ex.view(ex.G, f"layer{b.conv}.weight"))
+                        if need_dx:
+                            dx = a["dx"] if not (bi == 0 and grad_out_override is not None) else grad_out_override
+                            N.conv3x3_dgrad(dy, ex.view(ex.PB, f"layer{b.conv}.weight"), dx)
+                            g = dx
+                else:
+                    g = dy
+        # optimizer: one fused pass over the flat buffers (also zeroes G and refreshes the bf16 shadow)
+        N.sgd_momentum(ex.P, ex.G, ex.M, ex.PB, ex.lr, ex.mu)
+        N.counter_inc(ex.step_ctr)
+
+    def _last(self, slot: int = 0, labels: Optional[torch.Tensor] = None, grad_out_override=None) -> None:
+        ex = self.ex
+        self._forward(slot)
+        logits = self.act[-1]["logits"]
+        N.zero_(ex.loss_buf)
+        N.ce_fwd_bwd(logits, self.labels if labels is None else labels, self.dlogits, ex.loss_buf, ex.nan_flag)
+        self._backward(self.dlogits, grad_out_override)
+
+    def bind_inputs(self, tensors) -> None:
+        """Use externally owned buffers (mailbox slots) as the stage-input slots."""
+        assert len(tensors) >= 1 and tuple(tensors[0].shape) == tuple(self.x_in[0].shape), \
+            (tuple(tensors[0].shape), tuple(self.x_in[0].shape))
+        self.x_in = list(tensors)
+        self.n_slots = len(tensors)
+        self.free = list(range(self.n_slots))
+        self.graphs.clear()
+
+    # ---- graph management ---------------------------------------------------------
+    def run_forward(self, slot: int) -> None:
+        self._exec(("fwd", slot), lambda: self._forward(slot))
+
+    def run_backward(self, slot: int) -> None:
+        def body():
+            if self.ex.recompute:
+                self._forward(slot)
+            self._backward(self.dout_in)
+        self._exec(("bwd", slot), body)
+
+    def run_last(self) -> None:
+        self._exec(("last", 0), lambda: self._last())
+
+    def _exec(self, key, fn) -> None:
+        ex = self.ex
+        if not ex.use_graphs:
+            fn()
+            return
+        g = self.graphs.get(key)
+        if g is not None:
+            g.replay()
+            return
+        if not self._warm:
+            fn()                                       # first call ever: run eagerly (this is the real step)
+            self._warm = True
+            return
+        # second call onwards for this key: capture, then replay (capture itself does not execute)
+        g = torch.cuda.CUDAGraph()
+        cur = torch.cuda.current_stream()
+        cur.synchronize()
+        with torch.cuda.graph(g, stream=cur):
+            fn()
+        self.graphs[key] = g
+        g.replay()
