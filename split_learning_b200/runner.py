@@ -63,3 +63,43 @@ def run_inproc(cfg: Config, devices: Optional[Sequence[str]] = None, profiles: O
         raise TimeoutError("run_inproc: roles still alive after timeout")
     server.clients_objs = clients
     return server
+
+
+def run_variant(cfg: Config, client_specs: Sequence[dict], workdir: str = ".", timeout: float = 600.0, devices=None):
+    """Like ``run_inproc`` but with explicit per-client registration fields (``layer_id``, ``cluster``,
+    ``idx``/``in_cluster``/``out_cluster``, ``select``) — the CLI flags of the variant ``client.py`` scripts."""
+    broker = InProcBroker()
+    algo = cfg.b200.get("algorithm", "main")
+    server = server_class(algo)(cfg, broker, workdir=workdir)
+    errors: List[BaseException] = []
+
+    def guard(fn):
+        def run():
+            try:
+                fn()
+            except BaseException as e:
+                traceback.print_exc()
+                errors.append(e)
+                server.done = True
+        return run
+    threads = [threading.Thread(target=guard(lambda: server.start(idle_timeout=timeout)), daemon=True)]
+    for r, spec in enumerate(client_specs):
+        spec = dict(spec)
+        layer_id = spec.pop("layer_id")
+        cluster = spec.pop("cluster", -1)
+        dev = devices[r % len(devices)] if devices else "cpu"
+        cli = client_class(algo)(str(uuid.uuid4()), layer_id, broker, device=dev, b200_opts=cfg.b200, rank=r)
+
+        def body(cli=cli, cluster=cluster, spec=spec):
+            cli.register(dict(DEFAULT_PROFILE), cluster, **spec)
+            cli.wait_response(idle_timeout=timeout)
+        threads.append(threading.Thread(target=guard(body), daemon=True))
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout)
+    if errors:
+        raise errors[0]
+    if any(t.is_alive() for t in threads):
+        raise TimeoutError("run_variant: roles still alive after timeout")
+    return server

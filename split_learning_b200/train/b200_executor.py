@@ -284,11 +284,16 @@ class B200Executor(StageExecutor):
             return t.permute(0, 3, 1, 2).float().contiguous()       # NCHW fp32 on the compat wire
         return t.float()
 
+    def _enter(self) -> None:
+        """Tensor-API calls may hand us tensors produced on the caller's stream."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+
     def forward_only(self, data_id, x) -> torch.Tensor:
         xi = self._to_internal(x)
         B = xi.shape[0]
         pl = self.plan(B)
         slot = pl.acquire_slot()
+        self._enter()
         with torch.cuda.stream(self.stream):
             pl.x_in[slot].copy_(xi, non_blocking=True)
             pl.run_forward(slot)
@@ -303,8 +308,10 @@ class B200Executor(StageExecutor):
         g = grad.to(self.device)
         if self.out_kind == "image" and g.dim() == 4 and g.shape[1] == self.out_shape[0] and g.shape[-1] != self.out_shape[0]:
             g = g.permute(0, 2, 3, 1)
+        g = g.to(torch.bfloat16)
+        self._enter()
         with torch.cuda.stream(self.stream):
-            pl.dout_in.copy_(g.to(torch.bfloat16), non_blocking=True)
+            pl.dout_in.copy_(g, non_blocking=True)
             pl.run_backward(slot)
             res = None
             if not self.is_first:
@@ -318,9 +325,11 @@ class B200Executor(StageExecutor):
         xi = self._to_internal(x)
         B = xi.shape[0]
         pl = self.plan(B)
+        labels = labels.to(self.device)
+        self._enter()
         with torch.cuda.stream(self.stream):
             pl.x_in[0].copy_(xi, non_blocking=True)
-            pl.labels.copy_(labels.to(self.device), non_blocking=True)
+            pl.labels.copy_(labels, non_blocking=True)
             pl.run_last()
             res = None
             if not self.is_first:
