@@ -334,6 +334,43 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* y, 
   }
 }
 
+// Split-K epilogue of the tcgen05 conv: y = bf16(acc + bias) and the BN statistics of the rounded values
+// (acc: fp32 [P][C] partial-sum buffer filled with red.add by the K-slices).  bias/y/sum may be null.
+__global__ void __launch_bounds__(256) conv_finalize_kernel(const float* acc, const float* bias, __nv_bfloat16* y, float* sum,
+                                                           float* sumsq, long long P, int C) {
+  const int g = threadIdx.x;
+  float a[8], b[8], bs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = b[j] = 0.f; bs[j] = bias ? bias[g * 8 + j] : 0.f; }
+  for (long long r = blockIdx.x * (long long)blockDim.y + threadIdx.y; r < P; r += (long long)gridDim.x * blockDim.y) {
+    const float4 v0 = *reinterpret_cast<const float4*>(acc + r * C + g * 8);
+    const float4 v1 = *reinterpret_cast<const float4*>(acc + r * C + g * 8 + 4);
+    float f[8] = {v0.x + bs[0], v0.y + bs[1], v0.z + bs[2], v0.w + bs[3], v1.x + bs[4], v1.y + bs[5], v1.z + bs[6], v1.w + bs[7]};
+    const bf16x8 pk = pack8(f);
+    *reinterpret_cast<bf16x8*>(y + r * C + g * 8) = pk;
+    if (sum) {
+      float q[8];
+      unpack8(pk, q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] += q[j]; b[j] += q[j] * q[j]; }
+    }
+  }
+  if (sum == nullptr) return;
+  extern __shared__ float s_red[];
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * C; i += blockDim.x * blockDim.y) s_red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_red[g * 8 + j], a[j]);
+    atomicAdd(&s_red[C + g * 8 + j], b[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < C; i += blockDim.x * blockDim.y) {
+    atomicAdd(sum + i, s_red[i]);
+    atomicAdd(sumsq + i, s_red[C + i]);
+  }
+}
+
 // ============================================================================ first-layer direct conv (Cin <= 4)
 // x: fp32 NCHW [B][Cin][H][W]; w: fp32 [Cout][3][3][Cin]; y: bf16 NHWC [B][H][W][Cout] (pre-BN) + BN statistics.
 template <int CIN>
@@ -374,21 +411,6 @@ __global__ void __launch_bounds__(256) conv3x3_small_fwd_kernel(const float* __r
     uint4* o4 = reinterpret_cast<uint4*>(y + pix * Cout + g * 16);
     o4[0] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
     o4[1] = make_uint4(pack_bf16x2(acc[8], acc[9]), pack_bf16x2(acc[10], acc[11]), pack_bf16x2(acc[12], acc[13]), pack_bf16x2(acc[14], acc[15]));
-    if (sum) {
-#pragma unroll
-      for (int o = 0; o < 16; ++o) {
-        const float r = __bfloat162float(__float2bfloat16(acc[o]));
-        atomicAdd(&s_st[g * 16 + o], r);
-        atomicAdd(&s_st[Cout + g * 16 + o], r * r);
-      }
-    }
-  }
-  if (sum) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < Cout; i += blockDim.x) {
-      atomicAdd(sum + i, s_st[i]);
-      atomicAdd(sumsq + i, s_st[Cout + i]);
-    }
   }
 }
 
@@ -456,21 +478,32 @@ __global__ void linear_finalize_kernel(const float* acc, const float* bias, __nv
   }
 }
 // dz[b][n] = dy[b][n] * dropmask * (relu ? y>0 : 1)  (bf16, ld = ldz) ; db[n] = sum_b dz[b][n] (bf16-rounded values)
-__global__ void linear_bwd_prep_kernel(const float* dacc, const __nv_bfloat16* yout, const uint8_t* mask, __nv_bfloat16* dz,
-                                       float* dbias, int B, int N, int ldy, int ldz, int relu, float drop_p) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// blockDim = (32 columns, 8 row groups): rows are split over threadIdx.y, the bias gradient is combined in smem
+__global__ void __launch_bounds__(256) linear_bwd_prep_kernel(const float* dacc, const __nv_bfloat16* yout, const uint8_t* mask,
+                                                             __nv_bfloat16* dz, float* dbias, int B, int N, int ldy, int ldz,
+                                                             int relu, float drop_p) {
+  __shared__ float s_part[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float s = 0.f;
-  for (int b = 0; b < B; ++b) {
-    float g = dacc[(long long)b * N + n];
-    if (drop_p > 0.f) g = mask[(long long)b * N + n] ? g * keep_scale : 0.f;
-    if (relu && !(__bfloat162float(yout[(long long)b * ldy + n]) > 0.f)) g = 0.f;
-    const __nv_bfloat16 r = __float2bfloat16(g);
-    dz[(long long)b * ldz + n] = r;
-    s += __bfloat162float(r);
+  if (n < N) {
+    for (int b = threadIdx.y; b < B; b += 8) {
+      float g = dacc[(long long)b * N + n];
+      if (drop_p > 0.f) g = mask[(long long)b * N + n] ? g * keep_scale : 0.f;
+      if (relu && !(__bfloat162float(yout[(long long)b * ldy + n]) > 0.f)) g = 0.f;
+      const __nv_bfloat16 r = __float2bfloat16(g);
+      dz[(long long)b * ldz + n] = r;
+      s += __bfloat162float(r);
+    }
   }
-  if (dbias) dbias[n] = s;
+  s_part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N && dbias) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s_part[k][threadIdx.x];
+    dbias[n] = t;
+  }
 }
 // bf16 dropout on a dense activation (VGG layer 46) and its backward
 __global__ void dropout_fwd_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* mask, long long n, float p, uint32_t seed,
@@ -656,6 +689,13 @@ int slb_bn_relu_pool_bwd(const void* dout, const void* y, const float* gamma, co
   return last_err();
 }
 
+int slb_conv_finalize(const float* acc, const float* bias, void* y, float* sum, float* sumsq, long long P, int C, cudaStream_t st) {
+  if (C % 8) return -1;
+  const int tx = C / 8, ty = tx >= 256 ? 1 : 256 / tx;
+  conv_finalize_kernel<<<grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st>>>(
+      acc, bias, reinterpret_cast<__nv_bfloat16*>(y), sum, sumsq, P, C);
+  return last_err();
+}
 int slb_col_stats(const void* y, float* sum, float* sumsq, long long P, int C, cudaStream_t st) {
   if (C % 8) return -1;
   const int tx = C / 8, ty = tx >= 256 ? 1 : 256 / tx;
@@ -700,8 +740,9 @@ int slb_linear_finalize(const float* acc, const float* bias, void* out, float* o
 }
 int slb_linear_bwd_prep(const float* dacc, const void* yout, const uint8_t* mask, void* dz, float* dbias, int B, int N, int ldy,
                         int ldz, int relu, float drop_p, cudaStream_t st) {
-  linear_bwd_prep_kernel<<<(N + 127) / 128, 128, 0, st>>>(dacc, reinterpret_cast<const __nv_bfloat16*>(yout), mask,
-                                                         reinterpret_cast<__nv_bfloat16*>(dz), dbias, B, N, ldy, ldz, relu, drop_p);
+  linear_bwd_prep_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(dacc, reinterpret_cast<const __nv_bfloat16*>(yout), mask,
+                                                               reinterpret_cast<__nv_bfloat16*>(dz), dbias, B, N, ldy, ldz, relu,
+                                                               drop_p);
   return last_err();
 }
 int slb_dropout_fwd(const void* x, void* y, uint8_t* mask, long long n, float p, uint32_t seed, const uint32_t* step_ptr,

@@ -53,7 +53,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded spin: a descriptor/pipeline bug must trap, not hang the GPU box.
 #ifndef SLB_SPIN_LIMIT
-#define SLB_SPIN_LIMIT (1u << 26)
+#define SLB_SPIN_LIMIT (1u << 24)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;

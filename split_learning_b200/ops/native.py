@@ -71,29 +71,67 @@ def _check(code: int, what: str, n: int = 1):
 
 
 # ------------------------------------------------------------------ tensor-core ops
-def conv3x3_fwd(x, w_bf16, y, bias=None, col_sum=None, col_sumsq=None):
-    """x [B,H,W,Cin] bf16, w [Cout,3,3,Cin] bf16 -> y [B,H,W,Cout] bf16 (pre-BN) + optional BN sums."""
+def conv_tiling(M: int, N: int, Ca: int, target_ctas: int = 96):
+    """(block_n, k_split) for the implicit-GEMM conv: these problems are latency- not FLOP-bound at microbatch 32,
+    so spread every layer over ~all SMs — narrow N tiles first, then split K (fp32 vector red.add + finalize)."""
+    m_tiles = (M + 127) // 128
+    bn = 64
+    for cand in (256, 128, 64):
+        if N % cand == 0 and m_tiles * (N // cand) >= target_ctas:
+            bn = cand
+            break
+    bn = min(bn, N)
+    tiles = m_tiles * (N // bn)
+    k_iters = 9 * (Ca // 64)
+    k_split = 1
+    if tiles < target_ctas:
+        k_split = max(1, min((128 + tiles - 1) // tiles, k_iters // 4))
+    return bn, k_split
+
+
+def conv3x3_fwd(x, w_bf16, y, bias=None, col_sum=None, col_sumsq=None, acc=None, tiling=None):
+    """x [B,H,W,Cin] bf16, w [Cout,3,3,Cin] bf16 -> y [B,H,W,Cout] bf16 (pre-BN) + optional BN sums.
+    ``acc``: zeroed fp32 [M, Cout] scratch enabling split-K (then a finalize kernel produces y and the sums)."""
     B, H, W, Cin = x.shape
     Cout = w_bf16.shape[0]
+    bn, ks = tiling or conv_tiling(B * H * W, Cout, Cin)
+    if acc is None:
+        ks = 1
     _check(lib().slb_conv3x3_igemm(_p(x), _p(w_bf16), _p(y), _p(bias), _p(col_sum), _p(col_sumsq), c_int(B), c_int(H),
-                                   c_int(W), c_int(Cin), c_int(Cout), c_int(0), c_int(Cin), c_int(Cout), _stream()),
-           "conv3x3_fwd")
+                                   c_int(W), c_int(Cin), c_int(Cout), c_int(0), c_int(Cin), c_int(Cout), c_int(bn), c_int(ks),
+                                   _p(acc), _stream()), "conv3x3_fwd")
+    if ks > 1:
+        conv_finalize(acc, bias, y, col_sum, col_sumsq)
 
 
-def conv3x3_dgrad(dy, w_bf16, dx):
+def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None):
     """dy [B,H,W,Cout] bf16, w [Cout,3,3,Cin] bf16 -> dx [B,H,W,Cin] bf16."""
     B, H, W, Cout = dy.shape
     Cin = w_bf16.shape[3]
+    bn, ks = tiling or conv_tiling(B * H * W, Cin, Cout)
+    if acc is None:
+        ks = 1
     _check(lib().slb_conv3x3_igemm(_p(dy), _p(w_bf16), _p(dx), _p(None), _p(None), _p(None), c_int(B), c_int(H), c_int(W),
-                                   c_int(Cout), c_int(Cin), c_int(1), c_int(Cin), c_int(Cout), _stream()), "conv3x3_dgrad")
+                                   c_int(Cout), c_int(Cin), c_int(1), c_int(Cin), c_int(Cout), c_int(bn), c_int(ks), _p(acc),
+                                   _stream()), "conv3x3_dgrad")
+    if ks > 1:
+        conv_finalize(acc, None, dx, None, None)
 
 
-def conv3x3_wgrad(x, dy, dw_f32, k_split: int = 0):
-    """dw [Cout,3,3,Cin] fp32 += x^T (*) dy   (caller zeroes dw)."""
+def conv_finalize(acc, bias, y, col_sum, col_sumsq):
+    C = y.shape[-1]
+    P = y.numel() // C
+    _check(lib().slb_conv_finalize(_p(acc), _p(bias), _p(y), _p(col_sum), _p(col_sumsq), c_longlong(P), c_int(C), _stream()),
+           "conv_finalize")
+
+
+def conv3x3_wgrad(x, dy, dw_f32, k_split: int = 0, block_n: int = 0):
+    """dw [Cout,3,3,Cin] fp32 (+)= x^T (*) dy.  Split-K slices accumulate with red.add (caller zeroes dw); a layer
+    whose K fits one slice is written with plain stores."""
     B, H, W, Cin = x.shape
     Cout = dy.shape[3]
     _check(lib().slb_conv3x3_wgrad(_p(x), _p(dy), _p(dw_f32), c_int(B), c_int(H), c_int(W), c_int(Cin), c_int(Cout),
-                                   c_int(k_split), _stream()), "conv3x3_wgrad")
+                                   c_int(k_split), c_int(block_n), _stream()), "conv3x3_wgrad")
 
 
 EPI_ATOMIC, EPI_ATOMIC_T, EPI_STORE = 1, 2, 3
@@ -126,6 +164,43 @@ def linear_wgrad(dz, x, dw_f32):
     out_f = dw_f32.shape[0]
     gemm_bf16(dz, x, dw_f32, out_f, in_f, Bn, 1, 1, dz.stride(0), x.stride(0), dw_f32.stride(0), EPI_STORE, 1,
               256 if in_f >= 256 else 64)
+
+
+_NUM_SMS = {}
+
+
+def num_sms(device=None) -> int:
+    d = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    if d not in _NUM_SMS:
+        _NUM_SMS[d] = torch.cuda.get_device_properties(d).multi_processor_count
+    return _NUM_SMS[d]
+
+
+def conv_bn_act_p2p(x, w_bf16, bias, gamma, beta, running_mean, running_var, nbt, save_mean, save_invstd, col_sum, col_sumsq,
+                    y_opt, out, relu, pool, grid_bar, momentum=0.1, eps=1e-5, update_running=True, flag=None, seq=None,
+                    hint=None):
+    """Fused cut-tail forward: conv3x3 -> batch stats -> grid barrier -> BN+ReLU(+pool) out of TMEM -> store into
+    ``out`` (local or peer mailbox slot) -> publish flag.  ``y_opt``: optional local copy of the pre-BN output."""
+    B, H, W, Cin = x.shape
+    Cout = w_bf16.shape[0]
+    _check(lib().slb_conv_bn_act_p2p(_p(x), _p(w_bf16), _p(bias), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                                     _p(nbt), _p(save_mean), _p(save_invstd), _p(col_sum), _p(col_sumsq), _p(y_opt), _p(out),
+                                     c_int(B), c_int(H), c_int(W), c_int(Cin), c_int(Cout), c_int(int(relu)), c_int(int(pool)),
+                                     c_float(momentum), c_float(eps), c_int(int(update_running)), _p(grid_bar), _p(flag),
+                                     _p(seq), _p(hint), c_int(num_sms(x.device)), _stream()), "conv_bn_act_p2p")
+
+
+def fused_cut_supported(B, H, W, Cin, Cout, pool) -> bool:
+    if Cin % 64 or Cout % 64 or 128 % W:
+        return False
+    rows = 128 // W
+    th = rows if rows <= H else H
+    if pool and ((th & 1) or (H & 1) or (W & 1)):
+        return False
+    bn = 256 if Cout >= 256 else Cout
+    total = ((B * H * W + 127) // 128) * (Cout // bn)
+    grid = min(total, 148)
+    return (total + grid - 1) // grid <= 512 // bn
 
 
 # ------------------------------------------------------------------ memory-bound ops

@@ -62,14 +62,16 @@ def conv_fwd():
         y = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
         s1 = torch.zeros(Cout, device="cuda")
         s2 = torch.zeros(Cout, device="cuda")
-        N.conv3x3_fwd(x, w, y, bias, s1, s2)
+        bn_, ks_ = N.conv_tiling(B * H * W, Cout, Cin)
+        acc = torch.zeros(B * H * W, Cout, device="cuda") if ks_ > 1 else None
+        N.conv3x3_fwd(x, w, y, bias, s1, s2, acc=acc)
         torch.cuda.synchronize()
         ref = _ref_conv(x, w, bias)
         e = _rel(y, ref)
         yb = y.float().reshape(-1, Cout)
         e1 = _rel(s1, yb.sum(0))
         e2 = _rel(s2, (yb * yb).sum(0))
-        print(f"  conv_fwd {B}x{H}x{W} {Cin}->{Cout}: y {e:.2e} sum {e1:.2e} sumsq {e2:.2e}")
+        print(f"  conv_fwd {B}x{H}x{W} {Cin}->{Cout} bn={bn_} ksplit={ks_}: y {e:.2e} sum {e1:.2e} sumsq {e2:.2e}")
         worst = max(worst, e, e1, e2)
     return worst, 1.5e-2
 
@@ -81,7 +83,9 @@ def conv_dgrad():
         x, w, _ = _conv_case(B, H, W, Cin, Cout)
         dy = _bf(torch.randn(B, H, W, Cout, device="cuda"))
         dx = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.bfloat16)
-        N.conv3x3_dgrad(dy, w, dx)
+        bn_, ks_ = N.conv_tiling(B * H * W, Cin, Cout)
+        acc = torch.zeros(B * H * W, Cin, device="cuda") if ks_ > 1 else None
+        N.conv3x3_dgrad(dy, w, dx, acc=acc)
         torch.cuda.synchronize()
         xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
         F.conv2d(xr, w.float().permute(0, 3, 1, 2), None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
@@ -183,6 +187,49 @@ def bn_fwd_bwd():
 
 
 @check
+def fused_cut_tail():
+    """conv+BN+ReLU+pool fused kernel vs torch (the cut blocks of cuts 7, 14, 10, 5)."""
+    worst = 0.0
+    for (B, H, W, Cin, Cout, relu, pool) in [(32, 32, 32, 64, 64, 1, 1), (32, 16, 16, 128, 128, 1, 1), (32, 16, 16, 64, 128, 1, 0),
+                                             (32, 32, 32, 64, 64, 0, 0), (8, 32, 32, 64, 64, 1, 1), (32, 8, 8, 256, 256, 1, 1)]:
+        assert N.fused_cut_supported(B, H, W, Cin, Cout, pool)
+        x, w, bias = _conv_case(B, H, W, Cin, Cout, seed=5)
+        gamma = torch.rand(Cout, device="cuda") + 0.5
+        beta = torch.randn(Cout, device="cuda") * 0.1
+        rm, rv = torch.zeros(Cout, device="cuda"), torch.ones(Cout, device="cuda")
+        nbt = torch.zeros((), device="cuda", dtype=torch.int64)
+        sm, si = torch.empty(Cout, device="cuda"), torch.empty(Cout, device="cuda")
+        s1, s2 = torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
+        OH, OW = (H // 2, W // 2) if pool else (H, W)
+        out = torch.zeros(B, OH, OW, Cout, device="cuda", dtype=torch.bfloat16)
+        y = torch.zeros(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+        bar = torch.zeros(4, device="cuda", dtype=torch.int32)
+        flag = torch.zeros(4, device="cuda", dtype=torch.int32)
+        for rep in range(2):                      # second launch re-uses the barrier words (generation logic)
+            s1.zero_(); s2.zero_()
+            N.conv_bn_act_p2p(x, w, bias, gamma, beta, rm, rv, nbt, sm, si, s1, s2, y, out, relu, pool, bar,
+                              flag=flag[0:1], seq=flag[1:2])
+            torch.cuda.synchronize()
+        bn = torch.nn.BatchNorm2d(Cout).cuda().train()
+        with torch.no_grad():
+            bn.weight.copy_(gamma); bn.bias.copy_(beta)
+        conv = _ref_conv(x, w, bias).permute(0, 3, 1, 2)
+        z = bn(conv); bn(conv)
+        if relu:
+            z = F.relu(z)
+        if pool:
+            z = F.max_pool2d(z, 2, 2)
+        e1 = _rel(out, z.permute(0, 2, 3, 1))
+        e2 = _rel(y, conv.permute(0, 2, 3, 1))
+        e3 = max(_rel(rm, bn.running_mean), _rel(rv, bn.running_var))
+        print(f"  fused cut {B}x{H}x{W} {Cin}->{Cout} relu={relu} pool={pool}: out {e1:.2e} y {e2:.2e} running {e3:.2e} "
+              f"flag={flag[:2].tolist()} nbt={int(nbt)}")
+        assert flag[:2].tolist() == [2, 2] and int(nbt) == 2
+        worst = max(worst, e1, e2, e3)
+    return worst, 2e-2
+
+
+@check
 def conv1_direct():
     torch.manual_seed(2)
     B, Cin, H, W, Cout = 32, 3, 32, 32, 64
@@ -191,7 +238,8 @@ def conv1_direct():
     bias = torch.randn(Cout, device="cuda")
     y = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
     s1, s2 = torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
-    N.conv3x3_small_fwd(x, w, bias, y, s1, s2)
+    N.conv3x3_small_fwd(x, w, bias, y)
+    N.col_stats(y.view(-1, Cout), s1, s2)
     torch.cuda.synchronize()
     wr = w.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
     ref = F.conv2d(x, wr, bias, padding=1)

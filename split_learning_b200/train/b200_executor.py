@@ -165,7 +165,7 @@ def _align(n: int, a: int = 128) -> int:
 # ----------------------------------------------------------------------------- executor
 class B200Executor(StageExecutor):
     def __init__(self, model: SplitModel, model_name: str, learning: dict, device, is_first=False, is_last=False,
-                 recompute: bool = True, use_graphs: bool = True, seed: int = 1234):
+                 recompute: bool = True, use_graphs: bool = True, seed: int = 1234, fused_cut: bool = True):
         N.require()
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
@@ -175,6 +175,7 @@ class B200Executor(StageExecutor):
         self.is_first, self.is_last = is_first, is_last
         self.recompute = recompute
         self.use_graphs = use_graphs
+        self.fused_cut = fused_cut
         self.lr = float(learning.get("learning-rate", 0.01))
         self.mu = float(learning.get("momentum", 0.0))
         self.seed = seed
@@ -383,9 +384,16 @@ class _Plan:
             self.soff[key] = (scratch, n)
             scratch += _align(n, 4)
         for bi, b in enumerate(ex.blocks):
-            if isinstance(b, ConvBlock) and b.bn is not None:
-                reserve((bi, "sum"), b.cout)
-                reserve((bi, "sumsq"), b.cout)
+            if isinstance(b, ConvBlock):
+                if b.bn is not None:
+                    reserve((bi, "sum"), b.cout)
+                    reserve((bi, "sumsq"), b.cout)
+                if b.conv is not None and b.cin > 4:
+                    M = B * b.H * b.W
+                    if N.conv_tiling(M, b.cout, b.cin)[1] > 1:
+                        reserve((bi, "facc"), M * b.cout)           # split-K partial sums, forward
+                    if N.conv_tiling(M, b.cin, b.cout)[1] > 1 and not (bi == 0 and ex.is_first):
+                        reserve((bi, "dacc"), M * b.cin)            # split-K partial sums, dgrad
             elif isinstance(b, LinearBlock):
                 reserve((bi, "acc"), B * b.fout)
                 reserve((bi, "dacc_in"), B * b.fin)
@@ -466,7 +474,9 @@ class _Plan:
                 plain = b.conv is not None and b.bn is None          # cut right after the conv (e.g. cut 4)
                 if plain:
                     tgt = a["y"] if not (is_final and out_ptr_override is not None) else out_ptr_override
-                    N.conv3x3_fwd(x, ex.view(ex.PB, f"layer{b.conv}.weight"), tgt, ex.view(ex.P, f"layer{b.conv}.bias"))
+                    facc = self.s(bi, "facc") if (bi, "facc") in self.soff else None
+                    N.conv3x3_fwd(x, ex.view(ex.PB, f"layer{b.conv}.weight"), tgt, ex.view(ex.P, f"layer{b.conv}.bias"),
+                                  acc=facc)
                     if is_final and publish is not None:
                         N.set_flag(publish["flag"].data_ptr() if hasattr(publish["flag"], "data_ptr") else publish["flag"],
                                    0, publish["seq"], publish.get("hint_ptr", 0))
@@ -474,13 +484,35 @@ class _Plan:
                     a["y_eff"] = a["y"]
                     x = tgt
                     continue
+                fuse = (ex.fused_cut and is_final and out_ptr_override is not None and b.conv is not None and b.bn is not None
+                        and b.cin > 4 and N.fused_cut_supported(self.B, b.H, b.W, b.cin, b.cout, b.pool))
+                if fuse:
+                    # cut-tail kernel: GEMM + BN statistics + BN/ReLU/pool + store into the (peer) mailbox + flag
+                    st = ex.bn_state[b.bn]
+                    bar = a.get("grid_bar")
+                    if bar is None:
+                        bar = a["grid_bar"] = torch.zeros(4, device=ex.device, dtype=torch.int32)
+                    keep_y = a["y"] if not ex.recompute or ex.is_last else None
+                    kw = {}
+                    if publish is not None:
+                        kw = dict(flag=publish["flag"], seq=publish["seq"], hint=publish.get("hint"))
+                    N.conv_bn_act_p2p(x, ex.view(ex.PB, f"layer{b.conv}.weight"), ex.view(ex.P, f"layer{b.conv}.bias"),
+                                      ex.view(ex.P, f"layer{b.bn}.weight"), ex.view(ex.P, f"layer{b.bn}.bias"),
+                                      st["running_mean"], st["running_var"], st["num_batches_tracked"], a["save_mean"],
+                                      a["save_invstd"], self.s(bi, "sum"), self.s(bi, "sumsq"), keep_y, out_ptr_override,
+                                      b.relu, b.pool, bar, **kw)
+                    a["y_eff"] = a["y"]
+                    x = out_ptr_override
+                    continue
                 if b.conv is not None:
                     s1, s2 = self.s(bi, "sum"), self.s(bi, "sumsq")
                     bias = ex.view(ex.P, f"layer{b.conv}.bias")
                     if b.cin <= 4:
-                        N.conv3x3_small_fwd(x, ex.view(ex.P, f"layer{b.conv}.weight"), bias, a["y"], s1, s2)
+                        N.conv3x3_small_fwd(x, ex.view(ex.P, f"layer{b.conv}.weight"), bias, a["y"])
+                        N.col_stats(a["y"].reshape(-1, b.cout), s1, s2)
                     else:
-                        N.conv3x3_fwd(x, ex.view(ex.PB, f"layer{b.conv}.weight"), a["y"], bias, s1, s2)
+                        facc = self.s(bi, "facc") if (bi, "facc") in self.soff else None
+                        N.conv3x3_fwd(x, ex.view(ex.PB, f"layer{b.conv}.weight"), a["y"], bias, s1, s2, acc=facc)
                     y = a["y"]
                 else:
                     y = x
@@ -563,14 +595,18 @@ class _Plan:
                     N.bn_relu_pool_bwd(g, y, None, None, a["save_mean"], a["save_invstd"], None, None, dy, b.H, b.W,
                                        b.relu, b.pool, identity=True)
                 if b.conv is not None:
-                    N.col_stats(dy.reshape(-1, b.cout), ex.view(ex.G, f"layer{b.conv}.bias"), None)
+                    if b.bn is None:
+                        N.col_stats(dy.reshape(-1, b.cout), ex.view(ex.G, f"layer{b.conv}.bias"), None)
+                    # else: a conv bias feeding train-mode BatchNorm has an identically zero gradient
+                    # (sum_p dy = gamma*invstd*(sum dz - P*mean(dz) - mean(dz*xhat)*sum xhat) = 0): G stays 0.
                     if b.cin <= 4:
                         N.conv3x3_small_wgrad(a["in"], dy, ex.view(ex.G, f"layer{b.conv}.weight"))
                     else:
                         N.conv3x3_wgrad(a["in"], dy, ex.view(ex.G, f"layer{b.conv}.weight"))
                         if need_dx:
                             dx = a["dx"] if not (bi == 0 and grad_out_override is not None) else grad_out_override
-                            N.conv3x3_dgrad(dy, ex.view(ex.PB, f"layer{b.conv}.weight"), dx)
+                            dacc = self.s(bi, "dacc") if (bi, "dacc") in self.soff else None
+                            N.conv3x3_dgrad(dy, ex.view(ex.PB, f"layer{b.conv}.weight"), dx, acc=dacc)
                             g = dx
                 else:
                     g = dy

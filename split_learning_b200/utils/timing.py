@@ -1,0 +1,54 @@
+"""Timing / liveness helpers used by trainers, benchmarks and tools."""
+from __future__ import annotations
+
+import threading
+import time
+from typing import Callable, Optional
+
+
+class CudaTimer:
+    """CUDA-event stopwatch on the current stream (``with CudaTimer() as t: ...; t.ms``)."""
+
+    def __init__(self):
+        import torch
+        self._torch = torch
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e1 = torch.cuda.Event(enable_timing=True)
+        self.ms = 0.0
+
+    def __enter__(self):
+        self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        self.e1.record()
+        self.e1.synchronize()
+        self.ms = self.e0.elapsed_time(self.e1)
+        return False
+
+
+class Watchdog:
+    """Fires ``on_timeout`` when ``kick()`` has not been called for ``seconds`` (failure detection:
+    the reference dead-locks silently when a client dies)."""
+
+    def __init__(self, seconds: float, on_timeout: Callable[[], None]):
+        self.seconds, self.on_timeout = seconds, on_timeout
+        self._last = time.monotonic()
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def start(self):
+        self._t.start()
+        return self
+
+    def kick(self):
+        self._last = time.monotonic()
+
+    def stop(self):
+        self._stop.set()
+
+    def _run(self):
+        while not self._stop.wait(min(1.0, self.seconds / 4)):
+            if time.monotonic() - self._last > self.seconds:
+                self.on_timeout()
+                return
