@@ -53,7 +53,7 @@ def main():
         return
     extra = {k: v for k, v in (("idx", args.idx), ("in_cluster", args.incluster),
                                ("out_cluster", args.outcluster), ("select", args.select)) if v is not None}
-    client = client_class(cfg.b200.get("algorithm", "main"))(client_id, args.layer_id, channel, device, b200_opts=cfg.b200)
+    client = client_class(cfg.b200.get("algorithm", "main"), cfg.b200)(client_id, args.layer_id, channel, device, b200_opts=cfg.b200)
     print_with_color("[>>>] Client sending registration message to server...", "red")
     client.register(profile, -1 if args.cluster is None else args.cluster, **extra)
     client.wait_response()

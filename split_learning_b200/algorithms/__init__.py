@@ -12,10 +12,15 @@ def server_class(name: str = "main"):
     return variants.SERVERS[name]
 
 
-def client_class(name: str = "main"):
+def client_class(name: str = "main", opts=None):
+    """``opts``: the ``b200`` config section; ``data-plane: device`` selects the peer-memory client for the main
+    algorithm (activations/gradients through NVLink mailboxes instead of broker queues)."""
     from ..client import RpcClient
     name = (name or "main").lower()
     if name == "main":
+        if opts and str(opts.get("data-plane", "host")).lower() == "device":
+            from ..parallel.device_client import DeviceRpcClient
+            return DeviceRpcClient
         return RpcClient
     from . import variants
     return variants.CLIENTS[name]

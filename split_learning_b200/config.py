@@ -36,6 +36,7 @@ DEFAULT_B200 = {
     "watchdog-seconds": 120.0,     # replaces the reference's silent deadlock
     "synthetic-data": False,
     "routing": "round-robin",      # competing-consumer emulation on the device plane
+    "data-plane": "host",          # host = broker queues (any device) | device = peer-memory mailboxes (CUDA)
 }
 
 

@@ -635,6 +635,22 @@ using namespace slb;
 
 extern "C" {
 
+int slb_preload_elementwise() {
+  cudaFuncAttributes a;
+  int bad = 0;
+#define SLB_PRELOAD(k) bad += (cudaFuncGetAttributes(&a, k) != cudaSuccess)
+  SLB_PRELOAD(zero_kernel); SLB_PRELOAD(wait_flag_kernel); SLB_PRELOAD(set_flag_kernel); SLB_PRELOAD(counter_inc_kernel);
+  SLB_PRELOAD(bn_relu_pool_fwd_kernel); SLB_PRELOAD(bn_bwd_reduce_kernel<true>); SLB_PRELOAD(bn_bwd_reduce_kernel<false>);
+  SLB_PRELOAD(bn_bwd_apply_kernel<true>); SLB_PRELOAD(bn_bwd_apply_kernel<false>); SLB_PRELOAD(col_stats_kernel);
+  SLB_PRELOAD(conv_finalize_kernel); SLB_PRELOAD(conv3x3_small_fwd_kernel<3>); SLB_PRELOAD(conv3x3_small_fwd_kernel<1>);
+  SLB_PRELOAD(conv3x3_small_wgrad_kernel<3>); SLB_PRELOAD(conv3x3_small_wgrad_kernel<1>); SLB_PRELOAD(linear_finalize_kernel);
+  SLB_PRELOAD(linear_bwd_prep_kernel); SLB_PRELOAD(dropout_fwd_kernel); SLB_PRELOAD(dropout_bwd_kernel);
+  SLB_PRELOAD(ce_fwd_bwd_kernel); SLB_PRELOAD(sgd_momentum_kernel); SLB_PRELOAD(adamw_kernel); SLB_PRELOAD(cast_f32_bf16_kernel);
+  SLB_PRELOAD(fedavg_kernel);
+#undef SLB_PRELOAD
+  return bad;
+}
+
 int slb_zero(void* p, long long bytes, cudaStream_t st) {
   if (bytes % 16) return -1;
   zero_kernel<<<grid_for(bytes / 16, 256), 256, 0, st>>>(reinterpret_cast<float4*>(p), bytes / 16);

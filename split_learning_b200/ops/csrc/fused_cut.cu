@@ -361,6 +361,15 @@ using namespace slb;
 
 extern "C" {
 
+int slb_preload_fused() {
+  cudaFuncAttributes a;
+  int bad = 0;
+  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<64>) != cudaSuccess;
+  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<128>) != cudaSuccess;
+  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<256>) != cudaSuccess;
+  return bad;
+}
+
 // Fused cut-tail forward.  x [B,H,W,Cin] bf16, w [Cout][3][3][Cin] bf16.  `out` may be a peer pointer.
 // `grid_bar`: 4 zero-initialised uint32 owned by this call site.  sum/sumsq: zeroed by the caller.
 int slb_conv_bn_act_p2p(const void* x, const void* w, const float* bias, const float* gamma, const float* beta,

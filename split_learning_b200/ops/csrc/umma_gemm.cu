@@ -400,6 +400,12 @@ static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const
   }
 }
 
+template <int MODE, int BN>
+static int preload_one() {
+  cudaFuncAttributes a;
+  return cudaFuncGetAttributes(&a, umma_gemm_kernel<MODE, BN>) == cudaSuccess ? 0 : 1;
+}
+
 static void pixel_box(int H, int W, int pixels, int* tb, int* th, int* tw) {
   *tw = W;
   int rows = pixels / W;           // full-width rows in the tile
@@ -412,6 +418,16 @@ static void pixel_box(int H, int W, int pixels, int* tb, int* th, int* tw) {
 using namespace slb;
 
 extern "C" {
+
+// Force-load every instantiation (CUDA lazy loading would otherwise load a kernel at its first launch, which can
+// block behind a running flag-spinning kernel of a sibling stage sharing the GPU).
+int slb_preload_gemm() {
+  int bad = 0;
+  bad += preload_one<MODE_CONV, 64>() + preload_one<MODE_CONV, 128>() + preload_one<MODE_CONV, 256>() + preload_one<MODE_CONV, 32>();
+  bad += preload_one<MODE_WGRAD, 64>() + preload_one<MODE_WGRAD, 128>() + preload_one<MODE_WGRAD, 256>() + preload_one<MODE_WGRAD, 32>();
+  bad += preload_one<MODE_GEMM, 32>() + preload_one<MODE_GEMM, 64>() + preload_one<MODE_GEMM, 128>() + preload_one<MODE_GEMM, 256>();
+  return bad;
+}
 
 // y[B,H,W,Cout] (bf16, pre-BN) = conv3x3(x[B,H,W,Cin], w[Cout][3][3][Cin]) + bias ; optional per-channel
 // sum / sum-of-squares accumulation (caller zeroes them).  flip=1 computes the input gradient:

@@ -38,6 +38,21 @@ def lib():
     return _lib
 
 
+_preloaded = set()
+
+
+def preload(device=None) -> None:
+    """Load every kernel of the library on ``device`` now (see slb_preload_* for why)."""
+    d = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    if d in _preloaded:
+        return
+    with torch.cuda.device(d):
+        bad = lib().slb_preload_gemm() + lib().slb_preload_fused() + lib().slb_preload_elementwise()
+    if bad:
+        raise NativeError(f"{bad} kernels failed to load (wrong GPU architecture? this library is sm_100a only)")
+    _preloaded.add(d)
+
+
 def require():
     """Fail loudly when CUDA is present but the kernel library is not."""
     if torch.cuda.is_available():

@@ -1,0 +1,152 @@
+"""Client FSM with the device data plane: the same START / READY / SYN / NOTIFY / PAUSE / UPDATE
+conversation as ``client.RpcClient`` (the user-facing API), but activations and gradients move
+through peer-memory mailboxes written by the stage kernels instead of broker queues.
+
+Wiring happens while handling START: every client allocates the mailboxes it *consumes*
+(activations from upstream, gradients from downstream), exports them with CUDA IPC and posts
+the 64-byte handles to its chain partner's ``ipc_{client_id}`` queue; partners are derived
+from the START ``peers`` table (stage s member i <-> stage s+1 member i — the static pairing of
+the reference's competing-consumer queue).  If replica counts differ between adjacent stages,
+or the stage has no native plan, the client silently keeps the host data plane — that is a
+*topology* fallback (documented), never a kernel fallback.
+
+Only full microbatches go through the device plane (mailbox geometry is static): a trailing
+partial batch of the loader is dropped, which the reference's sample counts (multiples of the
+batch size) never produce.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import messages as M
+from ..client import RpcClient
+from ..log import print_with_color
+from .mailbox import Mailbox, MailboxSpec
+from .pipeline import DeviceStage
+
+
+class DeviceRpcClient(RpcClient):
+    def on_start(self, msg: dict) -> None:
+        self.dstage: Optional[DeviceStage] = None
+        super_ready = self.send_to_server
+        sent: List[dict] = []
+        self.send_to_server = lambda m: sent.append(m)       # hold READY until the mailboxes are wired
+        try:
+            super().on_start(msg)
+        finally:
+            self.send_to_server = super_ready
+        try:
+            self._wire(msg)
+        except Exception as e:          # topology not supported on the device plane → host plane
+            print_with_color(f"[device plane] falling back to host data plane: {e}", "yellow")
+            self.dstage = None
+        for m in sent:
+            self.send_to_server(m)
+
+    # ------------------------------------------------------------------
+    def _partners(self, msg: dict):
+        members: Dict[int, list] = msg["peers"]["members"]
+        me = [cid for cid, _ in members[self.layer_id]].index(str(self.client_id))
+        up = down = None
+        if self.layer_id > 1:
+            ups = members[self.layer_id - 1]
+            if len(ups) != len(members[self.layer_id]):
+                raise RuntimeError("unequal replica counts between adjacent stages")
+            up = ups[me][0]
+        if self.layer_id < self.num_layers:
+            downs = members[self.layer_id + 1]
+            if len(downs) != len(members[self.layer_id]):
+                raise RuntimeError("unequal replica counts between adjacent stages")
+            down = downs[me][0]
+        return up, down
+
+    def _wire(self, msg: dict) -> None:
+        from ..train.b200_executor import B200Executor
+        if not isinstance(self.executor, B200Executor) or self.num_layers < 2:
+            raise RuntimeError("stage has no native plan")
+        ex = self.executor
+        B = int(self.learning["batch-size"])
+        depth = int(self.learning.get("control-count", 3))
+        up, down = self._partners(msg)
+        dev = ex.device
+        fwd_in = grad_in = fwd_out = grad_out = None
+        my_q = f"ipc_{self.client_id}"
+        self.channel.queue_declare(my_q)
+        if up is not None:                                     # I consume activations
+            c, h, w = ex.in_shape
+            spec_in = MailboxSpec(depth, B, (B, h, w, c))
+            fwd_in, hdl = Mailbox.allocate_exportable(spec_in, dev)
+            self.channel.publish_obj(f"ipc_{up}", {"kind": "act", "handle": hdl, "shape": spec_in.payload_shape})
+        if down is not None:                                   # I consume gradients of my output
+            c, h, w = ex.out_shape
+            spec_out = MailboxSpec(depth, B, (B, h, w, c))
+            grad_in, hdl = Mailbox.allocate_exportable(spec_out, dev)
+            self.channel.publish_obj(f"ipc_{down}", {"kind": "grad", "handle": hdl, "shape": spec_out.payload_shape})
+        need = int(up is not None) + int(down is not None)
+        t0 = time.monotonic()
+        while need:
+            m = self.channel.get_obj(my_q, 0.25)
+            if m is None:
+                if time.monotonic() - t0 > self.watchdog:
+                    raise TimeoutError("peer never posted its IPC handle")
+                continue
+            spec = MailboxSpec(depth, B, tuple(m["shape"]))
+            mb = Mailbox.open_peer(spec, m["handle"], dev)
+            if m["kind"] == "act":                             # my downstream's activation ring: I produce into it
+                fwd_out = mb
+            else:                                              # my upstream's gradient ring
+                grad_out = mb
+            need -= 1
+        self.dstage = DeviceStage(ex, B, depth, fwd_in=fwd_in, grad_in=grad_in, fwd_out=fwd_out, grad_out=grad_out)
+        self._down, self._up = down, up
+
+    # ------------------------------------------------------------------
+    def run_stage(self):
+        if self.dstage is None:
+            return super().run_stage()
+        st, B = self.dstage, self.dstage.B
+        ex = self.executor
+        plan_q = f"plan_{self.client_id}"
+        if self.is_first:
+            batches = []
+            for batch in self.train_loader:
+                x, y = batch if not isinstance(batch, dict) else (batch["input_ids"], batch["labels"])
+                if x.shape[0] == B:
+                    batches.append((x.float().pin_memory(), torch.as_tensor(y).long().pin_memory()))
+            n = len(batches)
+            self.channel.publish_obj(f"plan_{self._down}", {"batches": n})
+        else:
+            t0 = time.monotonic()
+            while True:
+                m = self.channel.get_obj(plan_q, 0.25)
+                if m is not None:
+                    n = int(m["batches"])
+                    break
+                if time.monotonic() - t0 > self.watchdog:
+                    raise TimeoutError("upstream never announced its batch count")
+            if not self.is_last:
+                self.channel.publish_obj(f"plan_{self._down}", {"batches": n})
+        if self.is_last:
+            for it in range(n):
+                st.last(it)
+        else:
+            it_b = 0
+            for it in range(n):
+                if it - it_b >= st.depth:
+                    st.backward(it_b)
+                    it_b += 1
+                if self.is_first:
+                    st.stage_input(it, *batches[it])
+                st.forward(it)
+            while it_b < n:
+                st.backward(it_b)
+                it_b += 1
+        st.stream.synchronize()
+        st.check()
+        if self.is_first:
+            self.send_to_server(M.notify(self.client_id, self.layer_id, self.cluster))
+        self.trainer._wait_pause()
+        return (not ex.nan_detected()), n

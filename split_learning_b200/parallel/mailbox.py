@@ -41,6 +41,36 @@ def tensor_from_ptr(ptr: int, nbytes: int, device) -> torch.Tensor:
     return torch.as_tensor(_RawCuda(ptr, nbytes), device=device)
 
 
+class DevPtr:
+    """A typed view of raw device memory that is NOT a torch tensor (peer-mapped IPC memory must never be touched
+    by torch ops — they would run on, or copy from, the exporting device).  Kernels only need ``data_ptr()``."""
+
+    def __init__(self, ptr: int, shape, itemsize: int):
+        self._ptr, self.shape, self.itemsize = int(ptr), tuple(shape), itemsize
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+    def numel(self) -> int:
+        n = 1
+        for d in self.shape:
+            n *= d
+        return n
+
+    def element_size(self) -> int:
+        return self.itemsize
+
+    def reshape(self, *shape):
+        shape = shape[0] if len(shape) == 1 and isinstance(shape[0], (tuple, list)) else shape
+        if -1 in shape:
+            known = 1
+            for d in shape:
+                if d != -1:
+                    known *= d
+            shape = tuple(self.numel() // known if d == -1 else d for d in shape)
+        return DevPtr(self._ptr, shape, self.itemsize)
+
+
 @dataclass
 class MailboxSpec:
     depth: int
@@ -72,13 +102,22 @@ class MailboxSpec:
         return self.header_off + 256
 
 
+_SAME_PROCESS = {}          # IPC handle -> raw pointer, for partners that live in this very process (threads)
+
+
 class Mailbox:
     """View of a mailbox allocation (owner side or a peer-mapped producer side)."""
 
-    def __init__(self, spec: MailboxSpec, base: torch.Tensor, owner: bool, raw_ptr: Optional[int] = None):
+    def __init__(self, spec: MailboxSpec, base: Optional[torch.Tensor], owner: bool, raw_ptr: Optional[int] = None):
         self.spec, self.base, self.owner = spec, base, owner
         self.raw_ptr = raw_ptr if raw_ptr is not None else base.data_ptr()
         d = spec.depth
+        if base is None:                     # peer-mapped: raw pointer views only
+            self.payload = [DevPtr(self.raw_ptr + s * spec.payload_bytes, spec.payload_shape, 2) for s in range(d)]
+            self.labels = [DevPtr(self.raw_ptr + spec.labels_off + s * spec.batch * 8, (spec.batch,), 8) for s in range(d)]
+            self.flags = None
+            self.header = None
+            return
         self.payload: List[torch.Tensor] = []
         for s in range(d):
             nb = 2
@@ -113,18 +152,20 @@ class Mailbox:
         if rc != 0:
             raise N.NativeError(f"cudaIpcGetMemHandle failed: {rc}")
         base = tensor_from_ptr(ptr.value, spec.total_bytes, device)
+        _SAME_PROCESS[bytes(handle)] = ptr.value
         return Mailbox(spec, base, owner=True, raw_ptr=ptr.value), bytes(handle)
 
     @staticmethod
     def open_peer(spec: MailboxSpec, handle: bytes, device) -> "Mailbox":
+        if handle in _SAME_PROCESS:            # cudaIpcOpenMemHandle refuses handles exported by the same process
+            return Mailbox(spec, None, owner=False, raw_ptr=_SAME_PROCESS[handle])
         lib = N.lib()
         ptr = ctypes.c_void_p()
         buf = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
         rc = lib.slb_ipc_open(buf, ctypes.byref(ptr))
         if rc != 0:
             raise N.NativeError(f"cudaIpcOpenMemHandle failed: {rc}")
-        base = tensor_from_ptr(ptr.value, spec.total_bytes, device)
-        return Mailbox(spec, base, owner=False, raw_ptr=ptr.value)
+        return Mailbox(spec, None, owner=False, raw_ptr=ptr.value)
 
 
 class EdgeCounters:

@@ -26,6 +26,7 @@ import torch
 
 from ..ops import native as N
 from ..train.b200_executor import B200Executor
+from ..utils.timing import capture_graph
 from .mailbox import EdgeCounters, Mailbox, MailboxSpec
 
 
@@ -113,10 +114,7 @@ class DeviceStage:
                     self.launches_per[kind] = N.LAUNCHES - before
                     self._warmed.add(kind)
                     return
-                self.stream.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self.stream):
-                    body(slot)
+                g = capture_graph(self.stream, lambda: body(slot))
                 self.graphs[key] = g
             g.replay()
 

@@ -44,7 +44,7 @@ def run_inproc(cfg: Config, devices: Optional[Sequence[str]] = None, profiles: O
     clients = []
     for r, (layer_id, cluster, _i) in enumerate(ranks):
         dev = devices[r % len(devices)] if devices else "cpu"
-        cli = client_class(algo)(str(uuid.uuid4()), layer_id, broker, device=dev, b200_opts=cfg.b200, rank=r,
+        cli = client_class(algo, cfg.b200)(str(uuid.uuid4()), layer_id, broker, device=dev, b200_opts=cfg.b200, rank=r,
                                  **(client_kwargs or {}))
         prof = profiles[r] if profiles else dict(DEFAULT_PROFILE)
         clients.append(cli)
@@ -88,7 +88,7 @@ def run_variant(cfg: Config, client_specs: Sequence[dict], workdir: str = ".", t
         layer_id = spec.pop("layer_id")
         cluster = spec.pop("cluster", -1)
         dev = devices[r % len(devices)] if devices else "cpu"
-        cli = client_class(algo)(str(uuid.uuid4()), layer_id, broker, device=dev, b200_opts=cfg.b200, rank=r)
+        cli = client_class(algo, cfg.b200)(str(uuid.uuid4()), layer_id, broker, device=dev, b200_opts=cfg.b200, rank=r)
 
         def body(cli=cli, cluster=cluster, spec=spec):
             cli.register(dict(DEFAULT_PROFILE), cluster, **spec)

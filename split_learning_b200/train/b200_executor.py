@@ -169,6 +169,7 @@ class B200Executor(StageExecutor):
         N.require()
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
+        N.preload(self.device)
         self.model_cls = type(model)
         self.start_layer, self.end_layer = model.start_layer, model.end_layer
         self.model_name = model_name
@@ -289,6 +290,12 @@ class B200Executor(StageExecutor):
         """Tensor-API calls may hand us tensors produced on the caller's stream."""
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
 
+    def _grad_to_wire(self, gi: torch.Tensor) -> torch.Tensor:
+        if self.in_kind == "image":
+            c, h, w = self.in_shape
+            return gi.reshape(gi.shape[0], h, w, c).permute(0, 3, 1, 2).float().contiguous()
+        return gi.float()
+
     def forward_only(self, data_id, x) -> torch.Tensor:
         xi = self._to_internal(x)
         B = xi.shape[0]
@@ -316,8 +323,7 @@ class B200Executor(StageExecutor):
             pl.run_backward(slot)
             res = None
             if not self.is_first:
-                gi = pl.input_grad()
-                res = gi.permute(0, 3, 1, 2).float().contiguous() if self.in_kind == "image" else gi.float()
+                res = self._grad_to_wire(pl.input_grad())
         self.stream.synchronize()
         pl.release_slot(slot)
         return res
@@ -334,8 +340,7 @@ class B200Executor(StageExecutor):
             pl.run_last()
             res = None
             if not self.is_first:
-                gi = pl.input_grad()
-                res = gi.permute(0, 3, 1, 2).float().contiguous() if self.in_kind == "image" else gi.float()
+                res = self._grad_to_wire(pl.input_grad())
         self.stream.synchronize()
         return res
 
@@ -659,10 +664,7 @@ class _Plan:
             self._warm = True
             return
         # second call onwards for this key: capture, then replay (capture itself does not execute)
-        g = torch.cuda.CUDAGraph()
-        cur = torch.cuda.current_stream()
-        cur.synchronize()
-        with torch.cuda.graph(g, stream=cur):
-            fn()
+        from ..utils.timing import capture_graph
+        g = capture_graph(torch.cuda.current_stream(), fn)
         self.graphs[key] = g
         g.replay()

@@ -1,4 +1,4 @@
 """Small shared helpers."""
-from .timing import CudaTimer, Watchdog
+from .timing import CudaTimer, Watchdog, capture_graph
 
-__all__ = ["CudaTimer", "Watchdog"]
+__all__ = ["CudaTimer", "Watchdog", "capture_graph"]

@@ -52,3 +52,26 @@ class Watchdog:
             if time.monotonic() - self._last > self.seconds:
                 self.on_timeout()
                 return
+
+
+_CAPTURE_LOCK = threading.Lock()
+
+
+def capture_graph(stream, fn):
+    """Capture ``fn()`` (kernel launches on ``stream``) into a CUDA graph.
+
+    Unlike ``torch.cuda.graph`` this does NOT ``torch.cuda.synchronize()`` the whole device first: a sibling stage
+    sharing the GPU (threads in one process) may have a flag-spinning kernel in flight that only *our* next launch can
+    release, so a device-wide sync here would dead-lock.  Captures are serialised process-wide and use thread-local
+    capture mode so other threads may keep launching."""
+    import torch
+    g = torch.cuda.CUDAGraph()
+    with _CAPTURE_LOCK:
+        stream.synchronize()
+        with torch.cuda.stream(stream):
+            g.capture_begin(capture_error_mode="thread_local")
+            try:
+                fn()
+            finally:
+                g.capture_end()
+    return g

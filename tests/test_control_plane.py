@@ -1,0 +1,83 @@
+"""Transport, messages, auto-mode planning and mailbox geometry (CPU)."""
+import threading
+import time
+
+import numpy as np
+import pytest
+import yaml
+
+from split_learning_b200 import messages as M
+from split_learning_b200.config import normalize
+from split_learning_b200.runner import DEFAULT_PROFILE, run_inproc
+from split_learning_b200.transport import InProcBroker, TcpBroker, TcpChannel
+from split_learning_b200.transport.broker import delete_old_queues
+
+
+def test_inproc_broker_fifo_and_blocking_get():
+    b = InProcBroker()
+    assert b.basic_get("q") is None
+    threading.Timer(0.05, lambda: b.publish_obj("q", {"k": 1})).start()
+    t0 = time.monotonic()
+    assert b.get_obj("q", 2.0) == {"k": 1} and time.monotonic() - t0 < 1.0
+    for i in range(5):
+        b.publish_obj("q", i)
+    assert [b.get_obj("q") for _ in range(5)] == list(range(5))
+
+
+def test_tcp_broker_roundtrip_and_hygiene():
+    srv = TcpBroker(port=0)
+    try:
+        c1, c2 = TcpChannel(port=srv.port), TcpChannel(port=srv.port)
+        payload = b"x" * (3 << 20)                         # multi-MB frames (a state-dict sized message)
+        c1.basic_publish("rpc_queue", payload)
+        c1.publish_obj("reply_abc", {"action": "START"})
+        c1.publish_obj("keepme", 1)
+        assert c2.basic_get("rpc_queue", 2.0) == payload
+        assert c2.get_obj("reply_abc", 2.0)["action"] == "START"
+        assert c2.queue_depth("keepme") == 1
+        delete_old_queues(c2)                              # reply*/rpc_queue* deleted, everything else purged
+        assert c2.queue_depth("keepme") == 0 and "reply_abc" not in c2.list_queues()
+        c1.close(), c2.close()
+    finally:
+        srv.close()
+
+
+def test_message_schemas_match_reference_fields():
+    # SURVEY Appendix A
+    assert set(M.register("id", 1, {"speed": 1}, -1)) >= {"action", "client_id", "layer_id", "profile", "cluster", "message"}
+    s = M.start(None, [0, 7], "VGG16", "CIFAR10", {"batch-size": 32}, [500] * 10, True, 0)
+    assert set(s) >= {"action", "message", "parameters", "layers", "model_name", "data_name", "learning", "label_count",
+                      "refresh", "cluster"}
+    assert M.pause()["parameters"] is None and M.stop()["action"] == "STOP"
+    u = M.update("id", 2, True, 17, 0, {})
+    assert set(u) >= {"action", "client_id", "layer_id", "result", "size", "cluster", "message", "parameters"}
+    assert M.notify("id", 1, 0)["action"] == "NOTIFY" and M.reply_queue("x") == "reply_x"
+
+
+def _auto_cfg(tmp_path, selection):
+    raw = yaml.safe_load(open("/root/reference/config.yaml"))
+    raw["server"].update({"clients": [4, 2], "auto-mode": True, "validation": False, "global-round": 1})
+    raw["server"]["data-distribution"].update({"non-iid": True, "num-sample": 64})
+    raw["server"]["cluster-selection"] = {"num-cluster": 2, "algorithm-cluster": "KMeans", "selection-mode": selection}
+    raw["log_path"] = str(tmp_path)
+    raw["learning"]["batch-size"] = 8
+    raw["b200"] = {"synthetic-data": True, "watchdog-seconds": 60}
+    return normalize(raw)
+
+
+def test_auto_mode_partition_and_clusters(tmp_path):
+    """auto-mode: KMeans over label histograms -> per-cluster cut search from the clients' profiles
+    (reference src/Server.py:300-362).  Profiles make layer 7 the balanced cut."""
+    exe = [1.0] * 52
+    size = [8e6] * 52
+    size[6] = 1e3                                           # tiny activation after layer 7 -> best cut = 7
+    prof = dict(DEFAULT_PROFILE, exe_time=exe, size_data=size, network=1.0, speed=10.0)
+    profiles = [dict(prof) for _ in range(6)]
+    cfg = _auto_cfg(tmp_path, selection=False)
+    srv = run_inproc(cfg, profiles=profiles, workdir=str(tmp_path), timeout=600)
+    assert srv.history[0]["ok"]
+    assert len(srv.topology.clusters) == 2
+    for cl in srv.topology.clusters:
+        if cl.members[0] and cl.members[1]:
+            assert cl.cut_layers == [7]
+    assert sum(len(c.members[0]) for c in srv.topology.clusters) == 4
