@@ -373,81 +373,145 @@ __global__ void __launch_bounds__(256) conv_finalize_kernel(const float* acc, co
 
 // ============================================================================ first-layer direct conv (Cin <= 4)
 // x: fp32 NCHW [B][Cin][H][W]; w: fp32 [Cout][3][3][Cin]; y: bf16 NHWC [B][H][W][Cout] (pre-BN) + BN statistics.
-template <int CIN>
-__global__ void __launch_bounds__(256) conv3x3_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// One thread = one output pixel, all COUT channels in registers; weights are warp-broadcast smem reads; the BN
+// statistics are reduced across the 32 pixels of a warp with the register butterfly, then smem, then one red per CTA.
+__device__ __forceinline__ float warp_col_reduce32e(float (&v)[32]) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(128) conv3x3_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ bias, __nv_bfloat16* y,
-                                                               float* sum, float* sumsq, int B, int H, int W, int Cout) {
-  extern __shared__ float s_w[];                 // [Cout][9*CIN] + bias[Cout] + stats[2*Cout]
-  float* s_b = s_w + Cout * 9 * CIN;
-  float* s_st = s_b + Cout;
-  for (int i = threadIdx.x; i < Cout * 9 * CIN; i += blockDim.x) s_w[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) { s_b[i] = bias ? bias[i] : 0.f; s_st[i] = 0.f; s_st[Cout + i] = 0.f; }
+                                                               float* sum, float* sumsq, int B, int H, int W) {
+  constexpr int KK = 9 * CIN;
+  __shared__ float s_w[COUT * KK];
+  __shared__ float s_b[COUT];
+  __shared__ float s_st[2 * COUT];
+  for (int i = threadIdx.x; i < COUT * KK; i += blockDim.x) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) { s_b[i] = bias ? bias[i] : 0.f; s_st[i] = 0.f; s_st[COUT + i] = 0.f; }
   __syncthreads();
-  const int groups = Cout >> 4;                  // 16 output channels per thread
-  const long long total = (long long)B * H * W * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = static_cast<int>(i % groups);
-    const long long pix = i / groups;
+  const long long P = (long long)B * H * W;
+  const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool ok = pix < P;
+  float patch[KK];
+  if (ok) {
     const int ww = static_cast<int>(pix % W);
     const int hh = static_cast<int>((pix / W) % H);
     const long long b = pix / ((long long)W * H);
-    float patch[9 * CIN];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int ih = hh + t / 3 - 1, iw = ww + t % 3 - 1;
-      const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+      const bool in = ih >= 0 && ih < H && iw >= 0 && iw < W;
 #pragma unroll
-      for (int c = 0; c < CIN; ++c) patch[t * CIN + c] = ok ? __ldg(x + ((b * CIN + c) * H + ih) * W + iw) : 0.f;
+      for (int c = 0; c < CIN; ++c) patch[t * CIN + c] = in ? __ldg(x + ((b * CIN + c) * H + ih) * W + iw) : 0.f;
     }
-    float acc[16];
+  } else {
 #pragma unroll
-    for (int o = 0; o < 16; ++o) {
-      const float* wr = s_w + (g * 16 + o) * 9 * CIN;
-      float a = s_b[g * 16 + o];
+    for (int k = 0; k < KK; ++k) patch[k] = 0.f;
+  }
+#pragma unroll 1
+  for (int c0 = 0; c0 < COUT; c0 += 32) {
+    float acc[32];
 #pragma unroll
-      for (int k = 0; k < 9 * CIN; ++k) a = fmaf(patch[k], wr[k], a);
+    for (int o = 0; o < 32; ++o) {
+      const float* wr = s_w + (c0 + o) * KK;
+      float a = s_b[c0 + o];
+#pragma unroll
+      for (int k = 0; k < KK; ++k) a = fmaf(patch[k], wr[k], a);
       acc[o] = a;
     }
-    uint4* o4 = reinterpret_cast<uint4*>(y + pix * Cout + g * 16);
-    o4[0] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
-    o4[1] = make_uint4(pack_bf16x2(acc[8], acc[9]), pack_bf16x2(acc[10], acc[11]), pack_bf16x2(acc[12], acc[13]), pack_bf16x2(acc[14], acc[15]));
+    if (ok) {
+      uint4* o4 = reinterpret_cast<uint4*>(y + pix * COUT + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o4[j] = make_uint4(pack_bf16x2(acc[8 * j], acc[8 * j + 1]), pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]),
+                           pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]), pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]));
+    }
+    if (sum) {
+      float s1[32], s2[32];
+#pragma unroll
+      for (int o = 0; o < 32; ++o) {
+        const float r = ok ? __bfloat162float(__float2bfloat16(acc[o])) : 0.f;
+        s1[o] = r;
+        s2[o] = r * r;
+      }
+      const float c1 = warp_col_reduce32e(s1);
+      const float c2 = warp_col_reduce32e(s2);
+      atomicAdd(&s_st[c0 + (threadIdx.x & 31)], c1);
+      atomicAdd(&s_st[COUT + c0 + (threadIdx.x & 31)], c2);
+    }
+  }
+  if (sum) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+      atomicAdd(sum + i, s_st[i]);
+      atomicAdd(sumsq + i, s_st[COUT + i]);
+    }
   }
 }
 
-// dw[Cout][9*CIN] += sum_pix dy[pix][Cout] * patch[pix][9*CIN]    (block = 128 pixels)
+// dw[Cout][9*CIN] += sum_pix dy[pix][Cout] * patch[pix][9*CIN].  A block walks several 128-pixel chunks and keeps its
+// partial sums in registers, so the global reds are per block, not per chunk.
 template <int CIN>
 __global__ void __launch_bounds__(256) conv3x3_small_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                                  float* dw, int B, int H, int W, int Cout) {
   constexpr int KK = 9 * CIN;
+  constexpr int MAXO = 8;                         // outputs per thread: Cout*KK <= 256*8
   extern __shared__ float s_buf[];               // patch[128][KK] + dy[128][Cout]
   float* s_patch = s_buf;
   float* s_dy = s_buf + 128 * KK;
   const long long P = (long long)B * H * W;
-  const long long pix0 = blockIdx.x * 128LL;
-  for (int i = threadIdx.x; i < 128 * KK; i += blockDim.x) {
-    const int lp = i / KK, k = i - lp * KK;
-    const long long pix = pix0 + lp;
-    float v = 0.f;
-    if (pix < P) {
-      const int t = k / CIN, c = k - t * CIN;
-      const int ww = static_cast<int>(pix % W), hh = static_cast<int>((pix / W) % H);
-      const long long b = pix / ((long long)W * H);
-      const int ih = hh + t / 3 - 1, iw = ww + t % 3 - 1;
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[((b * CIN + c) * H + ih) * W + iw];
+  const int n_out = Cout * KK;
+  float acc[MAXO];
+#pragma unroll
+  for (int j = 0; j < MAXO; ++j) acc[j] = 0.f;
+  for (long long pix0 = blockIdx.x * 128LL; pix0 < P; pix0 += (long long)gridDim.x * 128) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * KK; i += blockDim.x) {
+      const int lp = i / KK, k = i - lp * KK;
+      const long long pix = pix0 + lp;
+      float v = 0.f;
+      if (pix < P) {
+        const int t = k / CIN, c = k - t * CIN;
+        const int ww = static_cast<int>(pix % W), hh = static_cast<int>((pix / W) % H);
+        const long long b = pix / ((long long)W * H);
+        const int ih = hh + t / 3 - 1, iw = ww + t % 3 - 1;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[((b * CIN + c) * H + ih) * W + iw];
+      }
+      s_patch[i] = v;
     }
-    s_patch[i] = v;
-  }
-  for (int i = threadIdx.x; i < 128 * Cout; i += blockDim.x) {
-    const long long pix = pix0 + i / Cout;
-    s_dy[i] = pix < P ? __bfloat162float(dy[pix * Cout + (i % Cout)]) : 0.f;
-  }
-  __syncthreads();
-  for (int o = threadIdx.x; o < Cout * KK; o += blockDim.x) {
-    const int co = o / KK, k = o - co * KK;
-    float a = 0.f;
+    for (int i = threadIdx.x; i < 128 * Cout; i += blockDim.x) {
+      const long long pix = pix0 + i / Cout;
+      s_dy[i] = pix < P ? __bfloat162float(dy[pix * Cout + (i % Cout)]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < MAXO; ++j) {
+      const int o = threadIdx.x + j * 256;
+      if (o < n_out) {
+        const int co = o / KK, k = o - co * KK;
+        float a = acc[j];
 #pragma unroll 8
-    for (int lp = 0; lp < 128; ++lp) a = fmaf(s_dy[lp * Cout + co], s_patch[lp * KK + k], a);
-    atomicAdd(dw + o, a);
+        for (int lp = 0; lp < 128; ++lp) a = fmaf(s_dy[lp * Cout + co], s_patch[lp * KK + k], a);
+        acc[j] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXO; ++j) {
+    const int o = threadIdx.x + j * 256;
+    if (o < n_out) atomicAdd(dw + o, acc[j]);
   }
 }
 
@@ -642,7 +706,7 @@ int slb_preload_elementwise() {
   SLB_PRELOAD(zero_kernel); SLB_PRELOAD(wait_flag_kernel); SLB_PRELOAD(set_flag_kernel); SLB_PRELOAD(counter_inc_kernel);
   SLB_PRELOAD(bn_relu_pool_fwd_kernel); SLB_PRELOAD(bn_bwd_reduce_kernel<true>); SLB_PRELOAD(bn_bwd_reduce_kernel<false>);
   SLB_PRELOAD(bn_bwd_apply_kernel<true>); SLB_PRELOAD(bn_bwd_apply_kernel<false>); SLB_PRELOAD(col_stats_kernel);
-  SLB_PRELOAD(conv_finalize_kernel); SLB_PRELOAD(conv3x3_small_fwd_kernel<3>); SLB_PRELOAD(conv3x3_small_fwd_kernel<1>);
+  SLB_PRELOAD(conv_finalize_kernel); { auto k1 = conv3x3_small_fwd_kernel<3, 64>; SLB_PRELOAD(k1); auto k2 = conv3x3_small_fwd_kernel<1, 64>; SLB_PRELOAD(k2); }
   SLB_PRELOAD(conv3x3_small_wgrad_kernel<3>); SLB_PRELOAD(conv3x3_small_wgrad_kernel<1>); SLB_PRELOAD(linear_finalize_kernel);
   SLB_PRELOAD(linear_bwd_prep_kernel); SLB_PRELOAD(dropout_fwd_kernel); SLB_PRELOAD(dropout_bwd_kernel);
   SLB_PRELOAD(ce_fwd_bwd_kernel); SLB_PRELOAD(sgd_momentum_kernel); SLB_PRELOAD(adamw_kernel); SLB_PRELOAD(cast_f32_bf16_kernel);
@@ -722,19 +786,21 @@ int slb_col_stats(const void* y, float* sum, float* sumsq, long long P, int C, c
 
 int slb_conv3x3_small_fwd(const float* x, const float* w, const float* bias, void* y, float* sum, float* sumsq, int B, int Cin,
                           int H, int W, int Cout, cudaStream_t st) {
-  if (Cout % 16) return -1;
-  const size_t smem = (size_t)(Cout * 9 * Cin + 3 * Cout) * sizeof(float);
-  const long long work = (long long)B * H * W * (Cout / 16);
-  const int grid = grid_for(work, 256, 148 * 4);
+  const long long P = (long long)B * H * W;
+  const int grid = static_cast<int>((P + 127) / 128);
   __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
-  if (Cin == 3) conv3x3_small_fwd_kernel<3><<<grid, 256, smem, st>>>(x, w, bias, yy, sum, sumsq, B, H, W, Cout);
-  else if (Cin == 1) conv3x3_small_fwd_kernel<1><<<grid, 256, smem, st>>>(x, w, bias, yy, sum, sumsq, B, H, W, Cout);
+  if (Cin == 3 && Cout == 64) conv3x3_small_fwd_kernel<3, 64><<<grid, 128, 0, st>>>(x, w, bias, yy, sum, sumsq, B, H, W);
+  else if (Cin == 3 && Cout == 32) conv3x3_small_fwd_kernel<3, 32><<<grid, 128, 0, st>>>(x, w, bias, yy, sum, sumsq, B, H, W);
+  else if (Cin == 1 && Cout == 64) conv3x3_small_fwd_kernel<1, 64><<<grid, 128, 0, st>>>(x, w, bias, yy, sum, sumsq, B, H, W);
+  else if (Cin == 1 && Cout == 32) conv3x3_small_fwd_kernel<1, 32><<<grid, 128, 0, st>>>(x, w, bias, yy, sum, sumsq, B, H, W);
   else return -2;
   return last_err();
 }
 int slb_conv3x3_small_wgrad(const float* x, const void* dy, float* dw, int B, int Cin, int H, int W, int Cout, cudaStream_t st) {
+  if (Cout * 9 * Cin > 2048) return -3;
   const size_t smem = (size_t)(128 * 9 * Cin + 128 * Cout) * sizeof(float);
-  const int grid = static_cast<int>(((long long)B * H * W + 127) / 128);
+  const long long chunks = ((long long)B * H * W + 127) / 128;
+  const int grid = static_cast<int>(chunks < 74 ? chunks : 74);
   const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(dy);
   if (Cin == 3) {
     static bool done3 = false;

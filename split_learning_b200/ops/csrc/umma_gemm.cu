@@ -43,6 +43,11 @@ struct GemmParams {
   int flip;             // 1: dgrad (mirrored taps)
   int b_row_stride;     // conv: columns of B per tap (= Cin of the weight tensor)
   int Cout;             // wgrad: number of output channels (rows per tap)
+  // split-K with in-kernel finalisation: the last K-slice of a tile to finish converts the fp32 partial sums
+  // (accumulated with red.add in `out`) into the bf16 result + BN statistics — no separate finalize launch.
+  uint32_t* tile_counters;   // [m_tiles * n_tiles], zero at rest (self-resetting)
+  __nv_bfloat16* fin_out;    // bf16 destination [M][fin_ld]
+  long long fin_ld;
 };
 
 template <int BLOCK_N>
@@ -106,6 +111,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(accum_bar, 1);
     mbar_fence_init();
   }
+  if (threadIdx.x == 32) tmem_slot[1] = 0;
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -306,7 +312,63 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      if (want_stats) {
+      if (p.epi == EPI_F32_ATOMIC && p.tile_counters != nullptr) {
+        // ---- serial split-K tail: last slice of this tile finalises it ----
+        __threadfence();
+        asm volatile("bar.sync 1, 128;");
+        if (et == 0) {
+          const uint32_t tix = blockIdx.x * gridDim.y + blockIdx.y;
+          const uint32_t t = atomicAdd(p.tile_counters + tix, 1u);
+          const uint32_t last = (t == static_cast<uint32_t>(p.k_split) - 1u) ? 1u : 0u;
+          if (last) p.tile_counters[tix] = 0;
+          tmem_slot[1] = last;
+        }
+        asm volatile("bar.sync 1, 128;");
+        if (tmem_slot[1]) {
+          __threadfence();
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_N; c += 32) {
+            const int col0 = n0 + c;
+            float f[32];
+            if (row_ok) {
+              const float4* a4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + row_off + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t4 = __ldcg(a4 + j);
+                f[4 * j] = t4.x; f[4 * j + 1] = t4.y; f[4 * j + 2] = t4.z; f[4 * j + 3] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = 0.f;
+            }
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
+            }
+            if (row_ok) {
+              uint4* o4 = reinterpret_cast<uint4*>(p.fin_out + static_cast<long long>(row) * p.fin_ld + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            }
+            if (want_stats) {
+              float s1[32], s2[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float r = row_ok ? __bfloat162float(__float2bfloat16(f[j])) : 0.f;
+                s1[j] = r;
+                s2[j] = r * r;
+              }
+              const float c1 = warp_col_reduce32(s1);
+              const float c2 = warp_col_reduce32(s2);
+              atomicAdd(&s_stats[c + lane_id()], c1);
+              atomicAdd(&s_stats[BLOCK_N + c + lane_id()], c2);
+            }
+          }
+        }
+      }
+      if (want_stats && (p.epi == EPI_BF16 || tmem_slot[1])) {
         asm volatile("bar.sync 1, 128;");
         for (int i = et; i < BLOCK_N; i += 128) {
           if (n0 + i < p.N) {
@@ -437,7 +499,7 @@ int slb_preload_gemm() {
 int slb_conv3x3_igemm(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
                       int B, int H, int W, int Ca /*channels of A*/, int Nout /*output channels*/, int flip,
                       int w_cin /*Cin of the weight tensor*/, int w_cout, int block_n, int k_split, float* acc,
-                      cudaStream_t st) {
+                      uint32_t* tile_counters, cudaStream_t st) {
   if (Ca % 64 != 0 || Nout % 64 != 0) return -10;
   const int M = B * H * W;
   if (128 % W != 0 && W % 128 != 0) return -11;
@@ -457,11 +519,19 @@ int slb_conv3x3_igemm(const void* x, const void* w, void* y, const float* bias, 
   p.M = M; p.N = Nout; p.k_iters = 9 * (Ca / 64);
   if (k_split < 1) k_split = 1;
   if (k_split > p.k_iters) k_split = p.k_iters;
+  {  // no empty K slices (the tile semaphore counts exactly k_split arrivals)
+    const int per = (p.k_iters + k_split - 1) / k_split;
+    k_split = (p.k_iters + per - 1) / per;
+  }
   p.k_split = k_split;
   p.a_mn = 0; p.b_mn = flip ? 1 : 0; p.ldo = Nout;
   if (k_split > 1) {
     if (acc == nullptr) return -17;
     p.epi = EPI_F32_ATOMIC; p.out = acc;
+    if (tile_counters != nullptr) {       // in-kernel finalisation by the last K-slice of every tile
+      p.tile_counters = tile_counters; p.fin_out = reinterpret_cast<__nv_bfloat16*>(y); p.fin_ld = Nout;
+      p.bias = bias; p.col_sum = col_sum; p.col_sumsq = col_sumsq;
+    }
   } else {
     p.epi = EPI_BF16; p.out = y;
     p.bias = bias; p.col_sum = col_sum; p.col_sumsq = col_sumsq;
@@ -498,6 +568,10 @@ int slb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int H, in
     if (k_split < 1) k_split = 1;
   }
   if (k_split > p.k_iters) k_split = p.k_iters;
+  {
+    const int per = (p.k_iters + k_split - 1) / k_split;
+    k_split = (p.k_iters + per - 1) / per;
+  }
   p.k_split = k_split;
   // a single K slice owns its output tile: plain stores (no zero-fill, no atomics)
   p.a_mn = 1; p.b_mn = 1; p.epi = k_split > 1 ? EPI_F32_ATOMIC : EPI_F32_STORE; p.out = dw; p.ldo = Cin;

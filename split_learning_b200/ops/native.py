@@ -104,7 +104,7 @@ def conv_tiling(M: int, N: int, Ca: int, target_ctas: int = 96):
     return bn, k_split
 
 
-def conv3x3_fwd(x, w_bf16, y, bias=None, col_sum=None, col_sumsq=None, acc=None, tiling=None):
+def conv3x3_fwd(x, w_bf16, y, bias=None, col_sum=None, col_sumsq=None, acc=None, tiling=None, counters=None):
     """x [B,H,W,Cin] bf16, w [Cout,3,3,Cin] bf16 -> y [B,H,W,Cout] bf16 (pre-BN) + optional BN sums.
     ``acc``: zeroed fp32 [M, Cout] scratch enabling split-K (then a finalize kernel produces y and the sums)."""
     B, H, W, Cin = x.shape
@@ -114,12 +114,12 @@ def conv3x3_fwd(x, w_bf16, y, bias=None, col_sum=None, col_sumsq=None, acc=None,
         ks = 1
     _check(lib().slb_conv3x3_igemm(_p(x), _p(w_bf16), _p(y), _p(bias), _p(col_sum), _p(col_sumsq), c_int(B), c_int(H),
                                    c_int(W), c_int(Cin), c_int(Cout), c_int(0), c_int(Cin), c_int(Cout), c_int(bn), c_int(ks),
-                                   _p(acc), _stream()), "conv3x3_fwd")
-    if ks > 1:
+                                   _p(acc), _p(counters), _stream()), "conv3x3_fwd")
+    if ks > 1 and counters is None:
         conv_finalize(acc, bias, y, col_sum, col_sumsq)
 
 
-def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None):
+def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None):
     """dy [B,H,W,Cout] bf16, w [Cout,3,3,Cin] bf16 -> dx [B,H,W,Cin] bf16."""
     B, H, W, Cout = dy.shape
     Cin = w_bf16.shape[3]
@@ -128,8 +128,8 @@ def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None):
         ks = 1
     _check(lib().slb_conv3x3_igemm(_p(dy), _p(w_bf16), _p(dx), _p(None), _p(None), _p(None), c_int(B), c_int(H), c_int(W),
                                    c_int(Cout), c_int(Cin), c_int(1), c_int(Cin), c_int(Cout), c_int(bn), c_int(ks), _p(acc),
-                                   _stream()), "conv3x3_dgrad")
-    if ks > 1:
+                                   _p(counters), _stream()), "conv3x3_dgrad")
+    if ks > 1 and counters is None:
         conv_finalize(acc, None, dx, None, None)
 
 

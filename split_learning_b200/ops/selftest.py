@@ -64,7 +64,15 @@ def conv_fwd():
         s2 = torch.zeros(Cout, device="cuda")
         bn_, ks_ = N.conv_tiling(B * H * W, Cout, Cin)
         acc = torch.zeros(B * H * W, Cout, device="cuda") if ks_ > 1 else None
-        N.conv3x3_fwd(x, w, y, bias, s1, s2, acc=acc)
+        ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)
+        N.conv3x3_fwd(x, w, y, bias, s1, s2, acc=acc, counters=ctr)          # in-kernel split-K finalisation
+        if ks_ > 1:                                                           # ... and the two-kernel variant
+            y2, t1, t2 = torch.empty_like(y), torch.zeros_like(s1), torch.zeros_like(s2)
+            acc.zero_()
+            N.conv3x3_fwd(x, w, y2, bias, t1, t2, acc=acc)
+            torch.cuda.synchronize()
+            assert int(ctr.abs().sum()) == 0, "tile semaphores must reset themselves"
+            assert _rel(y2, y) < 1e-2 and _rel(t1, s1) < 1e-3
         torch.cuda.synchronize()
         ref = _ref_conv(x, w, bias)
         e = _rel(y, ref)
@@ -85,11 +93,13 @@ def conv_dgrad():
         dx = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.bfloat16)
         bn_, ks_ = N.conv_tiling(B * H * W, Cin, Cout)
         acc = torch.zeros(B * H * W, Cin, device="cuda") if ks_ > 1 else None
-        N.conv3x3_dgrad(dy, w, dx, acc=acc)
+        ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)       # must outlive the asynchronous kernel
+        N.conv3x3_dgrad(dy, w, dx, acc=acc, counters=ctr)
         torch.cuda.synchronize()
         xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
         F.conv2d(xr, w.float().permute(0, 3, 1, 2), None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
         e = _rel(dx, xr.grad.permute(0, 2, 3, 1))
+        assert int(ctr.abs().sum()) == 0
         print(f"  conv_dgrad {B}x{H}x{W} {Cin}<-{Cout}: {e:.2e}")
         worst = max(worst, e)
     return worst, 1.5e-2
@@ -238,8 +248,7 @@ def conv1_direct():
     bias = torch.randn(Cout, device="cuda")
     y = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
     s1, s2 = torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
-    N.conv3x3_small_fwd(x, w, bias, y)
-    N.col_stats(y.view(-1, Cout), s1, s2)
+    N.conv3x3_small_fwd(x, w, bias, y, s1, s2)
     torch.cuda.synchronize()
     wr = w.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
     ref = F.conv2d(x, wr, bias, padding=1)

@@ -102,14 +102,38 @@ class MailboxSpec:
         return self.header_off + 256
 
 
-_SAME_PROCESS = {}          # IPC handle -> raw pointer, for partners that live in this very process (threads)
+_SAME_PROCESS = {}          # IPC handle -> (raw pointer, HostGate), for partners that live in this very process
+
+
+class HostGate:
+    """Host-side companion of a mailbox when both ends are threads of ONE process sharing a GPU: the consumer thread
+    does not enqueue its program before the producer thread has *enqueued* the matching publish.  This keeps flag-wait
+    kernels from spinning on work that is not even submitted yet — which on a shared GPU can dead-lock against CUDA's
+    lazy kernel loading (a first launch may wait for running kernels).  Cross-process edges need no gate."""
+
+    def __init__(self):
+        import threading
+        self._cv = threading.Condition()
+        self._n = 0
+
+    def post(self) -> None:
+        with self._cv:
+            self._n += 1
+            self._cv.notify_all()
+
+    def wait(self, count: int, timeout: float = 120.0) -> None:
+        with self._cv:
+            if not self._cv.wait_for(lambda: self._n >= count, timeout):
+                raise TimeoutError("producer thread never enqueued the matching publish")
 
 
 class Mailbox:
     """View of a mailbox allocation (owner side or a peer-mapped producer side)."""
 
-    def __init__(self, spec: MailboxSpec, base: Optional[torch.Tensor], owner: bool, raw_ptr: Optional[int] = None):
+    def __init__(self, spec: MailboxSpec, base: Optional[torch.Tensor], owner: bool, raw_ptr: Optional[int] = None,
+                 gate: Optional[HostGate] = None):
         self.spec, self.base, self.owner = spec, base, owner
+        self.gate = gate
         self.raw_ptr = raw_ptr if raw_ptr is not None else base.data_ptr()
         d = spec.depth
         if base is None:                     # peer-mapped: raw pointer views only
@@ -152,13 +176,17 @@ class Mailbox:
         if rc != 0:
             raise N.NativeError(f"cudaIpcGetMemHandle failed: {rc}")
         base = tensor_from_ptr(ptr.value, spec.total_bytes, device)
-        _SAME_PROCESS[bytes(handle)] = ptr.value
-        return Mailbox(spec, base, owner=True, raw_ptr=ptr.value), bytes(handle)
+        mb = Mailbox(spec, base, owner=True, raw_ptr=ptr.value)
+        _SAME_PROCESS[bytes(handle)] = (ptr.value, mb)
+        return mb, bytes(handle)
 
     @staticmethod
     def open_peer(spec: MailboxSpec, handle: bytes, device) -> "Mailbox":
         if handle in _SAME_PROCESS:            # cudaIpcOpenMemHandle refuses handles exported by the same process
-            return Mailbox(spec, None, owner=False, raw_ptr=_SAME_PROCESS[handle])
+            raw, owner_mb = _SAME_PROCESS[handle]
+            if owner_mb.gate is None:
+                owner_mb.gate = HostGate()
+            return Mailbox(spec, None, owner=False, raw_ptr=raw, gate=owner_mb.gate)
         lib = N.lib()
         ptr = ctypes.c_void_p()
         buf = (ctypes.c_uint8 * 64).from_buffer_copy(handle)

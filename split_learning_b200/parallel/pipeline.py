@@ -42,7 +42,7 @@ class DeviceStage:
     def __init__(self, ex: B200Executor, batch: int, depth: int,
                  fwd_in: Optional[Mailbox] = None, grad_in: Optional[Mailbox] = None,
                  fwd_out: Optional[Mailbox] = None, grad_out: Optional[Mailbox] = None,
-                 stream: Optional[torch.cuda.Stream] = None, wait_spins: int = 1 << 28):
+                 stream: Optional[torch.cuda.Stream] = None, wait_spins: Optional[int] = None):
         self.ex, self.B, self.depth = ex, batch, depth
         self.fwd_in, self.grad_in, self.fwd_out, self.grad_out = fwd_in, grad_in, fwd_out, grad_out
         self.stream = stream or ex.stream
@@ -53,7 +53,9 @@ class DeviceStage:
         self.exp_fwd = EdgeCounters(depth, dev)       # values I have consumed from upstream activations
         self.exp_grad = EdgeCounters(depth, dev)      # values I have consumed from downstream gradients
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.wait_spins = wait_spins
+        import os
+        self.wait_spins = wait_spins if wait_spins is not None else int(os.environ.get("SLB200_WAIT_SPINS", str(1 << 28)))
+        self._posted = {"F": 0, "B": 0, "L": 0}
         self.labels_slots = [torch.zeros(batch, dtype=torch.int64, device=dev) for _ in range(depth)]
         if fwd_in is not None:                        # consume activations in place from my mailbox
             self.plan.bind_inputs(fwd_in.payload)
@@ -118,14 +120,29 @@ class DeviceStage:
                 self.graphs[key] = g
             g.replay()
 
+    # Host gates exist only for same-process partners (see mailbox.HostGate); they order *enqueueing*, not execution.
+    def _gate_wait(self, mb: Optional[Mailbox], it: int) -> None:
+        if mb is not None and mb.gate is not None:
+            mb.gate.wait(it + 1)
+
+    def _gate_post(self, mb: Optional[Mailbox]) -> None:
+        if mb is not None and mb.gate is not None:
+            mb.gate.post()
+
     def forward(self, it: int) -> None:
+        self._gate_wait(self.fwd_in, it)
         self._exec("F", it % self.depth)
+        self._gate_post(self.fwd_out)
 
     def backward(self, it: int) -> None:
+        self._gate_wait(self.grad_in, it)
         self._exec("B", it % self.depth)
+        self._gate_post(self.grad_out)
 
     def last(self, it: int) -> None:
+        self._gate_wait(self.fwd_in, it)
         self._exec("L", it % self.depth)
+        self._gate_post(self.grad_out)
 
     def stage_input(self, it: int, x_host: torch.Tensor, y_host: torch.Tensor) -> None:
         """First stage: H2D copy of a microbatch (pinned host memory) into input slot ``it % depth``."""

@@ -34,9 +34,6 @@ def profile_model(model_name: str, batch: int = 4, data_name: Optional[str] = No
         for _ in range(repeats):
             h = x
             for i in range(1, n + 1):
-                layer = getattr(model, f"layer{i}", None)
-                single = klass(start_layer=i - 1, end_layer=i)
-                single_sd = single.state_dict()
                 if cuda:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()

@@ -436,6 +436,7 @@ class _Plan:
         self.dout_in = torch.zeros(last.shape, device=dev, dtype=bf)
         self.dlogits = torch.zeros(B, ex.num_classes, device=dev) if ex.is_last else None
         self.ticket = torch.zeros(4, device=dev, dtype=torch.int32)
+        self.tile_counters = torch.zeros(4096, device=dev, dtype=torch.int32)   # split-K tile semaphores (self-resetting)
         self.graphs: Dict[Tuple[str, int], torch.cuda.CUDAGraph] = {}
         self._warm = False
 
@@ -481,7 +482,7 @@ class _Plan:
                     tgt = a["y"] if not (is_final and out_ptr_override is not None) else out_ptr_override
                     facc = self.s(bi, "facc") if (bi, "facc") in self.soff else None
                     N.conv3x3_fwd(x, ex.view(ex.PB, f"layer{b.conv}.weight"), tgt, ex.view(ex.P, f"layer{b.conv}.bias"),
-                                  acc=facc)
+                                  acc=facc, counters=self.tile_counters)
                     if is_final and publish is not None:
                         N.set_flag(publish["flag"].data_ptr() if hasattr(publish["flag"], "data_ptr") else publish["flag"],
                                    0, publish["seq"], publish.get("hint_ptr", 0))
@@ -513,11 +514,11 @@ class _Plan:
                     s1, s2 = self.s(bi, "sum"), self.s(bi, "sumsq")
                     bias = ex.view(ex.P, f"layer{b.conv}.bias")
                     if b.cin <= 4:
-                        N.conv3x3_small_fwd(x, ex.view(ex.P, f"layer{b.conv}.weight"), bias, a["y"])
-                        N.col_stats(a["y"].reshape(-1, b.cout), s1, s2)
+                        N.conv3x3_small_fwd(x, ex.view(ex.P, f"layer{b.conv}.weight"), bias, a["y"], s1, s2)
                     else:
                         facc = self.s(bi, "facc") if (bi, "facc") in self.soff else None
-                        N.conv3x3_fwd(x, ex.view(ex.PB, f"layer{b.conv}.weight"), a["y"], bias, s1, s2, acc=facc)
+                        N.conv3x3_fwd(x, ex.view(ex.PB, f"layer{b.conv}.weight"), a["y"], bias, s1, s2, acc=facc,
+                                      counters=self.tile_counters)
                     y = a["y"]
                 else:
                     y = x
@@ -611,7 +612,7 @@ class _Plan:
                         if need_dx:
                             dx = a["dx"] if not (bi == 0 and grad_out_override is not None) else grad_out_override
                             dacc = self.s(bi, "dacc") if (bi, "dacc") in self.soff else None
-                            N.conv3x3_dgrad(dy, ex.view(ex.PB, f"layer{b.conv}.weight"), dx, acc=dacc)
+                            N.conv3x3_dgrad(dy, ex.view(ex.PB, f"layer{b.conv}.weight"), dx, acc=dacc, counters=self.tile_counters)
                             g = dx
                 else:
                     g = dy

@@ -66,8 +66,9 @@ def capture_graph(stream, fn):
     capture mode so other threads may keep launching."""
     import torch
     g = torch.cuda.CUDAGraph()
+    # No stream/device synchronisation while holding the lock: a sibling thread may need the lock to *launch* the very
+    # work our pending kernels are waiting for (observed dead-lock: stage 1 draining B(k) <- L(k) not yet captured).
     with _CAPTURE_LOCK:
-        stream.synchronize()
         with torch.cuda.stream(stream):
             g.capture_begin(capture_error_mode="thread_local")
             try:
