@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cut", type=int, default=7)
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--timeout", type=float, default=1500.0)
+    ap.add_argument("--breakdown", action="store_true", help="also report device time per stage program (F / L / B)")
     return ap.parse_args()
 
 
@@ -179,6 +180,31 @@ def run_ours(args) -> dict:
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop(t0, t1)
     pipe.synchronize()
+    breakdown = None
+    if args.breakdown:
+        evs = []
+        for _ in range(50):
+            if pipe.it_f - pipe.it_b >= pipe.depth:
+                a = torch.cuda.Event(enable_timing=True); a.record(pipe.stream)
+                pipe.step_backward()
+                b = torch.cuda.Event(enable_timing=True); b.record(pipe.stream)
+                evs.append(("B", a, b))
+            it = pipe.it_f
+            a = torch.cuda.Event(enable_timing=True); a.record(pipe.stream)
+            pipe.stages[0].forward(it)
+            b = torch.cuda.Event(enable_timing=True); b.record(pipe.stream)
+            pipe.stages[-1].last(it)
+            c = torch.cuda.Event(enable_timing=True); c.record(pipe.stream)
+            pipe.it_f += 1
+            evs += [("F", a, b), ("L", b, c)]
+        while pipe.it_b < pipe.it_f:
+            pipe.step_backward()
+        torch.cuda.synchronize()
+        acc = {}
+        for k, a, b in evs:
+            acc.setdefault(k, []).append(a.elapsed_time(b) * 1e3)
+        breakdown = {k: {"us": sum(v) / len(v), "launches": (pipe.stages[0] if k != "L" else pipe.stages[-1]).launches_per.get(k)}
+                     for k, v in acc.items()}
     loss = float(loss_host[0])
     value = K * B / (ms_dev / 1e3)
     return {
@@ -193,6 +219,7 @@ def run_ours(args) -> dict:
         "e2e": {"value": K * B / (ms_e2e / 1e3), "unit": "images/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": B * 3 * 32 * 32 * 4 + B * 8, "d2h_bytes_per_step": 16},
         "gpu_launches": per_step * K, "launches_per_step": per_step, "clocks": clocks, "final_loss": loss, "impl": "ours",
+        **({"breakdown": breakdown} if breakdown else {}),
     }
 
 

@@ -47,6 +47,8 @@ __device__ __forceinline__ void publish_flag(uint32_t* ticket, uint32_t* flag, u
 
 // ============================================================================ zero / flags
 __global__ void zero_kernel(float4* p, long long n4) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
     p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
@@ -56,6 +58,9 @@ __global__ void zero_kernel(float4* p, long long n4) {
 // receives 1 on timeout so a dead producer turns into an error instead of a hung GPU.
 __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t expected, uint32_t* expect_ctr, unsigned long long max_spins,
                                  int* status) {
+  // no pdl_trigger(): dependents must not become resident (and hog SM slots) while this kernel spins on a flag that
+  // another stream of the same GPU has yet to publish
+  pdl_wait();
   if (expect_ctr) expected = *expect_ctr + 1;
   unsigned long long spins = 0;
   while (ld_acquire_sys(flag) < expected) {
@@ -68,12 +73,16 @@ __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t expected, uint32
   if (expect_ctr) *expect_ctr = expected;
 }
 __global__ void set_flag_kernel(uint32_t* flag, uint32_t value, uint32_t* seq, uint32_t* hint) {
+  pdl_trigger();
+  pdl_wait();
   if (seq) { value = *seq + 1; *seq = value; }
   __threadfence_system();
   st_release_sys(flag, value);
   if (hint) st_release_sys(hint, value);
 }
-__global__ void counter_inc_kernel(uint32_t* c) { *c += 1; }
+__global__ void counter_inc_kernel(uint32_t* c) {
+  pdl_trigger();
+  pdl_wait(); *c += 1; }
 
 // ============================================================================ BN + ReLU + MaxPool forward
 struct BnFwdParams {
@@ -100,6 +109,8 @@ struct BnFwdParams {
 };
 
 __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const BnFwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_aff[];     // scale[C], shift[C]
   float* s_scale = s_aff;
   float* s_shift = s_aff + p.C;
@@ -231,6 +242,8 @@ __device__ __forceinline__ void bn_dz(const BnBwdParams& p, long long op, int g,
 // pass 1: dgamma / dbeta.  blockDim = (C/8, 256/(C/8)); grid-stride over output positions.
 template <bool POOL>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int NP = POOL ? 4 : 1;
   const int g = threadIdx.x;
   float sc[8], sh[8], mean[8], istd[8], ag[8], ab[8];
@@ -274,6 +287,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
 // pass 2: dy = gamma*invstd*(dz - dbeta/P - xhat*dgamma/P)
 template <bool POOL>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int NP = POOL ? 4 : 1;
   const int g = threadIdx.x;
   const float invP = 1.f / static_cast<float>(p.P);
@@ -309,6 +324,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
 
 // Column sums / sums of squares of a bf16 [P][C] matrix (BN statistics fallback, bias gradients).
 __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* y, float* sum, float* sumsq, long long P, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int g = threadIdx.x;
   float a[8], b[8];
 #pragma unroll
@@ -338,6 +355,8 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* y, 
 // (acc: fp32 [P][C] partial-sum buffer filled with red.add by the K-slices).  bias/y/sum may be null.
 __global__ void __launch_bounds__(256) conv_finalize_kernel(const float* acc, const float* bias, __nv_bfloat16* y, float* sum,
                                                            float* sumsq, long long P, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int g = threadIdx.x;
   float a[8], b[8], bs[8];
 #pragma unroll
@@ -394,6 +413,8 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(128) conv3x3_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ bias, __nv_bfloat16* y,
                                                                float* sum, float* sumsq, int B, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int KK = 9 * CIN;
   __shared__ float s_w[COUT * KK];
   __shared__ float s_b[COUT];
@@ -466,6 +487,8 @@ __global__ void __launch_bounds__(128) conv3x3_small_fwd_kernel(const float* __r
 template <int CIN>
 __global__ void __launch_bounds__(256) conv3x3_small_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                                  float* dw, int B, int H, int W, int Cout) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int KK = 9 * CIN;
   constexpr int MAXO = 8;                         // outputs per thread: Cout*KK <= 256*8
   extern __shared__ float s_buf[];               // patch[128][KK] + dy[128][Cout]
@@ -524,6 +547,8 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t a, uint32_t b, uint32_t c)
 // out[b][n] = dropout(relu(acc[b][n] + bias[n]))  -> bf16 (ld = ldo) ; also keeps fp32 logits when out_f32 != null
 __global__ void linear_finalize_kernel(const float* acc, const float* bias, __nv_bfloat16* out, float* out_f32, uint8_t* mask,
                                        int B, int N, int ldo, int relu, float drop_p, uint32_t seed, const uint32_t* step_ptr) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t step = step_ptr ? *step_ptr : 0u;
   const long long total = (long long)B * N;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -546,6 +571,8 @@ __global__ void linear_finalize_kernel(const float* acc, const float* bias, __nv
 __global__ void __launch_bounds__(256) linear_bwd_prep_kernel(const float* dacc, const __nv_bfloat16* yout, const uint8_t* mask,
                                                              __nv_bfloat16* dz, float* dbias, int B, int N, int ldy, int ldz,
                                                              int relu, float drop_p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_part[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -572,6 +599,8 @@ __global__ void __launch_bounds__(256) linear_bwd_prep_kernel(const float* dacc,
 // bf16 dropout on a dense activation (VGG layer 46) and its backward
 __global__ void dropout_fwd_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* mask, long long n, float p, uint32_t seed,
                                    const uint32_t* step_ptr) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t step = step_ptr ? *step_ptr : 0u;
   const float ks = 1.f / (1.f - p);
   const uint32_t thresh = static_cast<uint32_t>(p * 4294967296.0);
@@ -582,6 +611,8 @@ __global__ void dropout_fwd_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, uin
   }
 }
 __global__ void dropout_bwd_kernel(const float* dacc, const uint8_t* mask, __nv_bfloat16* dx, long long n, float p) {
+  pdl_trigger();
+  pdl_wait();
   const float ks = 1.f / (1.f - p);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dx[i] = __float2bfloat16((mask == nullptr || mask[i]) ? dacc[i] * (mask ? ks : 1.f) : 0.f);
@@ -591,6 +622,8 @@ __global__ void dropout_bwd_kernel(const float* dacc, const uint8_t* mask, __nv_
 // one warp per sample: loss_sum += -log softmax[label] / B; dlogits = (softmax - onehot) / B  (fp32, ld = ldd)
 __global__ void ce_fwd_bwd_kernel(const float* logits, const long long* labels, float* dlogits, float* loss_sum,
                                   int* nan_flag, int B, int C, int ldd) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B) return;
@@ -619,6 +652,8 @@ __global__ void ce_fwd_bwd_kernel(const float* logits, const long long* labels, 
 // ============================================================================ optimisers (flat)
 // v = mu*v + g ; p -= lr*v ; g = 0 ; optional bf16 shadow copy of p  (torch.optim.SGD, no dampening/nesterov/wd)
 __global__ void sgd_momentum_kernel(float4* p, float4* g, float4* m, uint2* p_bf16, long long n4, float lr, float mu, int first_step) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 gi = g[i];
     float4 mi = m[i], pi = p[i];
@@ -633,6 +668,8 @@ __global__ void sgd_momentum_kernel(float4* p, float4* g, float4* m, uint2* p_bf
 }
 __global__ void adamw_kernel(float4* p, float4* g, float4* m, float4* v, uint2* p_bf16, long long n4, float lr, float b1, float b2,
                              float eps, float wd, float bc1, float bc2) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 gi = g[i];
     float4 mi = m[i], vi = v[i], pi = p[i];
@@ -653,6 +690,8 @@ __global__ void adamw_kernel(float4* p, float4* g, float4* m, float4* v, uint2* 
   }
 }
 __global__ void cast_f32_bf16_kernel(const float4* x, uint2* y, long long n4) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = x[i];
     y[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
@@ -667,6 +706,8 @@ struct FedAvgParams {
   int nsrc;
 };
 __global__ void __launch_bounds__(512) fedavg_kernel(float4* out, uint2* out_bf16, const FedAvgParams p, long long n4) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
@@ -717,20 +758,20 @@ int slb_preload_elementwise() {
 
 int slb_zero(void* p, long long bytes, cudaStream_t st) {
   if (bytes % 16) return -1;
-  zero_kernel<<<grid_for(bytes / 16, 256), 256, 0, st>>>(reinterpret_cast<float4*>(p), bytes / 16);
+  launch_k(zero_kernel, grid_for(bytes / 16, 256), 256, 0, st, reinterpret_cast<float4*>(p), bytes / 16);
   return last_err();
 }
 int slb_wait_flag(const uint32_t* flag, uint32_t expected, uint32_t* expect_ctr, unsigned long long max_spins, int* status,
                   cudaStream_t st) {
-  wait_flag_kernel<<<1, 1, 0, st>>>(flag, expected, expect_ctr, max_spins, status);
+  launch_k(wait_flag_kernel, 1, 1, 0, st, flag, expected, expect_ctr, max_spins, status);
   return last_err();
 }
 int slb_set_flag(uint32_t* flag, uint32_t value, uint32_t* seq, uint32_t* hint, cudaStream_t st) {
-  set_flag_kernel<<<1, 1, 0, st>>>(flag, value, seq, hint);
+  launch_k(set_flag_kernel, 1, 1, 0, st, flag, value, seq, hint);
   return last_err();
 }
 int slb_counter_inc(uint32_t* c, cudaStream_t st) {
-  counter_inc_kernel<<<1, 1, 0, st>>>(c);
+  launch_k(counter_inc_kernel, 1, 1, 0, st, c);
   return last_err();
 }
 
@@ -744,7 +785,7 @@ int slb_bn_relu_pool_fwd(const void* y, const float* sum, const float* sumsq, co
                    save_mean, save_invstd, reinterpret_cast<__nv_bfloat16*>(out), P, C, H, W, relu, pool, momentum, eps,
                    update_running, identity, ticket, flag, seq, hint};
   const long long work = (pool ? (long long)P / 4 : P) * (C / 8);
-  bn_relu_pool_fwd_kernel<<<grid_for(work, 256, 148 * 4), 256, 2 * C * sizeof(float), st>>>(p);
+  launch_k(bn_relu_pool_fwd_kernel, grid_for(work, 256, 148 * 4), 256, 2 * C * sizeof(float), st, p);
   return last_err();
 }
 
@@ -760,11 +801,11 @@ int slb_bn_relu_pool_bwd(const void* dout, const void* y, const float* gamma, co
   const long long outP = pool ? (long long)P / 4 : P;
   const int grid = grid_for(outP, ty, 148 * 2);
   if (pool) {
-    if (!identity) bn_bwd_reduce_kernel<true><<<grid, block, 2 * C * sizeof(float), st>>>(p);
-    bn_bwd_apply_kernel<true><<<grid, block, 0, st>>>(p);
+    if (!identity) launch_k(bn_bwd_reduce_kernel<true>, grid, block, 2 * C * sizeof(float), st, p);
+    launch_k(bn_bwd_apply_kernel<true>, grid, block, 0, st, p);
   } else {
-    if (!identity) bn_bwd_reduce_kernel<false><<<grid, block, 2 * C * sizeof(float), st>>>(p);
-    bn_bwd_apply_kernel<false><<<grid, block, 0, st>>>(p);
+    if (!identity) launch_k(bn_bwd_reduce_kernel<false>, grid, block, 2 * C * sizeof(float), st, p);
+    launch_k(bn_bwd_apply_kernel<false>, grid, block, 0, st, p);
   }
   return last_err();
 }
@@ -772,14 +813,14 @@ int slb_bn_relu_pool_bwd(const void* dout, const void* y, const float* gamma, co
 int slb_conv_finalize(const float* acc, const float* bias, void* y, float* sum, float* sumsq, long long P, int C, cudaStream_t st) {
   if (C % 8) return -1;
   const int tx = C / 8, ty = tx >= 256 ? 1 : 256 / tx;
-  conv_finalize_kernel<<<grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st>>>(
+  launch_k(conv_finalize_kernel, grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st, 
       acc, bias, reinterpret_cast<__nv_bfloat16*>(y), sum, sumsq, P, C);
   return last_err();
 }
 int slb_col_stats(const void* y, float* sum, float* sumsq, long long P, int C, cudaStream_t st) {
   if (C % 8) return -1;
   const int tx = C / 8, ty = tx >= 256 ? 1 : 256 / tx;
-  col_stats_kernel<<<grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st>>>(
+  launch_k(col_stats_kernel, grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st, 
       reinterpret_cast<const __nv_bfloat16*>(y), sum, sumsq, P, C);
   return last_err();
 }
@@ -789,10 +830,10 @@ int slb_conv3x3_small_fwd(const float* x, const float* w, const float* bias, voi
   const long long P = (long long)B * H * W;
   const int grid = static_cast<int>((P + 127) / 128);
   __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
-  if (Cin == 3 && Cout == 64) conv3x3_small_fwd_kernel<3, 64><<<grid, 128, 0, st>>>(x, w, bias, yy, sum, sumsq, B, H, W);
-  else if (Cin == 3 && Cout == 32) conv3x3_small_fwd_kernel<3, 32><<<grid, 128, 0, st>>>(x, w, bias, yy, sum, sumsq, B, H, W);
-  else if (Cin == 1 && Cout == 64) conv3x3_small_fwd_kernel<1, 64><<<grid, 128, 0, st>>>(x, w, bias, yy, sum, sumsq, B, H, W);
-  else if (Cin == 1 && Cout == 32) conv3x3_small_fwd_kernel<1, 32><<<grid, 128, 0, st>>>(x, w, bias, yy, sum, sumsq, B, H, W);
+  if (Cin == 3 && Cout == 64) launch_k(conv3x3_small_fwd_kernel<3, 64>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
+  else if (Cin == 3 && Cout == 32) launch_k(conv3x3_small_fwd_kernel<3, 32>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
+  else if (Cin == 1 && Cout == 64) launch_k(conv3x3_small_fwd_kernel<1, 64>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
+  else if (Cin == 1 && Cout == 32) launch_k(conv3x3_small_fwd_kernel<1, 32>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
   else return -2;
   return last_err();
 }
@@ -805,46 +846,46 @@ int slb_conv3x3_small_wgrad(const float* x, const void* dy, float* dw, int B, in
   if (Cin == 3) {
     static bool done3 = false;
     if (!done3) { cudaFuncSetAttribute(conv3x3_small_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done3 = true; }
-    conv3x3_small_wgrad_kernel<3><<<grid, 256, smem, st>>>(x, d, dw, B, H, W, Cout);
+    launch_k(conv3x3_small_wgrad_kernel<3>, grid, 256, smem, st, x, d, dw, B, H, W, Cout);
   } else if (Cin == 1) {
     static bool done1 = false;
     if (!done1) { cudaFuncSetAttribute(conv3x3_small_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done1 = true; }
-    conv3x3_small_wgrad_kernel<1><<<grid, 256, smem, st>>>(x, d, dw, B, H, W, Cout);
+    launch_k(conv3x3_small_wgrad_kernel<1>, grid, 256, smem, st, x, d, dw, B, H, W, Cout);
   } else return -2;
   return last_err();
 }
 
 int slb_linear_finalize(const float* acc, const float* bias, void* out, float* out_f32, uint8_t* mask, int B, int N, int ldo,
                         int relu, float drop_p, uint32_t seed, const uint32_t* step_ptr, cudaStream_t st) {
-  linear_finalize_kernel<<<grid_for((long long)B * N, 256), 256, 0, st>>>(acc, bias, reinterpret_cast<__nv_bfloat16*>(out), out_f32,
+  launch_k(linear_finalize_kernel, grid_for((long long)B * N, 256), 256, 0, st, acc, bias, reinterpret_cast<__nv_bfloat16*>(out), out_f32,
                                                                          mask, B, N, ldo, relu, drop_p, seed, step_ptr);
   return last_err();
 }
 int slb_linear_bwd_prep(const float* dacc, const void* yout, const uint8_t* mask, void* dz, float* dbias, int B, int N, int ldy,
                         int ldz, int relu, float drop_p, cudaStream_t st) {
-  linear_bwd_prep_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(dacc, reinterpret_cast<const __nv_bfloat16*>(yout), mask,
+  launch_k(linear_bwd_prep_kernel, (N + 31) / 32, dim3(32, 8), 0, st, dacc, reinterpret_cast<const __nv_bfloat16*>(yout), mask,
                                                                reinterpret_cast<__nv_bfloat16*>(dz), dbias, B, N, ldy, ldz, relu,
                                                                drop_p);
   return last_err();
 }
 int slb_dropout_fwd(const void* x, void* y, uint8_t* mask, long long n, float p, uint32_t seed, const uint32_t* step_ptr,
                     cudaStream_t st) {
-  dropout_fwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+  launch_k(dropout_fwd_kernel, grid_for(n, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
                                                       mask, n, p, seed, step_ptr);
   return last_err();
 }
 int slb_dropout_bwd(const float* dacc, const uint8_t* mask, void* dx, long long n, float p, cudaStream_t st) {
-  dropout_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dacc, mask, reinterpret_cast<__nv_bfloat16*>(dx), n, p);
+  launch_k(dropout_bwd_kernel, grid_for(n, 256), 256, 0, st, dacc, mask, reinterpret_cast<__nv_bfloat16*>(dx), n, p);
   return last_err();
 }
 int slb_ce_fwd_bwd(const float* logits, const long long* labels, float* dlogits, float* loss_sum, int* nan_flag, int B, int C,
                    int ldd, cudaStream_t st) {
-  ce_fwd_bwd_kernel<<<(B * 32 + 127) / 128, 128, 0, st>>>(logits, labels, dlogits, loss_sum, nan_flag, B, C, ldd);
+  launch_k(ce_fwd_bwd_kernel, (B * 32 + 127) / 128, 128, 0, st, logits, labels, dlogits, loss_sum, nan_flag, B, C, ldd);
   return last_err();
 }
 int slb_sgd_momentum(float* p, float* g, float* m, void* p_bf16, long long n, float lr, float mu, int first_step, cudaStream_t st) {
   if (n % 4) return -1;
-  sgd_momentum_kernel<<<grid_for(n / 4, 256, 148 * 16), 256, 0, st>>>(reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
+  launch_k(sgd_momentum_kernel, grid_for(n / 4, 256, 148 * 16), 256, 0, st, reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
                                                                      reinterpret_cast<float4*>(m), reinterpret_cast<uint2*>(p_bf16),
                                                                      n / 4, lr, mu, first_step);
   return last_err();
@@ -852,14 +893,14 @@ int slb_sgd_momentum(float* p, float* g, float* m, void* p_bf16, long long n, fl
 int slb_adamw(float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float b1, float b2, float eps, float wd,
               float bc1, float bc2, cudaStream_t st) {
   if (n % 4) return -1;
-  adamw_kernel<<<grid_for(n / 4, 256, 148 * 16), 256, 0, st>>>(reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
+  launch_k(adamw_kernel, grid_for(n / 4, 256, 148 * 16), 256, 0, st, reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
                                                               reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
                                                               reinterpret_cast<uint2*>(p_bf16), n / 4, lr, b1, b2, eps, wd, bc1, bc2);
   return last_err();
 }
 int slb_cast_f32_bf16(const float* x, void* y, long long n, cudaStream_t st) {
   if (n % 4) return -1;
-  cast_f32_bf16_kernel<<<grid_for(n / 4, 256, 148 * 16), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y), n / 4);
+  launch_k(cast_f32_bf16_kernel, grid_for(n / 4, 256, 148 * 16), 256, 0, st, reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y), n / 4);
   return last_err();
 }
 // srcs: host array of nsrc device pointers (local or peer-mapped), coefs: host array
@@ -868,7 +909,7 @@ int slb_fedavg(float* out, void* out_bf16, const float* const* srcs, const float
   FedAvgParams p;
   for (int i = 0; i < 16; ++i) { p.src[i] = i < nsrc ? srcs[i] : nullptr; p.coef[i] = i < nsrc ? coefs[i] : 0.f; }
   p.nsrc = nsrc;
-  fedavg_kernel<<<grid_for(n / 4, 512, 148 * 4), 512, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<uint2*>(out_bf16), p, n / 4);
+  launch_k(fedavg_kernel, grid_for(n / 4, 512, 148 * 4), 512, 0, st, reinterpret_cast<float4*>(out), reinterpret_cast<uint2*>(out_bf16), p, n / 4);
   return last_err();
 }
 

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace slb {
 
@@ -171,9 +172,40 @@ __device__ __forceinline__ void red_add_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the stage programs is launched with programmaticStreamSerialization: it may begin (barrier init,
+// TMEM allocation, descriptor prefetch, parameter loads) while its predecessor drains, and must execute pdl_wait()
+// before touching global memory.  pdl_trigger() lets the *next* kernel start its own prologue early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// host: launch with the PDL attribute (SLB200_PDL=0 disables it; the device-side waits then are no-ops)
+inline int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SLB200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace slb

@@ -83,6 +83,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const GemmParams p) {
   using L = SmemLayout<BLOCK_N>;
   constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  pdl_trigger();                      // the next kernel may start its prologue now
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::TILE_BYTES);
@@ -117,6 +118,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                         // predecessor grids complete + visible; prologue above overlapped with their tail
 
   if (my_iters > 0) {
     if (warp == 0) {
@@ -445,7 +447,8 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& 
     if (e != cudaSuccess) return -static_cast<int>(e) - 1000;
     attr_done = true;
   }
-  k<<<grid, 192, SmemLayout<BN>::TOTAL, st>>>(a, b, p);
+  cudaError_t e0 = launch_k(k, grid, dim3(192), SmemLayout<BN>::TOTAL, st, a, b, p);
+  if (e0 != cudaSuccess) return -static_cast<int>(e0) - 2000;
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -static_cast<int>(e) - 2000;
 }

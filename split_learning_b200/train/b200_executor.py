@@ -437,6 +437,9 @@ class _Plan:
         self.dlogits = torch.zeros(B, ex.num_classes, device=dev) if ex.is_last else None
         self.ticket = torch.zeros(4, device=dev, dtype=torch.int32)
         self.tile_counters = torch.zeros(4096, device=dev, dtype=torch.int32)   # split-K tile semaphores (self-resetting)
+        # weight-gradient kernels run on a forked stream: they only feed the optimizer, so they overlap with the
+        # dY -> dX critical path of the layers below (captured as parallel branches of the CUDA graph)
+        self.side = torch.cuda.Stream(device=dev)
         self.graphs: Dict[Tuple[str, int], torch.cuda.CUDAGraph] = {}
         self._warm = False
 
@@ -559,6 +562,20 @@ class _Plan:
         """dout: gradient w.r.t. the stage output (bf16) — or fp32 dlogits on the last stage."""
         ex = self.ex
         g: Any = dout
+        main = torch.cuda.current_stream()
+        side = self.side
+        forked = False
+
+        def on_side(fn):
+            """Run ``fn`` (weight-gradient launches) on the side stream after everything issued so far on ``main``."""
+            nonlocal forked
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                fn()
+            forked = True
+
         for bi in range(len(ex.blocks) - 1, -1, -1):
             b, a = ex.blocks[bi], self.act[bi]
             need_dx = not (bi == 0 and ex.is_first)
@@ -567,7 +584,7 @@ class _Plan:
                 if g.dtype != torch.float32:
                     g = g.float()                                   # compat path only (outside graphs)
                 N.linear_bwd_prep(g, a["out"], a["mask"], a["dz"], ex.view(ex.G, f"layer{b.lin}.bias"), b.relu, b.drop)
-                N.linear_wgrad(a["dz"], a["in"], ex.view(ex.G, f"layer{b.lin}.weight"))
+                on_side(lambda a=a, b=b: N.linear_wgrad(a["dz"], a["in"], ex.view(ex.G, f"layer{b.lin}.weight")))
                 if need_dx:
                     dacc = self.s(bi, "dacc_in", (self.B, b.fin))
                     N.linear_dgrad(a["dz"], ex.view(ex.PB, f"layer{b.lin}.weight"), dacc,
@@ -606,9 +623,9 @@ class _Plan:
                     # else: a conv bias feeding train-mode BatchNorm has an identically zero gradient
                     # (sum_p dy = gamma*invstd*(sum dz - P*mean(dz) - mean(dz*xhat)*sum xhat) = 0): G stays 0.
                     if b.cin <= 4:
-                        N.conv3x3_small_wgrad(a["in"], dy, ex.view(ex.G, f"layer{b.conv}.weight"))
+                        on_side(lambda a=a, b=b, dy=dy: N.conv3x3_small_wgrad(a["in"], dy, ex.view(ex.G, f"layer{b.conv}.weight")))
                     else:
-                        N.conv3x3_wgrad(a["in"], dy, ex.view(ex.G, f"layer{b.conv}.weight"))
+                        on_side(lambda a=a, b=b, dy=dy: N.conv3x3_wgrad(a["in"], dy, ex.view(ex.G, f"layer{b.conv}.weight")))
                         if need_dx:
                             dx = a["dx"] if not (bi == 0 and grad_out_override is not None) else grad_out_override
                             dacc = self.s(bi, "dacc") if (bi, "dacc") in self.soff else None
@@ -616,6 +633,8 @@ class _Plan:
                             g = dx
                 else:
                     g = dy
+        if forked:
+            main.wait_stream(side)                      # join: every weight gradient is complete
         # optimizer: one fused pass over the flat buffers (also zeroes G and refreshes the bf16 shadow)
         N.sgd_momentum(ex.P, ex.G, ex.M, ex.PB, ex.lr, ex.mu)
         N.counter_inc(ex.step_ctr)
