@@ -218,6 +218,19 @@ class B200Executor(StageExecutor):
                 self.entries[f"layer{b.lin}.bias"] = (off, (b.fout,))
                 off += _align(b.fout)
         self.n_params = max(off, 128)
+        # contiguous [start, end) of every block's parameters in the flat buffers (per-block optimizer launches)
+        self.block_range: Dict[int, Tuple[int, int]] = {}
+        for bi, b in enumerate(self.blocks):
+            keys = []
+            if isinstance(b, ConvBlock):
+                keys = [f"layer{b.conv}.weight", f"layer{b.conv}.bias"] if b.conv is not None else []
+                keys += [f"layer{b.bn}.weight", f"layer{b.bn}.bias"] if b.bn is not None else []
+            elif isinstance(b, LinearBlock):
+                keys = [f"layer{b.lin}.weight", f"layer{b.lin}.bias"]
+            if keys:
+                lo = min(self.entries[k][0] for k in keys)
+                hi = max(_align(self.entries[k][0] + math.prod(self.entries[k][1])) for k in keys)
+                self.block_range[bi] = (lo, hi)
         dev = self.device
         self.P = torch.zeros(self.n_params, device=dev)
         self.G = torch.zeros(self.n_params, device=dev)
@@ -566,6 +579,10 @@ class _Plan:
         side = self.side
         forked = False
 
+        def sgd_block(bi):
+            lo, hi = ex.block_range[bi]
+            N.sgd_momentum(ex.P[lo:hi], ex.G[lo:hi], ex.M[lo:hi], ex.PB[lo:hi], ex.lr, ex.mu)
+
         def on_side(fn):
             """Run ``fn`` (weight-gradient launches) on the side stream after everything issued so far on ``main``."""
             nonlocal forked
@@ -592,6 +609,9 @@ class _Plan:
                     g = dacc
                     if bi == 0:                                     # stage input gradient leaves as bf16
                         N.dropout_bwd(dacc, None, a["dx_bf16"], 0.0)
+                # this block's optimizer step runs on the side stream as soon as its dgrad (the last reader of the
+                # bf16 weights) has been issued: the 134 MB classifier update hides behind the conv backward chain
+                on_side(lambda bi=bi: sgd_block(bi))
             elif isinstance(b, DropoutOp):
                 N.dropout_bwd(g, a["mask"], a["dx"], b.p)
                 g = a["dx"]
@@ -633,10 +653,10 @@ class _Plan:
                             g = dx
                 else:
                     g = dy
+                if bi in ex.block_range:
+                    on_side(lambda bi=bi: sgd_block(bi))
         if forked:
-            main.wait_stream(side)                      # join: every weight gradient is complete
-        # optimizer: one fused pass over the flat buffers (also zeroes G and refreshes the bf16 shadow)
-        N.sgd_momentum(ex.P, ex.G, ex.M, ex.PB, ex.lr, ex.mu)
+            main.wait_stream(side)                      # join: every weight gradient and parameter update is complete
         N.counter_inc(ex.step_ctr)
 
     def _last(self, slot: int = 0, labels: Optional[torch.Tensor] = None, grad_out_override=None) -> None:
