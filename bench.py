@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--timeout", type=float, default=1500.0)
     ap.add_argument("--breakdown", action="store_true", help="also report device time per stage program (F / L / B)")
+    ap.add_argument("--no-overlap", action="store_true", help="N=1: run both stages on one stream")
     return ap.parse_args()
 
 
@@ -122,7 +123,7 @@ def run_ours(args) -> dict:
     W, K, B = args.warmup, args.steps, args.batch
     ex1 = B200Executor(VGG16_CIFAR10(0, args.cut), "VGG16", learning, dev, is_first=True, use_graphs=not args.no_graphs)
     ex2 = B200Executor(VGG16_CIFAR10(args.cut, 52), "VGG16", learning, dev, is_last=True, use_graphs=not args.no_graphs)
-    pipe = LocalPipeline([ex1, ex2], B, args.depth)
+    pipe = LocalPipeline([ex1, ex2], B, args.depth, overlap=not (args.no_overlap or args.breakdown))
     pool = synthetic_batches(16, B, seed=1)
     loss_host = torch.zeros(4).pin_memory()
 
@@ -152,6 +153,7 @@ def run_ours(args) -> dict:
         pipe.step_forward()
     while pipe.it_b < pipe.it_f:
         pipe.step_backward()
+    pipe.join()
     with torch.cuda.stream(pipe.stream):
         e1.record()
     torch.cuda.synchronize()
@@ -168,11 +170,12 @@ def run_ours(args) -> dict:
             pipe.step_backward()
         pipe.feed(x, y)
         pipe.step_forward()
-        with torch.cuda.stream(pipe.stream):
+        with torch.cuda.stream(pipe.loss_stream):
             loss_host.copy_(pipe.loss(), non_blocking=True)
         n += 1
     while pipe.it_b < pipe.it_f:
         pipe.step_backward()
+    pipe.join()
     with torch.cuda.stream(pipe.stream):
         f1.record()
     torch.cuda.synchronize()
@@ -212,7 +215,7 @@ def run_ours(args) -> dict:
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"model": "VGG16_CIFAR10", "global_batch": B, "microbatch": B, "seq_len": None, "cut_layers": [args.cut],
-                   "clients": [1, 1], "control_count": args.depth, "parallelism": "pp2 (both stages on one GPU)",
+                   "clients": [1, 1], "control_count": args.depth, "parallelism": "pp2 (both stages on one GPU, one stream per stage)",
                    "optimizer": "SGD lr=5e-4 momentum=0.5, step per microbatch", "recompute": True,
                    "cuda_graphs": not args.no_graphs,
                    "l2": "per-step working set ~470 MB (fp32 master+momentum+grad+bf16 shadow) > 126 MB L2; no flush needed"},

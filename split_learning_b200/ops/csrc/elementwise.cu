@@ -763,6 +763,11 @@ int slb_zero(void* p, long long bytes, cudaStream_t st) {
 }
 int slb_wait_flag(const uint32_t* flag, uint32_t expected, uint32_t* expect_ctr, unsigned long long max_spins, int* status,
                   cudaStream_t st) {
+  static bool carve = false;
+  if (!carve) {   // an SM hosting this spinner should already be configured for large-smem CTAs of sibling kernels
+    cudaFuncSetAttribute(wait_flag_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carve = true;
+  }
   launch_k(wait_flag_kernel, 1, 1, 0, st, flag, expected, expect_ctr, max_spins, status);
   return last_err();
 }

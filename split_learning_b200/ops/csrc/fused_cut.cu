@@ -351,9 +351,12 @@ static int launch_fused(const CUtensorMap& a, const CUtensorMap& b, const FusedC
     if (e != cudaSuccess) return -static_cast<int>(e) - 1000;
     attr_done = true;
   }
-  void* args[] = {const_cast<CUtensorMap*>(&a), const_cast<CUtensorMap*>(&b), const_cast<FusedCutParams*>(&p)};
-  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k), dim3(grid), dim3(192), args,
-                                              FusedSmem<BN>::TOTAL, st);
+  // Plain (non-cooperative) launch with grid <= #SMs and one CTA per SM (152+ KB of smem each): co-residency of the
+  // software grid barrier holds as soon as every SM has drained whatever independent kernel of another stream it was
+  // running.  cudaLaunchCooperativeKernel is NOT used: the driver would not start it while any other kernel of the
+  // context is resident — e.g. the next stage's flag-wait kernel that only this kernel can release (observed dead-lock).
+  k<<<dim3(grid), dim3(192), FusedSmem<BN>::TOTAL, st>>>(a, b, p);
+  cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -static_cast<int>(e) - 2000;
 }
 
@@ -388,7 +391,11 @@ int slb_conv_bn_act_p2p(const void* x, const void* w, const float* bias, const f
   p.M = M; p.N = Cout; p.C = Cin; p.H = H; p.W = W;
   p.tiles_m = (M + 127) / 128; p.tiles_n = Cout / bn;
   const int total = p.tiles_m * p.tiles_n;
-  int grid = total < num_sms ? total : num_sms;
+  // Leave a few SMs out of the persistent grid: an SM that currently hosts a small flag-wait kernel of another stream
+  // cannot switch its shared-memory carve-out to admit a 150 KB CTA until that kernel exits — and that kernel may be
+  // waiting for *this* kernel's flag.  With spare SMs every CTA of the software grid barrier can always become resident.
+  const int usable = num_sms > 8 ? num_sms - 4 : num_sms;
+  int grid = total < usable ? total : usable;
   if ((total + grid - 1) / grid > 512 / bn) return -15;          // accumulators would not fit in TMEM
   CUtensorMap ta, tbm;
   {

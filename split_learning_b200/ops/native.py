@@ -214,7 +214,7 @@ def fused_cut_supported(B, H, W, Cin, Cout, pool) -> bool:
         return False
     bn = 256 if Cout >= 256 else Cout
     total = ((B * H * W + 127) // 128) * (Cout // bn)
-    grid = min(total, 148)
+    grid = min(total, 144)
     return (total + grid - 1) // grid <= 512 // bn
 
 

@@ -153,7 +153,13 @@ class DeviceStage:
 
     def check(self) -> None:
         if int(self.status[0].item()) != 0:
-            raise TimeoutError("device pipeline: a mailbox flag never arrived (peer stage dead?)")
+            def flags(mb):
+                return None if mb is None or mb.flags is None else mb.flags.tolist()
+            raise TimeoutError(
+                "device pipeline: a mailbox flag never arrived (peer stage dead?) "
+                f"[stage first={self.ex.is_first} last={self.ex.is_last} seq_fwd={self.seq_fwd.ctr[::4].tolist()} "
+                f"seq_grad={self.seq_grad.ctr[::4].tolist()} exp_fwd={self.exp_fwd.ctr[::4].tolist()} "
+                f"exp_grad={self.exp_grad.ctr[::4].tolist()} fwd_in.flags={flags(self.fwd_in)} grad_in.flags={flags(self.grad_in)}]")
 
     def reset_counters(self) -> None:
         for c in (self.seq_fwd, self.seq_grad, self.exp_fwd, self.exp_grad):
@@ -161,18 +167,21 @@ class DeviceStage:
 
 
 class LocalPipeline:
-    """All stages of one chain on one GPU / one stream (the N = 1 configuration).
+    """All stages of one chain on one GPU (the N = 1 configuration), one CUDA stream per stage.
 
-    The host enqueues a dependency-ordered schedule, so every flag wait is already satisfied
-    when its kernel runs; mailboxes are plain local allocations (producer pointer == consumer
-    pointer), i.e. exactly the multi-GPU kernels with ``peer = self``.
+    Mailboxes are plain local allocations (producer pointer == consumer pointer), i.e. exactly the
+    multi-GPU kernels with ``peer = self``; the mailbox flags are the only synchronisation between
+    the stage streams, so stage 1's recompute+backward of microbatch i-3 overlaps stage 2's work on
+    microbatch i.  The host enqueues producers before their consumers, so every flag wait is
+    released by work that is already submitted.  ``overlap=False`` puts all stages on one stream.
     """
 
-    def __init__(self, executors: Sequence[B200Executor], batch: int, depth: int):
+    def __init__(self, executors: Sequence[B200Executor], batch: int, depth: int, overlap: bool = True):
         assert executors[0].is_first and executors[-1].is_last
         self.depth, self.B = depth, batch
         dev = executors[0].device
         stream = executors[0].stream
+        self.overlap = overlap
         self.stages: List[DeviceStage] = []
         n = len(executors)
         acts = [Mailbox.allocate_local(act_spec(executors[i], batch, depth), dev) for i in range(n - 1)]
@@ -181,8 +190,10 @@ class LocalPipeline:
             self.stages.append(DeviceStage(
                 ex, batch, depth,
                 fwd_in=acts[i - 1] if i > 0 else None, grad_in=grads[i] if i < n - 1 else None,
-                fwd_out=acts[i] if i < n - 1 else None, grad_out=grads[i - 1] if i > 0 else None, stream=stream))
+                fwd_out=acts[i] if i < n - 1 else None, grad_out=grads[i - 1] if i > 0 else None,
+                stream=(ex.stream if overlap else stream)))
         self.stream = stream
+        self.streams = [st.stream for st in self.stages]
         self.it_f = 0
         self.it_b = 0
 
@@ -222,7 +233,18 @@ class LocalPipeline:
     def loss(self) -> torch.Tensor:
         return self.stages[-1].ex.loss_buf
 
+    @property
+    def loss_stream(self) -> torch.cuda.Stream:
+        return self.stages[-1].stream
+
+    def join(self) -> None:
+        """Make ``self.stream`` (stage 1's) wait for every other stage stream (for event timing)."""
+        for st in self.streams:
+            if st is not self.stream:
+                self.stream.wait_stream(st)
+
     def synchronize(self) -> None:
-        self.stream.synchronize()
+        for st in self.streams:
+            st.synchronize()
         for s in self.stages:
             s.check()

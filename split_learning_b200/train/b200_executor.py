@@ -176,7 +176,8 @@ class B200Executor(StageExecutor):
         self.is_first, self.is_last = is_first, is_last
         self.recompute = recompute
         self.use_graphs = use_graphs
-        self.fused_cut = fused_cut
+        import os
+        self.fused_cut = fused_cut and os.environ.get("SLB200_FUSED_CUT", "1") != "0"
         self.lr = float(learning.get("learning-rate", 0.01))
         self.mu = float(learning.get("momentum", 0.0))
         self.seed = seed

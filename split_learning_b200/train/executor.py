@@ -32,6 +32,12 @@ _ADAMW_MODELS = ("BERT", "KWT", "VIT")
 def make_optimizer(model: nn.Module, model_name: str, learning: dict) -> torch.optim.Optimizer:
     params = [p for p in model.parameters() if p.requires_grad]
     lr = float(learning.get("learning-rate", 0.01))
+    adamw = model_name.upper() in _ADAMW_MODELS
+    if params and params[0].is_cuda:
+        # CUDA: one flat buffer + the fused sm_100a optimizer kernels (no silent fallback: a missing library raises)
+        from ..ops.optim import FlatFusedOptimizer
+        return FlatFusedOptimizer(params, "adamw" if adamw else "sgd", lr=lr, momentum=float(learning.get("momentum", 0.0)),
+                                  weight_decay=float(learning.get("weight-decay", 0.01)))
     if model_name.upper() in _ADAMW_MODELS:
         return torch.optim.AdamW(params, lr=lr, weight_decay=float(learning.get("weight-decay", 0.01)))
     return torch.optim.SGD(params, lr=lr, momentum=float(learning.get("momentum", 0.0)))
@@ -57,7 +63,7 @@ class StageExecutor:
 class TorchExecutor(StageExecutor):
     def __init__(self, model: SplitModel, model_name: str, learning: dict, device="cpu", is_first=False,
                  is_last=False, recompute: bool = True, clip_grad_norm: float = 0.0):
-        self.model = model.to(device)
+        self.model = model.to(device)       # parameters must sit on the device before the optimizer re-homes them
         self.model_name = model_name
         self.device = device
         self.is_first, self.is_last = is_first, is_last
