@@ -132,6 +132,7 @@ class DeviceStage:
     def forward(self, it: int) -> None:
         self._gate_wait(self.fwd_in, it)
         self._exec("F", it % self.depth)
+        self._posted["F"] += 1
         self._gate_post(self.fwd_out)
 
     def backward(self, it: int) -> None:
@@ -142,6 +143,7 @@ class DeviceStage:
     def last(self, it: int) -> None:
         self._gate_wait(self.fwd_in, it)
         self._exec("L", it % self.depth)
+        self._posted["L"] += 1
         self._gate_post(self.grad_out)
 
     def stage_input(self, it: int, x_host: torch.Tensor, y_host: torch.Tensor) -> None:

@@ -89,6 +89,55 @@ def run_steps(st: DeviceStage, n_steps: int, batches=None, loss_host: Optional[t
                     loss_host.copy_(st.ex.loss_buf, non_blocking=True)
 
 
+def fedavg_round(st: DeviceStage, rank: int, world: int, dev) -> Optional[dict]:
+    """End-of-round aggregation as the reference does it once per round (src/Server.py:398-434) — here in place over
+    NVLink: every replica of a stage averages its flat fp32 parameters (+ BN running statistics) with its peers,
+    weights = microbatch counts.  Not part of the timed training steps (the reference aggregates outside the epoch
+    loop as well); its device time is reported separately.  Collective: every rank must call."""
+    from .fedavg import PeerFedAvg, average_int_state
+    n = world // 2
+    first_ranks, last_ranks = list(range(n)), list(range(n, world))
+    g_first = dist.new_group(first_ranks)
+    g_last = dist.new_group(last_ranks)
+    if n < 2:
+        return None
+    ex = st.ex
+    mine, grp = (first_ranks, g_first) if ex.is_first else (last_ranks, g_last)
+    stats = [t for bn in ex.bn_state.values() for t in (bn["running_mean"], bn["running_var"])]
+    n_stats = sum(t.numel() for t in stats)
+    flat_stats = torch.cat([t.reshape(-1) for t in stats]) if stats else torch.zeros(0, device=dev)
+    pad = (-n_stats) % 4
+    flat_stats = torch.cat([flat_stats, torch.zeros(pad, device=dev)]) if pad else flat_stats
+    fa = PeerFedAvg(ex.n_params, dev, mine, group=grp)
+    fs = PeerFedAvg(max(flat_stats.numel(), 4), dev, mine, group=grp)
+    weight = float(st._posted["F"] + st._posted["L"] or 1)      # microbatches processed (the reference's FedAvg weight)
+    ok = not ex.nan_detected()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    done = fa.average(ex.P, ex.PB, weight, ok=ok)
+    if flat_stats.numel():
+        fs.average(flat_stats, None, weight, ok=ok)
+        o = 0
+        for t in stats:
+            t.copy_(flat_stats[o:o + t.numel()].view_as(t))
+            o += t.numel()
+    average_int_state({f"nbt{i}": bn["num_batches_tracked"] for i, bn in ex.bn_state.items()}, weight, group=grp)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # replicas of a stage must now hold identical parameters
+    chk = ex.P[:1024].clone()
+    ref = chk.clone()
+    dist.broadcast(ref, src=mine[0], group=grp)
+    same = torch.tensor([float(torch.equal(chk, ref))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    return {"ms_max_over_ranks": float(ms.item()), "replicas_per_stage": n, "aggregated": bool(done),
+            "stage2_param_bytes": 4 * ex.n_params if not ex.is_first else None, "replicas_identical": bool(same.item() > 0.5),
+            "note": "in-place NVLink peer-load FedAvg incl. staging copy + 2 barriers; outside the timed steps"}
+
+
 def bench_multi_gpu(args) -> dict:
     from bench import ClockSampler, synthetic_batches     # bench.py is the entry script (repo root on sys.path)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -145,6 +194,9 @@ def bench_multi_gpu(args) -> dict:
     t1 = time.perf_counter()
     st.check()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
+    fed = None
+    if os.environ.get("SLB200_BENCH_FEDAVG", "1") != "0":
+        fed = fedavg_round(st, rank, world, dev)          # round end: NVLink FedAvg among the replicas of each stage
     per = torch.tensor([float(sum(st.launches_per.values()))], device=dev)
     dist.all_reduce(per, op=dist.ReduceOp.SUM)
     loss = torch.tensor([float(loss_host[0]) if not st.ex.is_first else 0.0], device=dev)
@@ -165,6 +217,6 @@ def bench_multi_gpu(args) -> dict:
                    "l2": "per-step working set ~470 MB on stage-2 GPUs > 126 MB L2; no flush needed"},
         "e2e": {"value": images / (results["e2e"] / 1e3), "unit": "images/s", "ms_per_step": results["e2e"] / K,
                 "h2d_bytes_per_step": n * (B * 3 * 32 * 32 * 4 + B * 8), "d2h_bytes_per_step": n * 16},
-        "gpu_launches": int(per.item()) // 1 * K // 1, "launches_per_step": int(per.item()), "clocks": clocks,
-        "final_loss": float(loss.item()) / n, "impl": "ours",
+        "gpu_launches": int(per.item()) * K, "launches_per_step": int(per.item()), "clocks": clocks,
+        "final_loss": float(loss.item()) / n, "impl": "ours", "fedavg_round": fed,
     }

@@ -269,3 +269,26 @@ def test_flat_fused_optimizer_matches_torch(model_name, kind):
         if sb[k].is_floating_point() and "in_proj_bias" not in k:
             # (the key-bias third of in_proj_bias has an analytically zero gradient: Adam turns fp32 noise into +-lr)
             assert torch.allclose(sa[k], sb[k], atol=2e-4, rtol=2e-3), k
+
+
+def test_launch_py_device_plane_across_processes(tmp_path):
+    """``launch.py``: server + one OS process per client, both clients on cuda:0, ``data-plane: device`` — the mailboxes
+    are shared through real CUDA IPC handles posted over the TCP broker (cross-process path of the multi-GPU runs)."""
+    import os, subprocess, sys, yaml
+    from split_learning_b200.checkpoint import load_checkpoint
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    raw = yaml.safe_load(open(os.path.join(root, "config.yaml")))
+    raw["server"].update({"clients": [1, 1], "global-round": 1, "validation": False})
+    raw["server"]["data-distribution"]["num-sample"] = 160
+    raw["server"]["manual"]["no-cluster"]["cut-layers"] = [7]
+    raw["log_path"] = str(tmp_path)
+    raw["learning"].update({"batch-size": 32, "control-count": 3})
+    raw["b200"] = {"synthetic-data": True, "data-plane": "device", "watchdog-seconds": 120, "port": 29933}
+    cfg = tmp_path / "config.yaml"
+    yaml.safe_dump(raw, open(cfg, "w"))
+    env = dict(os.environ, SLB200_QUIET="1", SLB200_WAIT_SPINS=str(1 << 26))
+    r = subprocess.run([sys.executable, os.path.join(root, "launch.py"), "--config", str(cfg), "--timeout", "280"],
+                       cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    assert len(sd) == 97 and int(sd["layer9.num_batches_tracked"]) == 5
