@@ -23,9 +23,7 @@ from __future__ import annotations
 
 import random
 import time
-from typing import Dict, List, Optional
-
-import torch
+from typing import List, Optional
 
 from .. import messages as M
 from ..checkpoint import checkpoint_path, save_checkpoint

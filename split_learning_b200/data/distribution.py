@@ -9,7 +9,7 @@ Unlike the reference (quirk C4) the numpy RNG *is* seeded from ``random-seed``.
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Optional
 
 import numpy as np
 

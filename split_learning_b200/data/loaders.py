@@ -17,7 +17,6 @@ import random
 from collections import defaultdict
 from typing import Dict, List, Optional, Sequence, Tuple
 
-import numpy as np
 import torch
 from torch.utils.data import DataLoader, Dataset, Subset
 

@@ -12,8 +12,6 @@ is numerically the reference's softmax(QK^T/sqrt(d))V with dropout on the probab
 """
 from __future__ import annotations
 
-import math
-
 import torch
 import torch.nn as nn
 import torch.nn.functional as F

@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes
 import os
 from ctypes import c_float, c_int, c_longlong, c_uint32, c_uint64, c_void_p
-from typing import Optional, Sequence
+from typing import Sequence
 
 import torch
 

@@ -19,7 +19,6 @@ import torch
 import torch.distributed as dist
 
 from ..models import VGG16_CIFAR10
-from ..ops import native as N
 from ..train.b200_executor import B200Executor
 from .mailbox import Mailbox, MailboxSpec
 from .pipeline import DeviceStage, act_spec

@@ -8,7 +8,7 @@ exact assignment when scikit-learn is importable (used for parity tests).
 """
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import Tuple
 
 import numpy as np
 

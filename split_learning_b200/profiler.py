@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import json
 import time
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 

@@ -8,7 +8,7 @@ from __future__ import annotations
 import threading
 import traceback
 import uuid
-from typing import Dict, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 from .algorithms import client_class, server_class
 from .config import Config

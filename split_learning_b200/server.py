@@ -15,7 +15,6 @@ each (cluster, stage) and are taken as already averaged.
 """
 from __future__ import annotations
 
-import copy
 import os
 import random
 import time
@@ -30,7 +29,7 @@ from .config import Config
 from .data.distribution import label_counts as make_label_counts
 from .fedavg import fedavg_state_dicts, has_nan
 from .log import Logger, print_with_color
-from .plan import ClientInfo, ClusterPlan, Topology, stage_layers
+from .plan import ClientInfo, ClusterPlan, Topology
 from .planning import auto_threshold, clustering_algorithm, partition, partition_multi
 from .transport import Channel
 
@@ -147,8 +146,6 @@ class Server:
                 c.train = True
                 if c.cluster is None or c.cluster < 0:
                     c.cluster = 0
-            if cfg.infor_cluster_given and any(c.extras.get("_unassigned", False) for c in self.clients):
-                pass
             # clients that registered without --cluster are dealt to clusters by infor-cluster
             self._assign_unclustered(ncl)
             clusters = []

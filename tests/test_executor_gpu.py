@@ -292,3 +292,30 @@ def test_launch_py_device_plane_across_processes(tmp_path):
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
     assert len(sd) == 97 and int(sd["layer9.num_batches_tracked"]) == 5
+
+
+@pytest.mark.parametrize("algo,clients,specs,extra", [
+    ("main", (2, 1), [dict(layer_id=1), dict(layer_id=1), dict(layer_id=2)], {}),
+    ("dcsl", (2, 1), [dict(layer_id=1, cluster=0), dict(layer_id=1, cluster=0), dict(layer_id=2, cluster=0)], {"local-round": 1}),
+    ("vanilla_sl", (2, 1), [dict(layer_id=1), dict(layer_id=1), dict(layer_id=2)], {}),
+])
+def test_host_plane_with_native_executor_on_gpu(tmp_path, algo, clients, specs, extra):
+    """Broker data plane (pickled CPU arrays, any topology/variant) driving the native sm_100a stage executor through its
+    tensor API: competing consumers (2:1), DCSL's SDA batch concatenation (B = 64 on the last stage), sequential hand-off."""
+    import yaml
+    from split_learning_b200.checkpoint import load_checkpoint
+    from split_learning_b200.config import normalize
+    from split_learning_b200.runner import run_variant
+    from split_learning_b200.train.b200_executor import B200Executor
+    raw = {"server": {"global-round": 1, "clients": list(clients), "no-cluster": {"cut-layers": [7]}, "model": "VGG16",
+                      "data-name": "CIFAR10", "parameters": {"load": False, "save": True}, "validation": False,
+                      "data-distribution": {"non-iid": False, "num-sample": 128, "num-label": 10, "dirichlet": {"alpha": 1}},
+                      "random-seed": 1},
+           "log_path": str(tmp_path), "debug_mode": False,
+           "learning": {"learning-rate": 0.01, "momentum": 0.5, "batch-size": 32, "control-count": 2, "clip-grad-norm": 0.0},
+           "b200": {"algorithm": algo, "synthetic-data": True, "watchdog-seconds": 120}}
+    raw["server"].update(extra)
+    srv = run_variant(normalize(raw), specs, workdir=str(tmp_path), devices=["cuda:0"], timeout=300)
+    assert srv.history and srv.history[0]["ok"]
+    sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    assert len(sd) == 97 and all(torch.isfinite(v.float()).all() for v in sd.values())
