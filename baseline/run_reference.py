@@ -65,6 +65,80 @@ def _config(n_first: int, n_last: int, batches: int):
 PROFILE = {"exe_time": [1.0] * 52, "size_data": [1.0] * 52, "speed": 1.0, "network": 1.0}
 
 
+def child_main(layer_id: int, port: int, W: int, K: int, out_path: str, device: str) -> None:
+    """One reference client in its own OS process (how the reference is deployed: ``python client.py --layer_id N``)."""
+    sys.path.insert(0, HERE)
+    _prepare_imports()
+    import torch
+    import pika
+    from src.RpcClient import RpcClient
+    torch.cuda.set_device(torch.device(device))
+    pika.use_remote("127.0.0.1", port)
+    marks, counts = [], {"n": 0}
+
+    def hook(queue, body):
+        if not queue.startswith("gradient_queue_1_"):
+            return
+        counts["n"] += 1
+        if counts["n"] in (W, W + K):
+            torch.cuda.synchronize()
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((time.perf_counter(), ev))
+    pika.on_get.append(hook)
+    cid = uuid.uuid4()
+    conn = pika.BlockingConnection(pika.ConnectionParameters("127.0.0.1"))
+    c = RpcClient(cid, layer_id, conn.channel(), device)
+    c.send_to_server({"action": "REGISTER", "client_id": cid, "layer_id": layer_id, "profile": PROFILE,
+                      "cluster": -1, "message": "Hello from Client!"})
+    c.wait_response()
+    ms = 0.0
+    if len(marks) == 2:
+        torch.cuda.synchronize()
+        ms = marks[0][1].elapsed_time(marks[1][1])
+    with open(out_path, "w") as f:
+        json.dump({"layer": layer_id, "ms": ms, "wall_ms": (marks[1][0] - marks[0][0]) * 1e3 if len(marks) == 2 else 0.0}, f)
+
+
+def _single_box_processes(args, cfg, port: int, W: int, K: int) -> float:
+    """N = 1: server + broker here, one subprocess per client, both clients on cuda:0."""
+    import subprocess
+    import tempfile
+    import pika
+    from src.Server import Server
+    pika.serve("127.0.0.1", port)
+    os.chdir("/tmp")
+
+    def serve():
+        try:
+            Server(copy.deepcopy(cfg)).start()
+        except SystemExit:
+            pass
+    th = threading.Thread(target=serve, daemon=True, name="ref-server")
+    th.start()
+    outs, procs = [], []
+    for layer in (1, 2):
+        out = tempfile.mktemp(prefix=f"ref_l{layer}_", suffix=".json")
+        outs.append(out)
+        log = open(out + ".log", "w")
+        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--child", str(layer), str(port), str(W), str(K),
+                                       out, "cuda:0"], stdout=subprocess.DEVNULL, stderr=log))
+    for p in procs:
+        try:
+            p.wait(args.timeout)
+        except subprocess.TimeoutExpired:
+            p.kill()
+    th.join(60)
+    ms = 0.0
+    for o in outs:
+        if os.path.exists(o):
+            ms = max(ms, json.load(open(o))["ms"])
+        elif os.path.exists(o + ".log"):
+            tail = open(o + ".log").read().strip().splitlines()[-3:]
+            sys.stderr.write("reference child failed: " + " | ".join(tail) + "\n")
+    return ms
+
+
 def main(args) -> dict:
     sys.path.insert(0, HERE)
     try:
@@ -93,6 +167,13 @@ def main(args) -> dict:
     cfg = _config(n_first, n_last, batches)
     port = 29655 + (int(os.environ.get("MASTER_PORT", "0")) % 97)
 
+    if world == 1:
+        t_wall = time.perf_counter()
+        ms_total = _single_box_processes(args, cfg, port, W, K)
+        if ms_total <= 0:
+            return {"impl": "reference", "unavailable": "timing marks missing (single-box process mode)"}
+        return _result(n, n_first, n_last, K, W, ms_total, outcome, time.perf_counter() - t_wall,
+                       "one OS process per client (both on cuda:0) + server/broker process")
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -169,6 +250,10 @@ def main(args) -> dict:
         return {}
     if ms_total <= 0:
         return {"impl": "reference", "unavailable": "timing marks missing"}
+    return _result(n, n_first, n_last, K, W, ms_total, outcome, time.perf_counter() - t_wall, "one OS process (rank) per client")
+
+
+def _result(n, n_first, n_last, K, W, ms_total, outcome, wall, deployment) -> dict:
     images = n_first * K * 32
     value = images / (ms_total / 1e3)
     return {
@@ -178,8 +263,12 @@ def main(args) -> dict:
         "config": {"model": "VGG16_CIFAR10", "global_batch": 32 * n_first, "microbatch": 32, "cut_layers": [7],
                    "clients": [n_first, n_last], "control_count": 3, "parallelism": f"pp2 x dp{n_first}",
                    "transport": "in-box broker (pika shim) + pickle, as the reference does over RabbitMQ",
-                   "l2": "inputs stream through host pickling each step", "install": outcome},
+                   "l2": "inputs stream through host pickling each step", "install": outcome, "deployment": deployment},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 32 * 3 * 32 * 32 * 4 + 32 * 64 * 16 * 16 * 4 * 2,
                 "d2h_bytes_per_step": 32 * 64 * 16 * 16 * 4 * 2},
-        "gpu_launches": None, "wall_seconds": time.perf_counter() - t_wall,
+        "gpu_launches": None, "wall_seconds": wall,
     }
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--child":
+    child_main(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6], sys.argv[7])

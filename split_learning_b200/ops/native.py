@@ -86,9 +86,30 @@ def _check(code: int, what: str, n: int = 1):
 
 
 # ------------------------------------------------------------------ tensor-core ops
-def conv_tiling(M: int, N: int, Ca: int, target_ctas: int = 96):
+_TUNING = None
+
+
+def _tuning():
+    """Measured (BLOCK_N, split-K) table written by tools/tune_conv.py on a B200 (falls back to the heuristic)."""
+    global _TUNING
+    if _TUNING is None:
+        import json
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "conv_tuning.json")
+        try:
+            with open(path) as f:
+                _TUNING = json.load(f)
+        except (OSError, ValueError):
+            _TUNING = {"conv": {}, "wgrad": {}}
+    return _TUNING
+
+
+def conv_tiling(M: int, N: int, Ca: int, target_ctas: int = 96, flip: int = 0):
     """(block_n, k_split) for the implicit-GEMM conv: these problems are latency- not FLOP-bound at microbatch 32,
-    so spread every layer over ~all SMs — narrow N tiles first, then split K (fp32 vector red.add + finalize)."""
+    so spread every layer over ~all SMs — narrow N tiles first, then split K (fp32 vector red.add + finalize).
+    A measured entry of ``conv_tuning.json`` for exactly this shape wins over the heuristic."""
+    hit = _tuning()["conv"].get(f"{M},{N},{Ca},{flip}")
+    if hit:
+        return int(hit["bn"]), int(hit["ks"])
     m_tiles = (M + 127) // 128
     bn = 64
     for cand in (256, 128, 64):
@@ -123,7 +144,7 @@ def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None):
     """dy [B,H,W,Cout] bf16, w [Cout,3,3,Cin] bf16 -> dx [B,H,W,Cin] bf16."""
     B, H, W, Cout = dy.shape
     Cin = w_bf16.shape[3]
-    bn, ks = tiling or conv_tiling(B * H * W, Cin, Cout)
+    bn, ks = tiling or conv_tiling(B * H * W, Cin, Cout, flip=1)
     if acc is None:
         ks = 1
     _check(lib().slb_conv3x3_igemm(_p(dy), _p(w_bf16), _p(dx), _p(None), _p(None), _p(None), c_int(B), c_int(H), c_int(W),
@@ -145,6 +166,10 @@ def conv3x3_wgrad(x, dy, dw_f32, k_split: int = 0, block_n: int = 0):
     whose K fits one slice is written with plain stores."""
     B, H, W, Cin = x.shape
     Cout = dy.shape[3]
+    if k_split == 0 and block_n == 0:
+        hit = _tuning()["wgrad"].get(f"{B * H * W},{Cin},{Cout}")
+        if hit:
+            block_n, k_split = int(hit["bn"]), int(hit["ks"])
     _check(lib().slb_conv3x3_wgrad(_p(x), _p(dy), _p(dw_f32), c_int(B), c_int(H), c_int(W), c_int(Cin), c_int(Cout),
                                    c_int(k_split), c_int(block_n), _stream()), "conv3x3_wgrad")
 

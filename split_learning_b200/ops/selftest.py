@@ -91,7 +91,7 @@ def conv_dgrad():
         x, w, _ = _conv_case(B, H, W, Cin, Cout)
         dy = _bf(torch.randn(B, H, W, Cout, device="cuda"))
         dx = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.bfloat16)
-        bn_, ks_ = N.conv_tiling(B * H * W, Cin, Cout)
+        bn_, ks_ = N.conv_tiling(B * H * W, Cin, Cout, flip=1)
         acc = torch.zeros(B * H * W, Cin, device="cuda") if ks_ > 1 else None
         ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)       # must outlive the asynchronous kernel
         N.conv3x3_dgrad(dy, w, dx, acc=acc, counters=ctr)

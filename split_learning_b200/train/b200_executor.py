@@ -411,7 +411,7 @@ class _Plan:
                     M = B * b.H * b.W
                     if N.conv_tiling(M, b.cout, b.cin)[1] > 1:
                         reserve((bi, "facc"), M * b.cout)           # split-K partial sums, forward
-                    if N.conv_tiling(M, b.cin, b.cout)[1] > 1 and not (bi == 0 and ex.is_first):
+                    if N.conv_tiling(M, b.cin, b.cout, flip=1)[1] > 1 and not (bi == 0 and ex.is_first):
                         reserve((bi, "dacc"), M * b.cin)            # split-K partial sums, dgrad
             elif isinstance(b, LinearBlock):
                 reserve((bi, "acc"), B * b.fout)
