@@ -111,10 +111,12 @@ def fedavg_round(st: DeviceStage, rank: int, world: int, dev) -> Optional[dict]:
     fs = PeerFedAvg(max(flat_stats.numel(), 4), dev, mine, group=grp)
     weight = float(st._posted["F"] + st._posted["L"] or 1)      # microbatches processed (the reference's FedAvg weight)
     ok = not ex.nan_detected()
+    done = fa.average(ex.P, ex.PB, weight, ok=ok)         # the aggregation itself (first call also pays NCCL sub-group setup)
     torch.cuda.synchronize()
+    dist.barrier(group=grp)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    done = fa.average(ex.P, ex.PB, weight, ok=ok)
+    fa.average(ex.P, ex.PB, weight, ok=ok)                # timed repeat (idempotent: replicas are already equal)
     if flat_stats.numel():
         fs.average(flat_stats, None, weight, ok=ok)
         o = 0
@@ -134,7 +136,8 @@ def fedavg_round(st: DeviceStage, rank: int, world: int, dev) -> Optional[dict]:
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
     return {"ms_max_over_ranks": float(ms.item()), "replicas_per_stage": n, "aggregated": bool(done),
             "stage2_param_bytes": 4 * ex.n_params if not ex.is_first else None, "replicas_identical": bool(same.item() > 0.5),
-            "note": "in-place NVLink peer-load FedAvg incl. staging copy + 2 barriers; outside the timed steps"}
+            "note": "in-place NVLink peer-load FedAvg (params + BN statistics) incl. staging copy, weight exchange and 2 barriers "
+                    "per buffer; steady-state repeat; outside the timed training steps"}
 
 
 def bench_multi_gpu(args) -> dict:
