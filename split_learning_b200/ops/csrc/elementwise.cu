@@ -322,6 +322,103 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
   }
 }
 
+// Single-launch BatchNorm backward: reduce (dgamma, dbeta) -> software grid barrier -> apply.  Every block of the grid
+// is co-resident (<= 296 blocks of 256 threads, a few KB of smem: 8 fit per SM), so the barrier cannot dead-lock; kernels
+// of other streams that may share the SMs always terminate on their own.  grid_bar: [0] arrivals (monotonic),
+// [1] generation, [2] finish ticket — owned by one call site, zero-initialised.
+template <bool POOL>
+__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const BnBwdParams p, uint32_t* grid_bar) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int NP = POOL ? 4 : 1;
+  const int g = threadIdx.x;
+  const bool leader = threadIdx.x == 0 && threadIdx.y == 0;
+  const uint32_t G = gridDim.x;
+  uint32_t gen = 0;
+  if (leader) gen = ld_acquire_gpu(grid_bar + 1);
+  float sc[8], sh[8], mean[8], istd[8], ag[8], ab[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    mean[j] = p.save_mean[c];
+    istd[j] = p.save_invstd[c];
+    sc[j] = p.gamma[c] * istd[j];
+    sh[j] = p.beta[c] - mean[j] * sc[j];
+    ag[j] = ab[j] = 0.f;
+  }
+  const long long outP = POOL ? static_cast<long long>(p.P) >> 2 : p.P;
+  for (long long op = blockIdx.x * (long long)blockDim.y + threadIdx.y; op < outP; op += (long long)gridDim.x * blockDim.y) {
+    float yv[NP][8], dz[NP][8];
+    long long ip[NP];
+    bn_dz<POOL>(p, op, g, sc, sh, yv, dz, ip);
+#pragma unroll
+    for (int q = 0; q < NP; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ab[j] += dz[q][j];
+        ag[j] += dz[q][j] * (yv[q][j] - mean[j]) * istd[j];
+      }
+  }
+  extern __shared__ float s_red[];            // [2][C]
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * p.C; i += blockDim.x * blockDim.y) s_red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_red[g * 8 + j], ag[j]);
+    atomicAdd(&s_red[p.C + g * 8 + j], ab[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < p.C; i += blockDim.x * blockDim.y) {
+    atomicAdd(p.dgamma + i, s_red[i]);
+    atomicAdd(p.dbeta + i, s_red[p.C + i]);
+  }
+  // ---- grid barrier ----
+  __syncthreads();
+  if (leader) {
+    __threadfence();
+    atomicAdd(grid_bar, 1u);
+    const uint32_t target = (gen + 1u) * G;
+    uint32_t spins = 0;
+    while (static_cast<int32_t>(ld_acquire_gpu(grid_bar) - target) < 0) {
+      __nanosleep(32);
+      if (++spins > (1u << 26)) { printf("slb: bn_bwd grid barrier timeout\n"); __trap(); }
+    }
+  }
+  __syncthreads();
+  // ---- apply ----
+  const float invP = 1.f / static_cast<float>(p.P);
+  float k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    k1[j] = __ldcg(p.dbeta + g * 8 + j) * invP;
+    k2[j] = __ldcg(p.dgamma + g * 8 + j) * invP;
+  }
+  for (long long op = blockIdx.x * (long long)blockDim.y + threadIdx.y; op < outP; op += (long long)gridDim.x * blockDim.y) {
+    float yv[NP][8], dz[NP][8];
+    long long ip[NP];
+    bn_dz<POOL>(p, op, g, sc, sh, yv, dz, ip);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = (yv[q][j] - mean[j]) * istd[j];
+        r[j] = sc[j] * (dz[q][j] - k1[j] - xhat * k2[j]);
+      }
+      *reinterpret_cast<bf16x8*>(p.dy + ip[q] * p.C + g * 8) = pack8(r);
+    }
+  }
+  __syncthreads();
+  if (leader) {
+    const uint32_t tk = atomicAdd(grid_bar + 2, 1u);
+    if (tk == G - 1u) {
+      grid_bar[2] = 0;
+      __threadfence();
+      atomicExch(grid_bar + 1, gen + 1u);
+    }
+  }
+}
+
 // Column sums / sums of squares of a bf16 [P][C] matrix (BN statistics fallback, bias gradients).
 __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* y, float* sum, float* sumsq, long long P, int C) {
   pdl_trigger();
@@ -747,6 +844,7 @@ int slb_preload_elementwise() {
   SLB_PRELOAD(zero_kernel); SLB_PRELOAD(wait_flag_kernel); SLB_PRELOAD(set_flag_kernel); SLB_PRELOAD(counter_inc_kernel);
   SLB_PRELOAD(bn_relu_pool_fwd_kernel); SLB_PRELOAD(bn_bwd_reduce_kernel<true>); SLB_PRELOAD(bn_bwd_reduce_kernel<false>);
   SLB_PRELOAD(bn_bwd_apply_kernel<true>); SLB_PRELOAD(bn_bwd_apply_kernel<false>); SLB_PRELOAD(col_stats_kernel);
+  SLB_PRELOAD(bn_bwd_fused_kernel<true>); SLB_PRELOAD(bn_bwd_fused_kernel<false>);
   SLB_PRELOAD(conv_finalize_kernel); { auto k1 = conv3x3_small_fwd_kernel<3, 64>; SLB_PRELOAD(k1); auto k2 = conv3x3_small_fwd_kernel<1, 64>; SLB_PRELOAD(k2); }
   SLB_PRELOAD(conv3x3_small_wgrad_kernel<3>); SLB_PRELOAD(conv3x3_small_wgrad_kernel<1>); SLB_PRELOAD(linear_finalize_kernel);
   SLB_PRELOAD(linear_bwd_prep_kernel); SLB_PRELOAD(dropout_fwd_kernel); SLB_PRELOAD(dropout_bwd_kernel);
@@ -796,7 +894,7 @@ int slb_bn_relu_pool_fwd(const void* y, const float* sum, const float* sumsq, co
 
 int slb_bn_relu_pool_bwd(const void* dout, const void* y, const float* gamma, const float* beta, const float* save_mean,
                          const float* save_invstd, float* dgamma, float* dbeta, void* dy, int P, int C, int H, int W, int relu,
-                         int pool, int identity, cudaStream_t st) {
+                         int pool, int identity, uint32_t* grid_bar, cudaStream_t st) {
   if (C % 8 || C > 2048) return -1;
   BnBwdParams p = {reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(y), gamma, beta,
                    save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dy), P, C, H, W, relu, pool, identity};
@@ -805,6 +903,24 @@ int slb_bn_relu_pool_bwd(const void* dout, const void* y, const float* gamma, co
   dim3 block(tx, ty);
   const long long outP = pool ? (long long)P / 4 : P;
   const int grid = grid_for(outP, ty, 148 * 2);
+  if (grid_bar != nullptr && !identity) {          // one launch: reduce -> grid barrier -> apply
+    // the software barrier needs every block co-resident: cap the grid at (SMs - 4) x measured occupancy
+    static int cap[2] = {0, 0};
+    if (cap[pool ? 1 : 0] == 0) {
+      int per_sm = 0, dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (pool) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<true>, 256, 2 * 2048 * sizeof(float));
+      else      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<false>, 256, 2 * 2048 * sizeof(float));
+      if (per_sm < 1) per_sm = 1;
+      if (per_sm > 2) per_sm = 2;
+      cap[pool ? 1 : 0] = (sms > 8 ? sms - 4 : sms) * per_sm;
+    }
+    const int g2 = grid < cap[pool ? 1 : 0] ? grid : cap[pool ? 1 : 0];
+    if (pool) launch_k(bn_bwd_fused_kernel<true>, g2, block, 2 * C * sizeof(float), st, p, grid_bar);
+    else      launch_k(bn_bwd_fused_kernel<false>, g2, block, 2 * C * sizeof(float), st, p, grid_bar);
+    return last_err();
+  }
   if (pool) {
     if (!identity) launch_k(bn_bwd_reduce_kernel<true>, grid, block, 2 * C * sizeof(float), st, p);
     launch_k(bn_bwd_apply_kernel<true>, grid, block, 0, st, p);

@@ -187,6 +187,14 @@ def bn_fwd_bwd():
         dy = torch.empty_like(y)
         N.bn_relu_pool_bwd(dout, y, gamma, beta, sm, si, dg, db, dy, H, W, relu, pool)
         torch.cuda.synchronize()
+        # single-launch variant (reduce -> grid barrier -> apply), twice on the same barrier words
+        bar = torch.zeros(4, device="cuda", dtype=torch.int32)
+        for _rep in range(2):
+            dg2, db2, dy2 = torch.zeros_like(dg), torch.zeros_like(db), torch.empty_like(dy)
+            N.bn_relu_pool_bwd(dout, y, gamma, beta, sm, si, dg2, db2, dy2, H, W, relu, pool, grid_bar=bar)
+            torch.cuda.synchronize()
+            assert _rel(dy2, dy) < 1e-2 and _rel(dg2, dg) < 1e-4 and _rel(db2, db) < 1e-4, "fused BN backward mismatch"
+        assert bar.tolist()[1] == 2 and bar.tolist()[2] == 0
         e3 = _rel(dy, yr.grad.permute(0, 2, 3, 1))
         e4 = max(_rel(dg, bn.weight.grad), _rel(db, bn.bias.grad))
         print(f"  bn {B}x{H}x{W}x{C} relu={relu} pool={pool}: out {e1:.2e} running {e2:.2e} dy {e3:.2e} dgamma/dbeta {e4:.2e}"

@@ -178,6 +178,9 @@ class B200Executor(StageExecutor):
         self.use_graphs = use_graphs
         import os
         self.fused_cut = fused_cut and os.environ.get("SLB200_FUSED_CUT", "1") != "0"
+        # single-launch BN backward (reduce -> grid barrier -> apply): measured SLOWER than two PDL-chained launches
+        # (L pass 825 us vs 776 us) — a software grid barrier costs more than a kernel boundary here.  Off by default.
+        self.fused_bn_bwd = os.environ.get("SLB200_FUSED_BN_BWD", "0") != "0"
         self.lr = float(learning.get("learning-rate", 0.01))
         self.mu = float(learning.get("momentum", 0.0))
         self.seed = seed
@@ -427,6 +430,7 @@ class _Plan:
                     d["y"] = torch.zeros(B, b.H, b.W, b.cout, device=dev, dtype=bf)
                     d["dy"] = torch.zeros(B, b.H, b.W, b.cout, device=dev, dtype=bf)
                 d["out"] = d["y"] if (b.conv is not None and b.bn is None) else torch.zeros(B, OH, OW, b.cout, device=dev, dtype=bf)
+                d["bwd_bar"] = torch.zeros(4, device=dev, dtype=torch.int32)     # grid-barrier words of the fused BN backward
                 d["save_mean"] = torch.zeros(b.cout, device=dev)
                 d["save_invstd"] = torch.ones(b.cout, device=dev)
                 d["dx"] = torch.zeros(B, b.H, b.W, b.cin, device=dev, dtype=bf) if (b.cin > 4 and b.conv is not None) else None
@@ -634,7 +638,8 @@ class _Plan:
                 elif b.bn is not None:
                     N.bn_relu_pool_bwd(g, y, ex.view(ex.P, f"layer{b.bn}.weight"), ex.view(ex.P, f"layer{b.bn}.bias"),
                                        a["save_mean"], a["save_invstd"], ex.view(ex.G, f"layer{b.bn}.weight"),
-                                       ex.view(ex.G, f"layer{b.bn}.bias"), dy, b.H, b.W, b.relu, b.pool)
+                                       ex.view(ex.G, f"layer{b.bn}.bias"), dy, b.H, b.W, b.relu, b.pool,
+                                       grid_bar=a["bwd_bar"] if ex.fused_bn_bwd else None)
                 else:
                     N.bn_relu_pool_bwd(g, y, None, None, a["save_mean"], a["save_invstd"], None, None, dy, b.H, b.W,
                                        b.relu, b.pool, identity=True)
