@@ -150,3 +150,51 @@ class DeviceRpcClient(RpcClient):
             self.send_to_server(M.notify(self.client_id, self.layer_id, self.cluster))
         self.trainer._wait_pause()
         return (not ex.nan_detected()), n
+
+    # ------------------------------------------------------------------ round end
+    def _replicas(self) -> List[str]:
+        return [cid for cid, _ in self.start_msg["peers"]["members"][self.layer_id]]
+
+    def upload(self, result: bool, size: int, send: bool = True) -> None:
+        """Round end.  With several replicas of this stage (single cluster) the weighted FedAvg runs in place over
+        peer memory (``parallel.fedavg``): every replica ends the round holding the averaged parameters, only the
+        group leader uploads a state-dict (for validation / checkpoint), and the next START carries no payload."""
+        members = self._replicas() if self.dstage is not None else []
+        single_cluster = int(self.start_msg.get("num_clusters", 1)) == 1
+        if len(members) < 2 or not single_cluster or not self.opts.get("device-fedavg", True):
+            return super().upload(result, size, send)
+        from .fedavg import BrokerComm, PeerFedAvg
+        ex = self.executor
+        me = str(self.client_id)
+        if getattr(self, "_fa_members", None) != members:
+            comm = BrokerComm(self.channel, f"fa_{self.cluster}_{self.layer_id}", members, me, timeout=self.watchdog)
+            stats = [t for bn in ex.bn_state.values() for t in (bn["running_mean"], bn["running_var"])]
+            n_stats = (sum(t.numel() for t in stats) + 3) // 4 * 4
+            self._fa = (comm, PeerFedAvg(ex.n_params, ex.device, comm=comm),
+                        PeerFedAvg(max(n_stats, 4), ex.device, comm=comm) if stats else None)
+            self._fa_members = members
+        comm, fa_p, fa_s = self._fa
+        done = fa_p.average(ex.P, ex.PB, float(size), ok=bool(result))
+        if done and fa_s is not None:
+            stats = [t for bn in ex.bn_state.values() for t in (bn["running_mean"], bn["running_var"])]
+            flat = torch.zeros(fa_s.n, device=ex.device)
+            o = 0
+            for t in stats:
+                flat[o:o + t.numel()].copy_(t.reshape(-1))
+                o += t.numel()
+            fa_s.average(flat, None, float(size), ok=True)
+            o = 0
+            for t in stats:
+                t.copy_(flat[o:o + t.numel()].view_as(t))
+                o += t.numel()
+        sizes = comm.all_gather_object((int(size), {k: int(v["num_batches_tracked"]) for k, v in ex.bn_state.items()}))
+        total = sum(s for s, _ in sizes) or 1
+        if done:
+            for k, v in ex.bn_state.items():         # integer counters: weighted mean, rounded (src/Utils.py:59-60)
+                v["num_batches_tracked"].fill_(round(sum(s * c[k] for s, c in sizes) / total))
+        leader = members and sorted(members)[0] == me
+        sd = None
+        if leader and send:
+            sd = {k: v.detach().to("cpu") for k, v in ex.state_dict().items()}
+        self.send_to_server(M.update(self.client_id, self.layer_id, bool(result) and done, total if leader else size,
+                                     self.cluster, sd, resident=True))

@@ -28,14 +28,67 @@ from ..ops import native as N
 from .mailbox import tensor_from_ptr
 
 
+class TorchDistComm:
+    """Control messages of a FedAvg group over torch.distributed (multi-GPU runner / bench)."""
+
+    def __init__(self, ranks: Sequence[int], group=None):
+        self.ranks, self.group = list(ranks), group
+        self.me = dist.get_rank()
+
+    def all_gather_object(self, obj):
+        out = [None] * len(self.ranks)
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def barrier(self):
+        dist.barrier(group=self.group)
+
+
+class BrokerComm:
+    """The same three primitives over the control-plane broker (``launch.py`` / ``client.py`` processes have no
+    torch.distributed rendezvous): every member posts to each member's ``grp_{name}_{member}`` queue."""
+
+    def __init__(self, channel, name: str, members: Sequence[str], me: str, timeout: float = 120.0):
+        self.ch, self.name, self.members, self.me_id, self.timeout = channel, name, sorted(members), me, timeout
+        self.ranks = list(range(len(self.members)))
+        self.me = self.members.index(me)
+        self.seq = 0
+        self._stash = {}
+        self.ch.queue_declare(self._q(me))
+
+    def _q(self, member) -> str:
+        return f"grp_{self.name}_{member}"
+
+    def all_gather_object(self, obj):
+        import time as _t
+        self.seq += 1
+        for m in self.members:
+            self.ch.publish_obj(self._q(m), {"seq": self.seq, "from": self.me, "obj": obj})
+        got = self._stash.pop(self.seq, {})
+        t0 = _t.monotonic()
+        while len(got) < len(self.members):
+            m = self.ch.get_obj(self._q(self.me_id), 0.25)
+            if m is None:
+                if _t.monotonic() - t0 > self.timeout:
+                    raise TimeoutError(f"FedAvg group {self.name}: peers silent")
+                continue
+            (got if m["seq"] == self.seq else self._stash.setdefault(m["seq"], {}))[m["from"]] = m["obj"]
+        return [got[i] for i in range(len(self.members))]
+
+    def barrier(self):
+        self.all_gather_object(None)
+
+
 class PeerFedAvg:
-    def __init__(self, n_elems: int, device, group_ranks: Sequence[int], group=None):
-        """Collective over ``group_ranks`` (all must call).  ``n_elems`` fp32 elements, multiple of 4."""
+    def __init__(self, n_elems: int, device, group_ranks: Sequence[int] = (), group=None, comm=None):
+        """Collective over the group (all members must call).  ``n_elems`` fp32 elements, multiple of 4.
+        ``comm``: a ``TorchDistComm`` / ``BrokerComm``; default = torch.distributed over ``group_ranks``."""
         self.n = (n_elems + 3) // 4 * 4
         self.device = torch.device(device)
-        self.ranks = list(group_ranks)
+        self.comm = comm or TorchDistComm(group_ranks, group)
+        self.ranks = list(self.comm.ranks)
         self.group = group
-        self.me = dist.get_rank()
+        self.me = self.comm.me
         lib = N.lib()
         ptr = ctypes.c_void_p()
         rc = lib.slb_malloc(ctypes.byref(ptr), ctypes.c_longlong(self.n * 4))
@@ -46,12 +99,16 @@ class PeerFedAvg:
         if rc != 0:
             raise N.NativeError(f"cudaIpcGetMemHandle failed: {rc}")
         self.staging = tensor_from_ptr(ptr.value, self.n * 4, self.device).view(torch.float32)
-        gathered: List[Optional[bytes]] = [None] * len(self.ranks)
-        dist.all_gather_object(gathered, bytes(handle), group=group)
+        from .mailbox import _SAME_PROCESS
+        _SAME_PROCESS[bytes(handle)] = (ptr.value, None)
+        gathered: List[Optional[bytes]] = self.comm.all_gather_object(bytes(handle))
         self.peer_ptrs: List[int] = []
         for r, h in zip(self.ranks, gathered):
             if r == self.me:
                 self.peer_ptrs.append(ptr.value)
+                continue
+            if h in _SAME_PROCESS:                 # a replica living in this very process (threads)
+                self.peer_ptrs.append(_SAME_PROCESS[h][0])
                 continue
             q = ctypes.c_void_p()
             buf = (ctypes.c_uint8 * 64).from_buffer_copy(h)
@@ -64,17 +121,15 @@ class PeerFedAvg:
                 cluster_scale: float = 1.0) -> bool:
         """In-place weighted average of ``flat_fp32`` across the group.  Returns False (and leaves the
         parameters untouched) when any member reports ``ok == False``."""
-        info = torch.tensor([float(weight), 1.0 if ok else 0.0], device=self.device)
-        allinfo = [torch.zeros_like(info) for _ in self.ranks]
-        dist.all_gather(allinfo, info, group=self.group)
+        allinfo = self.comm.all_gather_object((float(weight), bool(ok)))
         ws = [float(t[0]) for t in allinfo]
-        if not all(float(t[1]) > 0.5 for t in allinfo) or sum(ws) <= 0:
+        if not all(t[1] for t in allinfo) or sum(ws) <= 0:
             return False
         n = flat_fp32.numel()
         assert n <= self.n
         self.staging[:n].copy_(flat_fp32)
         torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)                       # every staging buffer is complete
+        self.comm.barrier()                                  # every staging buffer is complete
         coefs = [w / sum(ws) * cluster_scale for w in ws]
         n4 = n // 4 * 4
         N.fedavg(flat_fp32, flat_bf16, self.peer_ptrs, coefs, n4)
@@ -82,7 +137,7 @@ class PeerFedAvg:
             flat_fp32[n4:] = sum(c * torch.nan_to_num(tensor_from_ptr(p, self.n * 4, self.device).view(torch.float32)[n4:n])
                                  for c, p in zip(coefs, self.peer_ptrs))
         torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)                       # nobody overwrites staging before all have read
+        self.comm.barrier()                                  # nobody overwrites staging before all have read
         return True
 
 

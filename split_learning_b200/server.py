@@ -247,10 +247,12 @@ class Server:
         layers = self.topology.layers_for(c.cluster, c.layer_id)
         if self.topology.clusters[c.cluster].cut_layers[:1] == [0] and c.layer_id == 1:
             layers = [0, 0]
-        return M.start(self.stage_parameters_for(c, layers), layers, self.model_name, self.data_name,
+        resident = bool(getattr(self, "all_resident", False)) and len(self.topology.clusters) == 1
+        params = None if resident else self.stage_parameters_for(c, layers)
+        return M.start(params, layers, self.model_name, self.data_name,
                        self.learning, c.label_counts, self.refresh, c.cluster,
                        num_layers=self.num_stages, round=self.global_round - self.round + 1,
-                       peers=self._peer_table(c))
+                       peers=self._peer_table(c), num_clusters=len(self.topology.clusters), resident=resident)
 
     def _peer_table(self, c: ClientInfo) -> dict:
         """Who is upstream/downstream of this client (ranks + ids): lets the GPU data plane
@@ -310,6 +312,8 @@ class Server:
         if not message.get("result", True):
             self.round_result = False
         sd = message.get("parameters")
+        self._resident_votes = getattr(self, "_resident_votes", [])
+        self._resident_votes.append(bool(message.get("resident", False)))
         if self.save_parameters and self.round_result and sd is not None:
             if has_nan(sd):
                 self.round_result = False
@@ -323,6 +327,10 @@ class Server:
     def finish_round(self) -> None:
         print_with_color("Collected all parameters.", "yellow")
         self.current_clients = [0] * self.num_stages
+        votes = getattr(self, "_resident_votes", [])
+        # every client averaged in place over peer memory and still holds the result: next START needs no payload
+        self.all_resident = bool(votes) and all(votes) and self.round_result
+        self._resident_votes = []
         metrics = {"round": self.global_round - self.round + 1, "ok": self.round_result,
                    "seconds": time.monotonic() - self._round_t0}
         if self.save_parameters and self.round_result:

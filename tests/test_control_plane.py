@@ -81,3 +81,24 @@ def test_auto_mode_partition_and_clusters(tmp_path):
         if cl.members[0] and cl.members[1]:
             assert cl.cut_layers == [7]
     assert sum(len(c.members[0]) for c in srv.topology.clusters) == 4
+
+
+def test_broker_comm_allgather_and_barrier():
+    """FedAvg group primitives over the control-plane broker (used when clients have no torch.distributed)."""
+    from split_learning_b200.parallel.fedavg import BrokerComm
+    b = InProcBroker()
+    members = ["c", "a", "b"]
+    out = {}
+
+    def run(me):
+        comm = BrokerComm(b, "g", members, me, timeout=10)
+        r1 = comm.all_gather_object({"me": me})
+        comm.barrier()
+        r2 = comm.all_gather_object(me.upper())
+        out[me] = (r1, r2, comm.me)
+    ts = [threading.Thread(target=run, args=(m,)) for m in members]
+    [t.start() for t in ts]
+    [t.join(20) for t in ts]
+    assert set(out) == set(members)
+    for me, (r1, r2, idx) in out.items():
+        assert [d["me"] for d in r1] == ["a", "b", "c"] and r2 == ["A", "B", "C"] and sorted(members)[idx] == me

@@ -319,3 +319,32 @@ def test_host_plane_with_native_executor_on_gpu(tmp_path, algo, clients, specs, 
     assert srv.history and srv.history[0]["ok"]
     sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
     assert len(sd) == 97 and all(torch.isfinite(v.float()).all() for v in sd.values())
+
+
+def test_public_api_device_fedavg_resident_params(tmp_path, monkeypatch):
+    """clients [2,2] on the device plane: at round end the replicas of each stage FedAvg in place over peer memory
+    (``parallel.fedavg`` driven through the control-plane broker), only the group leaders upload a state-dict, and the
+    second round's START carries no parameters (they are resident and identical on every replica)."""
+    import yaml
+    from split_learning_b200.checkpoint import load_checkpoint
+    from split_learning_b200.config import normalize
+    from split_learning_b200.runner import run_inproc
+    monkeypatch.setenv("SLB200_WAIT_SPINS", str(1 << 24))
+    raw = yaml.safe_load(open("config.yaml"))
+    raw["server"].update({"clients": [2, 2], "global-round": 2, "validation": False})
+    raw["server"]["data-distribution"]["num-sample"] = 160
+    raw["server"]["manual"]["no-cluster"]["cut-layers"] = [7]
+    raw["log_path"] = str(tmp_path)
+    raw["learning"].update({"batch-size": 32, "control-count": 2, "learning-rate": 0.01})
+    raw["b200"] = {"synthetic-data": True, "data-plane": "device", "watchdog-seconds": 120}
+    srv = run_inproc(normalize(raw), devices=["cuda:0"], workdir=str(tmp_path), timeout=600)
+    assert [h["ok"] for h in srv.history] == [True, True]
+    assert srv.all_resident                                   # every UPDATE of the last round was 'resident'
+    clients = srv.clients_objs
+    assert all(c.dstage is not None for c in clients)
+    for layer in (1, 2):
+        a, b = [c for c in clients if c.layer_id == layer]
+        assert torch.equal(a.executor.P, b.executor.P)        # replicas hold the identical averaged parameters
+        assert a.rounds_done == 2
+    sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    assert len(sd) == 97 and int(sd["layer9.num_batches_tracked"]) == 10     # 5 microbatches per replica per round, averaged
