@@ -234,6 +234,9 @@ class DCSLClient(SequentialClient):
 class FlexServer(Server):
     ALGORITHM = "flex"
 
+    def label_matrix(self):
+        return self.cfg.label_matrix if self.cfg.label_matrix is not None else "flex"
+
     def cluster_and_selection(self) -> None:
         cfg = self.cfg
         ncl = cfg.num_cluster
@@ -367,6 +370,9 @@ class FlexClient(RpcClient):
 # =============================================================================== 2LS
 class TwoLSServer(Server):
     ALGORITHM = "2ls"
+
+    def label_matrix(self):
+        return self.cfg.label_matrix if self.cfg.label_matrix is not None else "2ls"
 
     def cluster_and_selection(self) -> None:
         cfg = self.cfg

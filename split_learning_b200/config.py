@@ -67,6 +67,7 @@ class Config:
     num_label: int = 10
     dirichlet_alpha: float = 1.0
     non_iid_rate: Optional[float] = None
+    label_matrix: Any = None            # explicit per-client label probabilities, or a preset name ("flex" / "2ls")
     refresh: bool = True
     random_seed: Optional[int] = 1
     # topology
@@ -160,6 +161,7 @@ def normalize(raw: Dict[str, Any]) -> Config:
     cfg.num_label = int(dd.get("num-label", 10))
     cfg.dirichlet_alpha = float(_get(dd, "dirichlet", "alpha", default=1))
     cfg.non_iid_rate = dd.get("non-iid-rate", s.get("non-iid-rate"))
+    cfg.label_matrix = dd.get("label-matrix")
     cfg.refresh = bool(dd.get("refresh", dd.get("refresh-each-round", True)))
     cfg.random_seed = s.get("random-seed", 1)
 

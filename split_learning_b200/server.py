@@ -126,11 +126,16 @@ class Server:
             self.logger.log_info(f"{self.learning}")
             self.begin_round()
 
+    def label_matrix(self):
+        """Fixed non-IID matrix, if configured (the FLEX / 2LS servers default to their built-in presets)."""
+        return self.cfg.label_matrix
+
     def distribution(self) -> None:
         n1 = self.total_clients[0]
         self.label_counts = make_label_counts(
             n1, self.cfg.num_label, self.cfg.num_sample, non_iid=self.cfg.non_iid,
-            alpha=self.cfg.dirichlet_alpha, seed=self.cfg.random_seed, non_iid_rate=self.cfg.non_iid_rate)
+            alpha=self.cfg.dirichlet_alpha, seed=self.cfg.random_seed, non_iid_rate=self.cfg.non_iid_rate,
+            matrix=self.label_matrix())
         pool = self.label_counts.tolist()
         for c in self.clients:
             c.label_counts = pool.pop() if c.layer_id == 1 else []

@@ -113,3 +113,14 @@ def test_checkpoint_slice_merge_roundtrip(tmp_path, ref):
     theirs = ref("src.model.VGG16_CIFAR10").VGG16_CIFAR10()
     theirs.load_state_dict(torch.load(p, weights_only=True))
     assert load_checkpoint(str(tmp_path / "missing.pth")) is None
+
+
+def test_variant_label_matrices():
+    from split_learning_b200.data.distribution import preset_matrix
+    flex = label_counts(9, 4, 5000, True, matrix="flex")
+    # other/FLEX/src/Server.py:81-90: 75 % dominant label (0,1,0,1,2,1,2,0,2) + 25 % of the last label
+    assert flex.shape == (9, 4) and flex[0].tolist() == [3750, 0, 0, 1250] and flex[4].tolist() == [0, 0, 3750, 1250]
+    two = preset_matrix("2ls", 9, 10)
+    assert np.allclose(two.sum(1), 1.0) and two[0, :4].tolist() == [0.3, 0.3, 0.3, 0.1]
+    explicit = label_counts(3, 2, 100, True, matrix=[[1.0, 0.0], [0.5, 0.5]])
+    assert explicit.tolist() == [[100, 0], [50, 50], [100, 0]]
