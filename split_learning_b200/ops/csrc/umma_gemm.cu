@@ -48,7 +48,18 @@ struct GemmParams {
   uint32_t* tile_counters;   // [m_tiles * n_tiles], zero at rest (self-resetting)
   __nv_bfloat16* fin_out;    // bf16 destination [M][fin_ld]
   long long fin_ld;
+  // transformer epilogue (EPI_BF16, MODE_GEMM): out = act(acc + bias + residual); aux_out keeps the pre-activation
+  int act;                        // 0 none, 1 ReLU, 2 GELU (erf), 3 tanh
+  __nv_bfloat16* aux_out;         // [M][ldo] or nullptr
+  const __nv_bfloat16* residual;  // [M][ldo] or nullptr
 };
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == 1) return fmaxf(x, 0.f);
+  if (act == 2) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  if (act == 3) return tanhf(x);
+  return x;
+}
 
 template <int BLOCK_N>
 struct SmemLayout {
@@ -250,6 +261,42 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float x = __uint_as_float(v[j]);
             if (p.bias != nullptr && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
             f[j] = x;
+          }
+          if constexpr (MODE == MODE_GEMM) {
+            if (p.residual != nullptr && row_store) {
+              const __nv_bfloat16* rs = p.residual + row_off + col0;
+              if (col0 + 32 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(rs) + j);
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 t = __bfloat1622float2(h2[e]);
+                    f[8 * j + 2 * e] += t.x;
+                    f[8 * j + 2 * e + 1] += t.y;
+                  }
+                }
+              } else {
+                for (int j = 0; j < 32 && col0 + j < p.N; ++j) f[j] += __bfloat162float(rs[j]);
+              }
+            }
+            if (p.aux_out != nullptr && row_store) {
+              __nv_bfloat16* ao = p.aux_out + row_off + col0;
+              if (col0 + 32 <= p.N) {
+                uint4* a4 = reinterpret_cast<uint4*>(ao);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  a4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                     pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              } else {
+                for (int j = 0; j < 32 && col0 + j < p.N; ++j) ao[j] = __float2bfloat16(f[j]);
+              }
+            }
+            if (p.act != 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+            }
           }
           if (row_store) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
@@ -607,6 +654,30 @@ int slb_gemm_bf16(const void* A, const void* Bm, float* out, int M, int N, int K
   if (epi == EPI_F32_STORE) k_split = 1;
   p.k_split = k_split; p.a_mn = a_mn; p.b_mn = b_mn; p.epi = epi; p.out = out; p.ldo = ldo;
   dim3 grid((M + 127) / 128, (N + block_n - 1) / block_n, k_split);
+  return dispatch_bn<MODE_GEMM>(block_n, ta, tbm, p, grid, st);
+}
+
+// Transformer GEMM: out_bf16[M][ldo] = act(A * B + bias + residual), optional pre-activation copy in `aux`.
+// Same operand-major options as slb_gemm_bf16; no split-K (token counts give >= 1 wave of 128 x block_n tiles).
+int slb_gemm_bf16_act(const void* A, const void* Bm, void* out, int M, int N, int K, int a_mn, int b_mn, long long lda,
+                      long long ldb, long long ldo, int block_n, const float* bias, int act, void* aux,
+                      const void* residual, cudaStream_t st) {
+  if (block_n != 32 && block_n != 64 && block_n != 128 && block_n != 256) return -3;
+  if (b_mn && block_n < 64) return -4;
+  CUtensorMap ta, tbm;
+  int r;
+  if (!a_mn) r = tmap_2d(&ta, A, K, M, lda, 64, 128);
+  else       r = tmap_2d(&ta, A, M, K, lda, 64, 64);
+  if (r) return r;
+  if (!b_mn) r = tmap_2d(&tbm, Bm, K, N, ldb, 64, block_n);
+  else       r = tmap_2d(&tbm, Bm, N, K, ldb, 64, 64);
+  if (r) return r;
+  GemmParams p = {};
+  p.M = M; p.N = N; p.k_iters = (K + 63) / 64; p.k_split = 1;
+  p.a_mn = a_mn; p.b_mn = b_mn; p.epi = EPI_BF16; p.out = out; p.ldo = ldo;
+  p.bias = bias; p.act = act; p.aux_out = reinterpret_cast<__nv_bfloat16*>(aux);
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  dim3 grid((M + 127) / 128, (N + block_n - 1) / block_n, 1);
   return dispatch_bn<MODE_GEMM>(block_n, ta, tbm, p, grid, st);
 }
 

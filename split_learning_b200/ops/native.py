@@ -47,7 +47,8 @@ def preload(device=None) -> None:
     if d in _preloaded:
         return
     with torch.cuda.device(d):
-        bad = lib().slb_preload_gemm() + lib().slb_preload_fused() + lib().slb_preload_elementwise()
+        bad = (lib().slb_preload_gemm() + lib().slb_preload_fused() + lib().slb_preload_elementwise()
+               + lib().slb_preload_transformer())
     if bad:
         raise NativeError(f"{bad} kernels failed to load (wrong GPU architecture? this library is sm_100a only)")
     _preloaded.add(d)
@@ -356,3 +357,91 @@ def counter_inc(ctr):
 
 def memcpy_async(dst_ptr: int, src_ptr: int, nbytes: int):
     _check(lib().slb_memcpy_async(c_void_p(dst_ptr), c_void_p(src_ptr), c_longlong(nbytes), _stream()), "memcpy_async", 0)
+
+
+# ------------------------------------------------------------------ token-model (transformer) ops
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "tanh": 3}
+
+
+def _gemm_bn(n: int, m: int, b_mn: bool = False) -> int:
+    """Column-tile width: wide tiles unless that leaves most SMs idle."""
+    m_tiles = (m + 127) // 128
+    for cand in (128, 64, 32):
+        if cand == 32 and b_mn:
+            break
+        if n >= cand and m_tiles * ((n + cand - 1) // cand) >= 96:
+            return cand
+    return 64 if (n > 32 or b_mn) else 32
+
+
+def gemm_act(a, b, out, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldo=None, bias=None, act=None, aux=None,
+             residual=None):
+    """out_bf16[M, N] = act(A B^T + bias + residual).  A: [M, K] (K-major) or [K, M] storage (``a_mn``);
+    B: [N, K] (K-major) or [K, N] storage (``b_mn``).  ``aux`` receives the pre-activation."""
+    lda = lda if lda is not None else (M if a_mn else K)
+    ldb = ldb if ldb is not None else (N if b_mn else K)
+    ldo = ldo if ldo is not None else N
+    bn = _gemm_bn(N, M, b_mn)
+    _check(lib().slb_gemm_bf16_act(_p(a), _p(b), _p(out), c_int(M), c_int(N), c_int(K), c_int(int(a_mn)), c_int(int(b_mn)),
+                                   c_longlong(lda), c_longlong(ldb), c_longlong(ldo), c_int(bn), _p(bias), c_int(ACT[act]),
+                                   _p(aux), _p(residual), _stream()), "gemm_act")
+
+
+def gemm_f32(a, b, out, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldo=None, k_split=1):
+    """out_fp32[M, N] += A B^T (fp32 red.add epilogue: accumulates into a live gradient buffer, any ``k_split``)."""
+    lda = lda if lda is not None else (M if a_mn else K)
+    ldb = ldb if ldb is not None else (N if b_mn else K)
+    ldo = ldo if ldo is not None else N
+    bn = _gemm_bn(N, M, b_mn)
+    _check(lib().slb_gemm_bf16(_p(a), _p(b), _p(out), c_int(M), c_int(N), c_int(K), c_int(int(a_mn)), c_int(int(b_mn)),
+                               c_longlong(lda), c_longlong(ldb), c_longlong(ldo), c_int(1), c_int(max(1, k_split)), c_int(bn),
+                               _stream()), "gemm_f32")
+
+
+def attn_fwd(q, k, v, ldq, ldk, ldv, q_col, k_col, v_col, out, ldo, lse, key_bias, B, S, H, Dh, p_drop=0.0, seed=0):
+    _check(lib().slb_attn_fwd(_p(q), _p(k), _p(v), c_longlong(ldq), c_longlong(ldk), c_longlong(ldv), c_int(q_col),
+                              c_int(k_col), c_int(v_col), _p(out), c_longlong(ldo), _p(lse), _p(key_bias), c_int(B), c_int(S),
+                              c_int(H), c_int(Dh), c_float(p_drop), c_uint32(seed & 0xFFFFFFFF), _stream()), "attn_fwd")
+
+
+def attn_bwd(q, k, v, dout, ldq, ldk, ldv, lddo, q_col, k_col, v_col, do_col, dq, dk, dv, lddq, lddk, lddv, dq_col,
+             dk_col, dv_col, lse, key_bias, B, S, H, Dh, p_drop=0.0, seed=0):
+    _check(lib().slb_attn_bwd(_p(q), _p(k), _p(v), _p(dout), c_longlong(ldq), c_longlong(ldk), c_longlong(ldv),
+                              c_longlong(lddo), c_int(q_col), c_int(k_col), c_int(v_col), c_int(do_col), _p(dq), _p(dk),
+                              _p(dv), c_longlong(lddq), c_longlong(lddk), c_longlong(lddv), c_int(dq_col), c_int(dk_col),
+                              c_int(dv_col), _p(lse), _p(key_bias), c_int(B), c_int(S), c_int(H), c_int(Dh),
+                              c_float(p_drop), c_uint32(seed & 0xFFFFFFFF), _stream()), "attn_bwd")
+
+
+def ln_fwd(x, res, gamma, beta, y, pre, mean, rstd, rows, D, eps, p_drop=0.0, seed=0):
+    _check(lib().slb_ln_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(pre), _p(mean), _p(rstd), c_int(rows), c_int(D),
+                            c_float(eps), c_float(p_drop), c_uint32(seed & 0xFFFFFFFF), _stream()), "ln_fwd")
+
+
+def ln_bwd(dy, pre, gamma, mean, rstd, dpre, dgamma, dbeta, rows, D):
+    _check(lib().slb_ln_bwd(_p(dy), _p(pre), _p(gamma), _p(mean), _p(rstd), _p(dpre), _p(dgamma), _p(dbeta), c_int(rows),
+                            c_int(D), _stream()), "ln_bwd")
+
+
+def act_bwd(dy, ref, dz, n, kind):
+    _check(lib().slb_act_bwd(_p(dy), _p(ref), _p(dz), c_longlong(n), c_int(ACT[kind]), _stream()), "act_bwd")
+
+
+def colsum_bf16(x, out, rows, cols, ld=None):
+    _check(lib().slb_colsum_bf16(_p(x), _p(out), c_int(rows), c_int(cols), c_longlong(ld if ld is not None else cols),
+                                 _stream()), "colsum_bf16")
+
+
+def dropout_bf16(x, y, n, p, seed):
+    _check(lib().slb_dropout_bf16(_p(x), _p(y), c_longlong(n), c_float(p), c_uint32(seed & 0xFFFFFFFF), _stream()),
+           "dropout_bf16")
+
+
+def embed3_fwd(ids, tts, word, pos, typ, out, tokens, S, D):
+    _check(lib().slb_embed3_fwd(_p(ids), _p(tts), _p(word), _p(pos), _p(typ), _p(out), c_int(tokens), c_int(S), c_int(D),
+                                _stream()), "embed3_fwd")
+
+
+def embed3_bwd(ids, tts, g, dword, dpos, dtyp, tokens, S, D, pad_id=-1):
+    _check(lib().slb_embed3_bwd(_p(ids), _p(tts), _p(g), _p(dword), _p(dpos), _p(dtyp), c_int(tokens), c_int(S), c_int(D),
+                                c_longlong(pad_id), _stream()), "embed3_bwd")

@@ -21,7 +21,9 @@ def _align(n: int, a: int = 128) -> int:
 
 class FlatFusedOptimizer(torch.optim.Optimizer):
     def __init__(self, params: Iterable[torch.nn.Parameter], kind: str = "sgd", lr: float = 1e-3, momentum: float = 0.0,
-                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01):
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, shadow: bool = False):
+        """``shadow``: keep a flat bf16 copy of the parameters, refreshed inside the update kernel; the token-model
+        kernels (``ops.nn``) read weights through ``param._slb_bf16`` views of it."""
         params = [p for p in params if p.requires_grad]
         if not params:
             raise ValueError("no trainable parameters")
@@ -48,6 +50,18 @@ class FlatFusedOptimizer(torch.optim.Optimizer):
         self._params: List[torch.nn.Parameter] = params
         self._offs = offs
         self.steps = 0
+        self.flat_pb = None
+        if shadow:
+            self.flat_pb = torch.empty(total, dtype=torch.bfloat16, device=dev)
+            for p, o in zip(params, offs):
+                p._slb_bf16 = self.flat_pb[o:o + p.numel()].view_as(p)
+            self.refresh_shadow()
+
+    def refresh_shadow(self) -> None:
+        if self.flat_pb is not None:
+            N.cast_f32_bf16(self.flat_p, self.flat_pb)
+            for p in self._params:
+                p._slb_ver = p._version
 
     def zero_grad(self, set_to_none: bool = True) -> None:      # the fused kernels zero the flat gradient buffer
         for p, o in zip(self._params, self._offs):
@@ -64,8 +78,8 @@ class FlatFusedOptimizer(torch.optim.Optimizer):
         self.steps += 1
         if self.kind == "adamw":
             b1, b2 = g["betas"]
-            N.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, None, g["lr"], b1, b2, g["eps"], g["weight_decay"],
+            N.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_pb, g["lr"], b1, b2, g["eps"], g["weight_decay"],
                     self.steps)
         else:
-            N.sgd_momentum(self.flat_p, self.flat_g, self.flat_m, None, g["lr"], g["momentum"])
+            N.sgd_momentum(self.flat_p, self.flat_g, self.flat_m, self.flat_pb, g["lr"], g["momentum"])
         return None

@@ -29,7 +29,7 @@ from ..models import SplitModel
 _ADAMW_MODELS = ("BERT", "KWT", "VIT")
 
 
-def make_optimizer(model: nn.Module, model_name: str, learning: dict) -> torch.optim.Optimizer:
+def make_optimizer(model: nn.Module, model_name: str, learning: dict, shadow: bool = False) -> torch.optim.Optimizer:
     params = [p for p in model.parameters() if p.requires_grad]
     lr = float(learning.get("learning-rate", 0.01))
     adamw = model_name.upper() in _ADAMW_MODELS
@@ -37,7 +37,7 @@ def make_optimizer(model: nn.Module, model_name: str, learning: dict) -> torch.o
         # CUDA: one flat buffer + the fused sm_100a optimizer kernels (no silent fallback: a missing library raises)
         from ..ops.optim import FlatFusedOptimizer
         return FlatFusedOptimizer(params, "adamw" if adamw else "sgd", lr=lr, momentum=float(learning.get("momentum", 0.0)),
-                                  weight_decay=float(learning.get("weight-decay", 0.01)))
+                                  weight_decay=float(learning.get("weight-decay", 0.01)), shadow=shadow)
     if model_name.upper() in _ADAMW_MODELS:
         return torch.optim.AdamW(params, lr=lr, weight_decay=float(learning.get("weight-decay", 0.01)))
     return torch.optim.SGD(params, lr=lr, momentum=float(learning.get("momentum", 0.0)))
@@ -62,14 +62,18 @@ class StageExecutor:
 
 class TorchExecutor(StageExecutor):
     def __init__(self, model: SplitModel, model_name: str, learning: dict, device="cpu", is_first=False,
-                 is_last=False, recompute: bool = True, clip_grad_norm: float = 0.0):
+                 is_last=False, recompute: bool = True, clip_grad_norm: float = 0.0, native: bool = False):
         self.model = model.to(device)       # parameters must sit on the device before the optimizer re-homes them
+        self.native = bool(native)
+        if self.native:                     # token-model blocks -> fused sm_100a ops (train/token_native.py)
+            from .token_native import nativize
+            nativize(self.model)
         self.model_name = model_name
         self.device = device
         self.is_first, self.is_last = is_first, is_last
         self.recompute = recompute
         self.clip = float(clip_grad_norm or 0.0)
-        self.opt = make_optimizer(self.model, model_name, learning)
+        self.opt = make_optimizer(self.model, model_name, learning, shadow=self.native)
         self.criterion = nn.CrossEntropyLoss()
         self._store: Dict[Any, Any] = {}
         self._nan = torch.zeros((), dtype=torch.bool, device=device)
@@ -78,6 +82,10 @@ class TorchExecutor(StageExecutor):
 
     # -- helpers -------------------------------------------------------------
     def _call(self, x):
+        out = self._call_model(x)
+        return out.float() if self.native and out.dtype != torch.float32 else out    # stage boundary is fp32
+
+    def _call_model(self, x):
         if isinstance(x, dict):
             return self.model(input_ids=x["input_ids"]) if self.is_first else self.model(x)
         if self.model_name.upper() == "BERT" and self.is_first:
@@ -166,6 +174,10 @@ def make_executor(model: SplitModel, model_name: str, learning: dict, device, is
         if supports(model):
             return B200Executor(model, model_name, learning, device=dev, is_first=is_first, is_last=is_last,
                                 recompute=bool(opts.get("recompute", True)))
+        from .token_native import supports as token_supports
+        if token_supports(model) and opts.get("native-tokens", True):
+            return TorchExecutor(model, model_name, learning, device=dev, is_first=is_first, is_last=is_last,
+                                 recompute=bool(opts.get("recompute", True)), clip_grad_norm=clip, native=True)
         if kind == "b200":
             raise RuntimeError(f"no native sm_100a plan for {type(model).__name__}")
     return TorchExecutor(model, model_name, learning, device=dev, is_first=is_first, is_last=is_last,
