@@ -87,7 +87,7 @@ def test_layernorm_fwd_bwd(rows, d, res):
     gr, br = g.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
     pre = xr + rr if res else xr
     if res:
-        pre = pre.to(BF).float() + (pre - pre.detach())          # the kernel normalises the bf16-rounded sum
+        pre = pre + (pre.detach().to(BF).float() - pre.detach())   # the kernel normalises the bf16-rounded sum
     yr = torch.nn.functional.layer_norm(pre, (d,), gr, br, 1e-5)
     yr.backward(dy.float())
     _close(y, yr, 2e-2, "y")
