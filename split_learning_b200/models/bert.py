@@ -200,7 +200,9 @@ class BERT_EMOTION(SplitModel):
         + [LayerSpec("module", (Pooler, _H)), LayerSpec("module", (Classifier, _H, 4))]
     )
 
-    def forward(self, x, attention_mask=None, token_type_ids=None, **kwargs):
+    def forward(self, x=None, attention_mask=None, token_type_ids=None, input_ids=None, **kwargs):
+        if x is None:
+            x = input_ids
         for i in self.owned_indices():
             layer = getattr(self, f"layer{i}")
             if i == 1:
