@@ -764,9 +764,14 @@ __global__ void sgd_momentum_kernel(float4* p, float4* g, float4* m, uint2* p_bf
   }
 }
 __global__ void adamw_kernel(float4* p, float4* g, float4* m, float4* v, uint2* p_bf16, long long n4, float lr, float b1, float b2,
-                             float eps, float wd, float bc1, float bc2) {
+                             float eps, float wd, float bc1, float bc2, const uint32_t* step_ptr) {
   pdl_trigger();
   pdl_wait();
+  if (step_ptr != nullptr) {          // step count lives on the device: a captured graph stays valid across replays
+    const float t = static_cast<float>(*step_ptr);
+    bc1 = 1.f - powf(b1, t);
+    bc2 = 1.f - powf(b2, t);
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 gi = g[i];
     float4 mi = m[i], vi = v[i], pi = p[i];
@@ -1012,11 +1017,11 @@ int slb_sgd_momentum(float* p, float* g, float* m, void* p_bf16, long long n, fl
   return last_err();
 }
 int slb_adamw(float* p, float* g, float* m, float* v, void* p_bf16, long long n, float lr, float b1, float b2, float eps, float wd,
-              float bc1, float bc2, cudaStream_t st) {
+              float bc1, float bc2, const uint32_t* step_ptr, cudaStream_t st) {
   if (n % 4) return -1;
   launch_k(adamw_kernel, grid_for(n / 4, 256, 148 * 16), 256, 0, st, reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
                                                               reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
-                                                              reinterpret_cast<uint2*>(p_bf16), n / 4, lr, b1, b2, eps, wd, bc1, bc2);
+                                                              reinterpret_cast<uint2*>(p_bf16), n / 4, lr, b1, b2, eps, wd, bc1, bc2, step_ptr);
   return last_err();
 }
 int slb_cast_f32_bf16(const float* x, void* y, long long n, cudaStream_t st) {

@@ -27,6 +27,9 @@ __device__ __forceinline__ float drop_scale(uint32_t seed, uint32_t idx, float p
   const uint32_t r = fmix32(idx * 0x9E3779B9u + seed) >> 8;            // 24 random bits
   return (static_cast<float>(r) * (1.f / 16777216.f) >= p) ? inv_keep : 0.f;
 }
+__device__ __forceinline__ uint32_t mix_seed(uint32_t seed, const uint32_t* ofs) {
+  return ofs ? seed + __ldg(ofs) * 0x9E3779B9u : seed;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // byte offset of the 16-byte chunk holding columns [c8*8, c8*8+8) of row r inside a [128 rows][128 cols] bf16 tile
@@ -43,6 +46,7 @@ struct AttnParams {
   const float* key_bias;           // [B][S] additive bias on the logits, or nullptr
   float p_drop;
   uint32_t seed;
+  const uint32_t* seed_ofs;        // optional device counter mixed into the seed (fresh masks per CUDA-graph replay)
   __nv_bfloat16* out;              // forward: O [B*S][ldo], head h at column h*Dh
   long long ldo;
   float* lse;                      // [B*H][128] log-sum-exp of the scaled logits
@@ -144,6 +148,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   }
   float sum = 0.f;
+  const uint32_t seed = mix_seed(p.seed, p.seed_ofs);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   const uint32_t idx0 = (static_cast<uint32_t>(blockIdx.x) * 128u + row) * 128u;
 #pragma unroll 1
@@ -160,7 +165,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (col < p.S) {
           x = exp2f((__uint_as_float(v[j]) * p.scale + (kb ? __ldg(kb + col) : 0.f) - mx) * LOG2E);
           sum += x;
-          if (p.p_drop > 0.f) x *= drop_scale(p.seed, idx0 + col, p.p_drop, inv_keep);
+          if (p.p_drop > 0.f) x *= drop_scale(seed, idx0 + col, p.p_drop, inv_keep);
         }
         e[j] = x;
       }
@@ -262,6 +267,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const float* kb = p.key_bias ? p.key_bias + static_cast<long long>(b) * p.S : nullptr;
   constexpr float LOG2E = 1.4426950408889634f;
   const float lse = row_ok ? p.lse[static_cast<long long>(blockIdx.x) * 128 + row] : 0.f;
+  const uint32_t seed = mix_seed(p.seed, p.seed_ofs);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   const uint32_t idx0 = (static_cast<uint32_t>(blockIdx.x) * 128u + row) * 128u;
 
@@ -281,7 +287,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float x = 0.f;
         if (col < p.S && row_ok) {
           x = exp2f((__uint_as_float(s[j]) * p.scale + (kb ? __ldg(kb + col) : 0.f) - lse) * LOG2E);
-          if (p.p_drop > 0.f) x *= drop_scale(p.seed, idx0 + col, p.p_drop, inv_keep);
+          if (p.p_drop > 0.f) x *= drop_scale(seed, idx0 + col, p.p_drop, inv_keep);
           D += x * __uint_as_float(g[j]);
         }
         e[j] = x;
@@ -311,7 +317,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float x = 0.f;
         if (col < p.S && row_ok) {
           const float pr = exp2f((__uint_as_float(s[j]) * p.scale + (kb ? __ldg(kb + col) : 0.f) - lse) * LOG2E);
-          const float mk = p.p_drop > 0.f ? drop_scale(p.seed, idx0 + col, p.p_drop, inv_keep) : 1.f;
+          const float mk = p.p_drop > 0.f ? drop_scale(seed, idx0 + col, p.p_drop, inv_keep) : 1.f;
           x = pr * (__uint_as_float(g[j]) * mk - D) * p.scale;
         }
         e[j] = x;
@@ -364,8 +370,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res, const float* __restrict__ gamma,
               const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ pre,
-              float* __restrict__ mean, float* __restrict__ rstd, int rows, int D, float eps, float p_drop, uint32_t seed) {
+              float* __restrict__ mean, float* __restrict__ rstd, int rows, int D, float eps, float p_drop, uint32_t seed,
+              const uint32_t* __restrict__ seed_ofs) {
   pdl_wait();
+  seed = mix_seed(seed, seed_ofs);
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = lane_id(), D2 = D >> 1;
@@ -493,8 +501,9 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int 
 
 __global__ void __launch_bounds__(256)
 dropout_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n2, float p,
-                    uint32_t seed) {
+                    uint32_t seed, const uint32_t* __restrict__ seed_ofs) {
   pdl_wait();
+  seed = mix_seed(seed, seed_ofs);
   const float inv_keep = 1.f / (1.f - p);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n2;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -577,7 +586,7 @@ extern "C" {
 // q/k/v: bf16 [B*S][ld*]; head h of Q lives at columns q_col + h*Dh ...  out: [B*S][ldo]; lse: [B*H][128] fp32
 int slb_attn_fwd(const void* q, const void* k, const void* v, long long ldq, long long ldk, long long ldv, int q_col,
                  int k_col, int v_col, void* out, long long ldo, float* lse, const float* key_bias, int B, int S, int H,
-                 int Dh, float p_drop, unsigned seed, cudaStream_t st) {
+                 int Dh, float p_drop, unsigned seed, const unsigned* seed_ofs, cudaStream_t st) {
   if (S < 1 || S > 128 || (Dh != 32 && Dh != 64)) return -3;
   if ((q_col | k_col | v_col) & 31 || ((ldq | ldk | ldv | ldo) & 7)) return -4;
   CUtensorMap tq, tk, tv;
@@ -588,7 +597,7 @@ int slb_attn_fwd(const void* q, const void* k, const void* v, long long ldq, lon
   if ((r = tmap_rows(&tv, v, rows, ldv, ldv))) return r;
   AttnParams p = {};
   p.B = B; p.S = S; p.H = H; p.Dh = Dh; p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
-  p.scale = 1.f / sqrtf(static_cast<float>(Dh)); p.key_bias = key_bias; p.p_drop = p_drop; p.seed = seed;
+  p.scale = 1.f / sqrtf(static_cast<float>(Dh)); p.key_bias = key_bias; p.p_drop = p_drop; p.seed = seed; p.seed_ofs = seed_ofs;
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.lse = lse;
   static bool attr = false;
   if (!attr) {
@@ -603,7 +612,8 @@ int slb_attn_fwd(const void* q, const void* k, const void* v, long long ldq, lon
 int slb_attn_bwd(const void* q, const void* k, const void* v, const void* dout, long long ldq, long long ldk,
                  long long ldv, long long lddo, int q_col, int k_col, int v_col, int do_col, void* dq, void* dk, void* dv,
                  long long lddq, long long lddk, long long lddv, int dq_col, int dk_col, int dv_col, const float* lse,
-                 const float* key_bias, int B, int S, int H, int Dh, float p_drop, unsigned seed, cudaStream_t st) {
+                 const float* key_bias, int B, int S, int H, int Dh, float p_drop, unsigned seed, const unsigned* seed_ofs,
+                 cudaStream_t st) {
   if (S < 1 || S > 128 || (Dh != 32 && Dh != 64)) return -3;
   if ((q_col | k_col | v_col | do_col) & 31 || ((ldq | ldk | ldv | lddo | lddq | lddk | lddv) & 7) ||
       ((dq_col | dk_col | dv_col) & 7))
@@ -617,7 +627,7 @@ int slb_attn_bwd(const void* q, const void* k, const void* v, const void* dout, 
   if ((r = tmap_rows(&tdo, dout, rows, lddo, lddo))) return r;
   AttnParams p = {};
   p.B = B; p.S = S; p.H = H; p.Dh = Dh; p.q_col = q_col; p.k_col = k_col; p.v_col = v_col; p.do_col = do_col;
-  p.scale = 1.f / sqrtf(static_cast<float>(Dh)); p.key_bias = key_bias; p.p_drop = p_drop; p.seed = seed;
+  p.scale = 1.f / sqrtf(static_cast<float>(Dh)); p.key_bias = key_bias; p.p_drop = p_drop; p.seed = seed; p.seed_ofs = seed_ofs;
   p.lse = const_cast<float*>(lse);
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dk = reinterpret_cast<__nv_bfloat16*>(dk);
   p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
@@ -633,11 +643,13 @@ int slb_attn_bwd(const void* q, const void* k, const void* v, const void* dout, 
 }
 
 int slb_ln_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* pre, float* mean,
-               float* rstd, int rows, int D, float eps, float p_drop, unsigned seed, cudaStream_t st) {
+               float* rstd, int rows, int D, float eps, float p_drop, unsigned seed, const unsigned* seed_ofs,
+               cudaStream_t st) {
   if (D & 1) return -3;
   ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(res), gamma, beta,
-      reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(pre), mean, rstd, rows, D, eps, p_drop, seed);
+      reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(pre), mean, rstd, rows, D, eps, p_drop, seed,
+      seed_ofs);
   return check_launch();
 }
 int slb_ln_bwd(const void* dy, const void* pre, const float* gamma, const float* mean, const float* rstd, void* dpre,
@@ -666,13 +678,14 @@ int slb_colsum_bf16(const void* x, float* out, int rows, int cols, long long ld,
   colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols, ld, rpb);
   return check_launch();
 }
-int slb_dropout_bf16(const void* x, void* y, long long n, float p, unsigned seed, cudaStream_t st) {
+int slb_dropout_bf16(const void* x, void* y, long long n, float p, unsigned seed, const unsigned* seed_ofs,
+                     cudaStream_t st) {
   if (n & 1 || n >= (1ll << 32)) return -3;
   const long long n2 = n / 2;
   int grid = static_cast<int>((n2 + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   dropout_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                            reinterpret_cast<__nv_bfloat16*>(y), n2, p, seed);
+                                            reinterpret_cast<__nv_bfloat16*>(y), n2, p, seed, seed_ofs);
   return check_launch();
 }
 int slb_embed3_fwd(const long long* ids, const long long* tts, const float* word, const float* pos, const float* type,

@@ -324,10 +324,12 @@ def sgd_momentum(p, g, m, p_bf16, lr, mu, first_step=False):
                                   c_int(int(first_step)), _stream()), "sgd_momentum")
 
 
-def adamw(p, g, m, v, p_bf16, lr, b1, b2, eps, wd, step):
-    bc1, bc2 = 1.0 - b1 ** step, 1.0 - b2 ** step
+def adamw(p, g, m, v, p_bf16, lr, b1, b2, eps, wd, step, step_ptr=None):
+    """``step_ptr``: device uint32 holding the step count (graph-capturable); else ``step`` is baked into the launch."""
+    bc1, bc2 = 1.0 - b1 ** max(step, 1), 1.0 - b2 ** max(step, 1)
     _check(lib().slb_adamw(_p(p), _p(g), _p(m), _p(v), _p(p_bf16), c_longlong(p.numel()), c_float(lr), c_float(b1),
-                           c_float(b2), c_float(eps), c_float(wd), c_float(bc1), c_float(bc2), _stream()), "adamw")
+                           c_float(b2), c_float(eps), c_float(wd), c_float(bc1), c_float(bc2), _p(step_ptr), _stream()),
+           "adamw")
 
 
 def cast_f32_bf16(x, y):
@@ -361,6 +363,8 @@ def memcpy_async(dst_ptr: int, src_ptr: int, nbytes: int):
 
 # ------------------------------------------------------------------ token-model (transformer) ops
 ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "tanh": 3}
+# ``seed_ofs``: optional device uint32 mixed into the dropout seed of the token kernels.  A graph-captured training step
+# passes its replay counter, so the masks baked into the graph (seeds are launch arguments) change from replay to replay.
 
 
 def _gemm_bn(n: int, m: int, b_mn: bool = False) -> int:
@@ -398,24 +402,25 @@ def gemm_f32(a, b, out, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldo
                                _stream()), "gemm_f32")
 
 
-def attn_fwd(q, k, v, ldq, ldk, ldv, q_col, k_col, v_col, out, ldo, lse, key_bias, B, S, H, Dh, p_drop=0.0, seed=0):
+def attn_fwd(q, k, v, ldq, ldk, ldv, q_col, k_col, v_col, out, ldo, lse, key_bias, B, S, H, Dh, p_drop=0.0, seed=0,
+             seed_ofs=None):
     _check(lib().slb_attn_fwd(_p(q), _p(k), _p(v), c_longlong(ldq), c_longlong(ldk), c_longlong(ldv), c_int(q_col),
                               c_int(k_col), c_int(v_col), _p(out), c_longlong(ldo), _p(lse), _p(key_bias), c_int(B), c_int(S),
-                              c_int(H), c_int(Dh), c_float(p_drop), c_uint32(seed & 0xFFFFFFFF), _stream()), "attn_fwd")
+                              c_int(H), c_int(Dh), c_float(p_drop), c_uint32(seed & 0xFFFFFFFF), _p(seed_ofs), _stream()), "attn_fwd")
 
 
 def attn_bwd(q, k, v, dout, ldq, ldk, ldv, lddo, q_col, k_col, v_col, do_col, dq, dk, dv, lddq, lddk, lddv, dq_col,
-             dk_col, dv_col, lse, key_bias, B, S, H, Dh, p_drop=0.0, seed=0):
+             dk_col, dv_col, lse, key_bias, B, S, H, Dh, p_drop=0.0, seed=0, seed_ofs=None):
     _check(lib().slb_attn_bwd(_p(q), _p(k), _p(v), _p(dout), c_longlong(ldq), c_longlong(ldk), c_longlong(ldv),
                               c_longlong(lddo), c_int(q_col), c_int(k_col), c_int(v_col), c_int(do_col), _p(dq), _p(dk),
                               _p(dv), c_longlong(lddq), c_longlong(lddk), c_longlong(lddv), c_int(dq_col), c_int(dk_col),
                               c_int(dv_col), _p(lse), _p(key_bias), c_int(B), c_int(S), c_int(H), c_int(Dh),
-                              c_float(p_drop), c_uint32(seed & 0xFFFFFFFF), _stream()), "attn_bwd")
+                              c_float(p_drop), c_uint32(seed & 0xFFFFFFFF), _p(seed_ofs), _stream()), "attn_bwd")
 
 
-def ln_fwd(x, res, gamma, beta, y, pre, mean, rstd, rows, D, eps, p_drop=0.0, seed=0):
+def ln_fwd(x, res, gamma, beta, y, pre, mean, rstd, rows, D, eps, p_drop=0.0, seed=0, seed_ofs=None):
     _check(lib().slb_ln_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(pre), _p(mean), _p(rstd), c_int(rows), c_int(D),
-                            c_float(eps), c_float(p_drop), c_uint32(seed & 0xFFFFFFFF), _stream()), "ln_fwd")
+                            c_float(eps), c_float(p_drop), c_uint32(seed & 0xFFFFFFFF), _p(seed_ofs), _stream()), "ln_fwd")
 
 
 def ln_bwd(dy, pre, gamma, mean, rstd, dpre, dgamma, dbeta, rows, D):
@@ -432,8 +437,8 @@ def colsum_bf16(x, out, rows, cols, ld=None):
                                  _stream()), "colsum_bf16")
 
 
-def dropout_bf16(x, y, n, p, seed):
-    _check(lib().slb_dropout_bf16(_p(x), _p(y), c_longlong(n), c_float(p), c_uint32(seed & 0xFFFFFFFF), _stream()),
+def dropout_bf16(x, y, n, p, seed, seed_ofs=None):
+    _check(lib().slb_dropout_bf16(_p(x), _p(y), c_longlong(n), c_float(p), c_uint32(seed & 0xFFFFFFFF), _p(seed_ofs), _stream()),
            "dropout_bf16")
 
 

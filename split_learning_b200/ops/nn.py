@@ -13,6 +13,7 @@ dense softmax attention S <= 128 (+key-padding bias, +probability dropout), drop
 from __future__ import annotations
 
 import random
+import threading
 from typing import Optional
 
 import torch
@@ -29,6 +30,19 @@ def seed_all(seed: int) -> None:
 
 def next_seed() -> int:
     return _rng.getrandbits(32)
+
+
+_tls = threading.local()
+
+
+def set_seed_offset(counter: Optional[torch.Tensor]) -> None:
+    """Device uint32/int32 scalar mixed into every dropout seed issued from this thread (``None`` = off).  A
+    graph-captured step points it at its replay counter so that masks differ between replays."""
+    _tls.seed_ofs = counter
+
+
+def _seed_ofs():
+    return getattr(_tls, "seed_ofs", None)
 
 
 def bf16_of(p: torch.Tensor) -> torch.Tensor:
@@ -139,16 +153,17 @@ class _LayerNormFn(torch.autograd.Function):
         pre = torch.empty_like(x2) if fused else None
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty_like(mean)
-        N.ln_fwd(x2, res2, gamma, beta, y, pre, mean, rstd, rows, d, eps, p_drop, seed)
+        ofs = _seed_ofs() if p_drop > 0.0 else None
+        N.ln_fwd(x2, res2, gamma, beta, y, pre, mean, rstd, rows, d, eps, p_drop, seed, ofs)
         ctx.gamma, ctx.beta = gamma, beta
-        ctx.cfg = (x.shape, residual is not None, p_drop, seed)
+        ctx.cfg = (x.shape, residual is not None, p_drop, seed, ofs)
         ctx.save_for_backward(pre if fused else x2, mean, rstd)
         return y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
         pre, mean, rstd = ctx.saved_tensors
-        shape, has_res, p_drop, seed = ctx.cfg
+        shape, has_res, p_drop, seed, ofs = ctx.cfg
         rows, d = pre.shape
         dy2 = _as_bf16(dy).reshape(rows, d).contiguous()
         dpre = torch.empty_like(dy2)
@@ -158,7 +173,7 @@ class _LayerNormFn(torch.autograd.Function):
         dx = dpre
         if p_drop > 0.0:
             dx = torch.empty_like(dpre)
-            N.dropout_bf16(dpre, dx, dpre.numel(), p_drop, seed)
+            N.dropout_bf16(dpre, dx, dpre.numel(), p_drop, seed, ofs)
         return dx.view(shape), None, None, (dpre.view(shape) if has_res else None), None, None, None
 
 
@@ -182,9 +197,10 @@ class _AttentionFn(torch.autograd.Function):
         out = torch.empty(b, s, e, dtype=_BF, device=q.device)
         lse = torch.empty(b * heads * 128, dtype=torch.float32, device=q.device)
         kb = key_bias.float().contiguous() if key_bias is not None else None
+        ofs = _seed_ofs() if p_drop > 0.0 else None
         N.attn_fwd(q, k, v, q.shape[-1], k.shape[-1], v.shape[-1], cols[0], cols[1], cols[2], out, e, lse, kb, b, s, heads, dh,
-                   p_drop, seed)
-        ctx.cfg = (cols, heads, dh, p_drop, seed, packed, ctx_e)
+                   p_drop, seed, ofs)
+        ctx.cfg = (cols, heads, dh, p_drop, seed, packed, ctx_e, ofs)
         ctx.save_for_backward(q, k, v, lse, kb if kb is not None else lse)
         ctx.has_kb = kb is not None
         return out
@@ -192,7 +208,7 @@ class _AttentionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         q, k, v, lse, kb = ctx.saved_tensors
-        cols, heads, dh, p_drop, seed, packed, e = ctx.cfg
+        cols, heads, dh, p_drop, seed, packed, e, ofs = ctx.cfg
         b, s, _ = q.shape
         do = _as_bf16(dout).contiguous()
         if packed:
@@ -204,7 +220,7 @@ class _AttentionFn(torch.autograd.Function):
             dcols = (0, 0, 0)
         N.attn_bwd(q, k, v, do, q.shape[-1], k.shape[-1], v.shape[-1], e, cols[0], cols[1], cols[2], 0, dq, dk, dv,
                    dq.shape[-1], dk.shape[-1], dv.shape[-1], dcols[0], dcols[1], dcols[2], lse, kb if ctx.has_kb else None,
-                   b, s, heads, dh, p_drop, seed)
+                   b, s, heads, dh, p_drop, seed, ofs)
         if packed:
             return dqkv, None, None, None, None, None, None, None
         return dq, dk, dv, None, None, None, None, None
@@ -227,16 +243,17 @@ class _DropoutFn(torch.autograd.Function):
     def forward(ctx, x, p, seed):
         x2 = _as_bf16(x).contiguous()
         y = torch.empty_like(x2)
-        N.dropout_bf16(x2, y, x2.numel(), p, seed)
-        ctx.cfg = (p, seed)
+        ofs = _seed_ofs()
+        N.dropout_bf16(x2, y, x2.numel(), p, seed, ofs)
+        ctx.cfg = (p, seed, ofs)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        p, seed = ctx.cfg
+        p, seed, ofs = ctx.cfg
         d2 = _as_bf16(dy).contiguous()
         dx = torch.empty_like(d2)
-        N.dropout_bf16(d2, dx, d2.numel(), p, seed)
+        N.dropout_bf16(d2, dx, d2.numel(), p, seed, ofs)
         return dx, None, None
 
 

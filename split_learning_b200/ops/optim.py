@@ -50,6 +50,7 @@ class FlatFusedOptimizer(torch.optim.Optimizer):
         self._params: List[torch.nn.Parameter] = params
         self._offs = offs
         self.steps = 0
+        self.dev_step = torch.zeros(1, dtype=torch.int32, device=dev)     # AdamW bias correction reads it on the device
         self.flat_pb = None
         if shadow:
             self.flat_pb = torch.empty(total, dtype=torch.bfloat16, device=dev)
@@ -75,11 +76,12 @@ class FlatFusedOptimizer(torch.optim.Optimizer):
             if p.grad is not None and p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * o:
                 self.flat_g[o:o + p.numel()].view_as(p).add_(p.grad)
                 p.grad = self.flat_g[o:o + p.numel()].view_as(p)
-        self.steps += 1
+        self.steps += 1                     # host mirror only (not advanced by graph replays)
         if self.kind == "adamw":
             b1, b2 = g["betas"]
+            N.counter_inc(self.dev_step)
             N.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_pb, g["lr"], b1, b2, g["eps"], g["weight_decay"],
-                    self.steps)
+                    self.steps, self.dev_step)
         else:
             N.sgd_momentum(self.flat_p, self.flat_g, self.flat_m, self.flat_pb, g["lr"], g["momentum"])
         return None

@@ -62,7 +62,8 @@ class StageExecutor:
 
 class TorchExecutor(StageExecutor):
     def __init__(self, model: SplitModel, model_name: str, learning: dict, device="cpu", is_first=False,
-                 is_last=False, recompute: bool = True, clip_grad_norm: float = 0.0, native: bool = False):
+                 is_last=False, recompute: bool = True, clip_grad_norm: float = 0.0, native: bool = False,
+                 graphs: bool = False):
         self.model = model.to(device)       # parameters must sit on the device before the optimizer re-homes them
         self.native = bool(native)
         if self.native:                     # token-model blocks -> fused sm_100a ops (train/token_native.py)
@@ -78,6 +79,13 @@ class TorchExecutor(StageExecutor):
         self._store: Dict[Any, Any] = {}
         self._nan = torch.zeros((), dtype=torch.bool, device=device)
         self._loss = None
+        self.graphs = bool(graphs) and self.native
+        if self.graphs:
+            self._graphs: Dict[Any, Any] = {}
+            self._warm: Dict[Any, int] = {}
+            self._replay_ctr = torch.zeros(1, dtype=torch.int32, device=device)
+            self._loss_buf = torch.zeros((), device=device)
+            self._cap_stream = torch.cuda.Stream(device)
         self.model.train()
 
     # -- helpers -------------------------------------------------------------
@@ -100,10 +108,85 @@ class TorchExecutor(StageExecutor):
             x = x.float().detach().requires_grad_(True)
         return x
 
+    # -- CUDA-graph capture of whole steps (native token models) -------------------------------------
+    # A step of these models is a few hundred small kernels issued from Python (~30 us each on the host) while the GPU
+    # needs a fraction of that: after two eager warm-up calls per input signature the whole call — forward, autograd
+    # backward, gradient clipping, fused AdamW — is captured once and replayed.  What would be baked into the graph
+    # lives on the device instead: the AdamW step count (bias correction) and a replay counter mixed into every
+    # dropout seed (``ops.nn.set_seed_offset``).
+    _MAX_GRAPHS = 6
+
+    def _graphed(self, kind: str, tensors, body):
+        from ..ops import nn as F
+        F.set_seed_offset(self._replay_ctr)
+        key = (kind,) + tuple((tuple(t.shape), t.dtype) for t in tensors)
+        ent = self._graphs.get(key)
+        if ent is None:
+            seen = self._warm.get(key, 0)
+            if seen < 2 or len(self._graphs) >= self._MAX_GRAPHS:
+                self._warm[key] = seen + 1
+                return body(*tensors)
+            from ..utils.timing import capture_graph
+            statics = [torch.empty_like(t) for t in tensors]
+            for st, t in zip(statics, tensors):
+                st.copy_(t)
+            outs = []
+            cur = torch.cuda.current_stream()
+            self._cap_stream.wait_stream(cur)
+            g = capture_graph(self._cap_stream, lambda: outs.extend(body(*statics)))
+            ent = self._graphs[key] = (statics, g, outs)
+        statics, g, outs = ent
+        for st, t in zip(statics, tensors):
+            st.copy_(t, non_blocking=True)
+        g.replay()
+        return tuple(o.clone() if o is not None else None for o in outs)
+
+    def _tick(self):
+        if self.graphs:
+            from ..ops import native as N
+            N.counter_inc(self._replay_ctr)
+
+    # -- bodies (run eagerly, or once under capture) -----------------------------------------------------
+    def _body_forward(self, x):
+        self._tick()
+        with torch.no_grad():
+            return (self._call(x),)
+
+    def _body_backward(self, x, grad):
+        self._tick()
+        self.opt.zero_grad(set_to_none=True)
+        want_dx = x.is_floating_point() and not self.is_first
+        if want_dx:
+            x = x.detach().requires_grad_(True)
+        out = self._call(x)
+        out.backward(gradient=grad.to(out.dtype))
+        self.opt.step()
+        return (x.grad if want_dx else None,)
+
+    def _body_last(self, x, labels):
+        self._tick()
+        self.opt.zero_grad(set_to_none=True)
+        want_dx = x.is_floating_point() and not self.is_first
+        if want_dx:
+            x = x.detach().requires_grad_(True)
+        out = self._call(x)
+        loss = self.criterion(out, labels)
+        self._nan |= torch.isnan(loss.detach())
+        self._loss_buf.copy_(loss.detach())
+        loss.backward()
+        if self.clip > 0:
+            nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
+        self.opt.step()
+        return (x.grad if want_dx else None,)
+
     # -- StageExecutor -----------------------------------------------------------
     def forward_only(self, data_id, x) -> torch.Tensor:
         self.model.train()
         x = self._prep_input(x)
+        if self.graphs and self.recompute and isinstance(x, torch.Tensor):
+            out, = self._graphed("fwd", (x.detach(),), self._body_forward)
+            self._store[data_id] = (x, None)
+            return out
         if self.recompute:
             with torch.no_grad():
                 out = self._call(x)
@@ -116,6 +199,9 @@ class TorchExecutor(StageExecutor):
     def backward(self, data_id, grad) -> Optional[torch.Tensor]:
         self.model.train()
         x, out = self._store.pop(data_id)
+        if self.graphs and out is None and isinstance(x, torch.Tensor):
+            gx, = self._graphed("bwd", (x.detach(), grad.to(self.device).float()), self._body_backward)
+            return gx
         self.opt.zero_grad(set_to_none=True)
         if out is None:                       # faithful mode: recompute with *current* weights
             out = self._call(x)
@@ -129,6 +215,10 @@ class TorchExecutor(StageExecutor):
         self.model.train()
         x = self._prep_input(x)
         labels = labels.to(self.device)
+        if self.graphs and isinstance(x, torch.Tensor):
+            gx, = self._graphed("last", (x.detach(), labels), self._body_last)
+            self._loss = self._loss_buf
+            return gx
         self.opt.zero_grad(set_to_none=True)
         out = self._call(x)
         loss = self.criterion(out, labels)
@@ -147,6 +237,8 @@ class TorchExecutor(StageExecutor):
 
     def load_state_dict(self, sd):
         self.model.load_state_dict(sd)
+        if hasattr(self.opt, "refresh_shadow"):
+            self.opt.refresh_shadow()
 
     def nan_detected(self) -> bool:
         return bool(self._nan.item())
@@ -177,7 +269,8 @@ def make_executor(model: SplitModel, model_name: str, learning: dict, device, is
         from .token_native import supports as token_supports
         if token_supports(model) and opts.get("native-tokens", True):
             return TorchExecutor(model, model_name, learning, device=dev, is_first=is_first, is_last=is_last,
-                                 recompute=bool(opts.get("recompute", True)), clip_grad_norm=clip, native=True)
+                                 recompute=bool(opts.get("recompute", True)), clip_grad_norm=clip, native=True,
+                                 graphs=bool(opts.get("token-graphs", True)))
         if kind == "b200":
             raise RuntimeError(f"no native sm_100a plan for {type(model).__name__}")
     return TorchExecutor(model, model_name, learning, device=dev, is_first=is_first, is_last=is_last,

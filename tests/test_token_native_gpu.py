@@ -308,3 +308,34 @@ def test_native_bert_lora_stage():
         ("lora_" in k or "layer15" in k) for k in names), names
     merge_lora(m)
     assert all("lora" not in k for k in m.state_dict())
+
+
+def test_graphed_steps_match_eager_and_redraw_dropout():
+    """Whole-step CUDA graphs: same trajectory as the eager native path, fresh dropout masks on every replay, device-side
+    AdamW step count."""
+    _need()
+    from split_learning_b200.models import get_model_class
+    from split_learning_b200.train.executor import TorchExecutor
+    cls = get_model_class("KWT", "SPEECHCOMMANDS")
+    learning = {"learning-rate": 2e-3, "weight-decay": 0.01}
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(16, 40, 98, generator=g)
+    y = torch.randint(0, 10, (16,), generator=g)
+    finals = {}
+    for graphs in (False, True):
+        torch.manual_seed(7)
+        e1 = TorchExecutor(cls(0, 8), "KWT", learning, "cuda", True, False, native=True, graphs=graphs)
+        e2 = TorchExecutor(cls(8, 17), "KWT", learning, "cuda", False, True, native=True, graphs=graphs)
+        for it in range(25):
+            a = e1.forward_only(it, x)
+            gx = e2.forward_backward_last(a, y)
+            e1.backward(it, gx)
+        finals[graphs] = e2.last_loss()
+        if graphs:
+            assert len(e1._graphs) == 2 and len(e2._graphs) == 1          # fwd + bwd, last
+            assert int(e2.opt.dev_step.item()) == 25
+            a1 = e1.forward_only("a", x)
+            a2 = e1.forward_only("b", x)
+            assert not torch.equal(a1, a2)                                # position dropout re-drawn per replay
+            e1._store.clear()
+    assert finals[True] < 1.2 and abs(finals[True] - finals[False]) < 0.6, finals

@@ -21,12 +21,12 @@ from split_learning_b200.train.executor import TorchExecutor  # noqa: E402
 CASES = [("KWT", "SPEECHCOMMANDS", 8, 32), ("ViT", "CIFAR10", 6, 32), ("BERT", "AGNEWS", 6, 8), ("BERT", "EMOTION", 12, 8)]
 
 
-def run(name, data, cut, batch, native, steps, warmup):
+def run(name, data, cut, batch, native, steps, warmup, graphs=False):
     cls = get_model_class(name, data)
     learning = {"learning-rate": 1e-4, "weight-decay": 0.01}
     torch.manual_seed(0)
-    e1 = TorchExecutor(cls(0, cut), name, learning, "cuda", True, False, native=native)
-    e2 = TorchExecutor(cls(cut, len(cls.LAYERS)), name, learning, "cuda", False, True, native=native)
+    e1 = TorchExecutor(cls(0, cut), name, learning, "cuda", True, False, native=native, graphs=graphs)
+    e2 = TorchExecutor(cls(cut, len(cls.LAYERS)), name, learning, "cuda", False, True, native=native, graphs=graphs)
     x = cls.example_input(batch, device="cuda")
     y = torch.randint(0, cls.num_classes(), (batch,), device="cuda")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -59,7 +59,9 @@ if __name__ == "__main__":
         r = {"model": f"{name}_{data}", "cut": cut, "batch": batch}
         for native in (False, True):
             r["native" if native else "torch"] = run(name, data, cut, batch, native, a.steps, a.warmup)
+        r["native_graphs"] = run(name, data, cut, batch, True, a.steps, a.warmup, graphs=True)
         r["speedup"] = round(r["torch"]["ms_per_step"] / r["native"]["ms_per_step"], 2)
+        r["speedup_graphs"] = round(r["torch"]["ms_per_step"] / r["native_graphs"]["ms_per_step"], 2)
         rows.append(r)
         print(json.dumps(r), flush=True)
     if a.out:
