@@ -54,6 +54,40 @@ def profile_model(model_name: str, batch: int = 4, data_name: Optional[str] = No
     return {"exe_time": exe, "size_data": sizes, "speed": round(batch / (total * 1e-9), 2) if total > 0 else 0.0}
 
 
+def profile_speed(model_name: str, batch: int = 4, data_name: Optional[str] = None, rounds: int = 100,
+                  device: Optional[str] = None, train: Optional[bool] = None) -> Dict:
+    """Whole-model throughput only — the FLEX profiler (other/FLEX/profiling.py:23-92): BERT-like models time a full
+    training step (forward of the mean, backward, AdamW), CNNs a forward pass; returns ``{"speed": samples/s}``.
+    The step runs through the stage executor, i.e. the native sm_100a path on CUDA."""
+    from .train.executor import make_executor
+    device = device or ("cuda" if torch.cuda.is_available() else "cpu")
+    klass = get_model_class(model_name, data_name)
+    train = (model_name.upper() in ("BERT", "KWT", "VIT")) if train is None else train
+    x = klass.example_input(batch, device=device)
+    cuda = torch.device(device).type == "cuda"
+    if train:
+        ex = make_executor(klass(), model_name, {"learning-rate": 1e-5, "weight-decay": 0.01}, device, True, True)
+        y = torch.zeros(batch, dtype=torch.long, device=device)
+        fn = lambda: ex.forward_backward_last(x, y)
+    else:
+        model = klass().to(device).eval()
+
+        def fn():
+            with torch.no_grad():
+                model(x)
+    for _ in range(3):
+        fn()
+    if cuda:
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        fn()
+    if cuda:
+        torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / rounds
+    return {"speed": round(batch / dt, 2)}
+
+
 _CACHE: Dict = {}
 
 
@@ -90,6 +124,14 @@ def probe_bandwidth(sizes_mb=(1, 2, 4, 8), repeats: int = 20) -> float:
         torch.cuda.synchronize()
         speeds.append((mb << 20) * repeats / (e0.elapsed_time(e1) * 1e6))
     return round(sum(speeds) / len(speeds), 4)
+
+
+def write_speed_profile(model_name: str, batch: int = 4, path: str = "profiling.json", data_name: Optional[str] = None,
+                        rounds: int = 100) -> Dict:
+    info = profile_speed(model_name, batch, data_name, rounds)
+    with open(path, "w") as f:
+        json.dump(info, f)
+    return info
 
 
 def write_profile(model_name: str, batch: int = 4, path: str = "profiling.json", data_name: Optional[str] = None) -> Dict:

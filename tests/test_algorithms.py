@@ -124,3 +124,12 @@ def test_variant_label_matrices():
     assert np.allclose(two.sum(1), 1.0) and two[0, :4].tolist() == [0.3, 0.3, 0.3, 0.1]
     explicit = label_counts(3, 2, 100, True, matrix=[[1.0, 0.0], [0.5, 0.5]])
     assert explicit.tolist() == [[100, 0], [50, 50], [100, 0]]
+
+
+def test_flex_speed_profile(tmp_path):
+    """other/FLEX/profiling.py: whole-model samples/s only."""
+    from split_learning_b200.profiler import write_speed_profile
+    info = write_speed_profile("KWT", 2, str(tmp_path / "profiling.json"), None, rounds=2)
+    assert set(info) == {"speed"} and info["speed"] > 0
+    info = write_speed_profile("VGG16", 2, str(tmp_path / "p2.json"), "CIFAR10", rounds=1)
+    assert info["speed"] > 0
