@@ -322,6 +322,10 @@ typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled2 get_encode2() {
+  // cuTensorMapEncodeTiled is a driver call: it needs a context bound to *this* thread.  Autograd worker threads may
+  // reach us before any runtime call has bound the primary context (seen as CUresult 201) -> bind it once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { int d = 0; cudaGetDevice(&d); cudaSetDevice(d); ctx_bound = true; }   // capture-safe, unlike cudaFree(0)
   static PFN_encodeTiled2 fn = nullptr;
   if (!fn) {
     void* q = nullptr;

@@ -56,7 +56,7 @@ struct AttnParams {
 };
 
 static constexpr int ATT_TILE = 16384;                       // one [128][64] bf16 box
-static constexpr int ATT_FWD_SMEM = 3 * ATT_TILE + 32768 + 1024 + 1024;
+static constexpr int ATT_FWD_SMEM = 3 * ATT_TILE + 1024 + 1024;   // P re-uses the Q/K tiles -> 4 CTAs per SM
 static constexpr int ATT_BWD_SMEM = 4 * ATT_TILE + 2 * 32768 + 1024 + 1024;
 
 // store `n` fp32 accumulator columns (a 32-wide TMEM chunk) as bf16, 16-byte vectors
@@ -84,7 +84,7 @@ __device__ __forceinline__ void store_head_tile(uint32_t tmem_lane_base, int tco
 }
 
 // ----------------------------------------------------------------------------- attention forward
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 4)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -92,8 +92,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;
   uint8_t* sK = smem + ATT_TILE;
   uint8_t* sV = smem + 2 * ATT_TILE;
-  uint8_t* sP = smem + 3 * ATT_TILE;                                    // 32 KB: [128][128] bf16, two panels
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * ATT_TILE + 32768);
+  uint8_t* sP = smem;                  // [128][128] bf16, two panels: overwrites Q and K once S = Q K^T has retired
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * ATT_TILE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -106,7 +106,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < 3; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  if (warp == 0) tmem_alloc<128>(tmem_slot);       // S [0,128); O re-uses [0,64) after the softmax has consumed S
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -186,8 +186,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const uint32_t idesc = umma_idesc_bf16(128, 64, false, true);       // A = P (K-major), B = V (MN-major)
     const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
-    for (int k = 0; k < 8; ++k)                                          // O~ = P~ V  -> TMEM [128, 192)
-      umma_bf16(tmem + 128, umma_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+    for (int k = 0; k < 8; ++k)                                          // O~ = P~ V  -> TMEM [0, 64)
+      umma_bf16(tmem, umma_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
                 umma_desc_sw128(va + k * 2048, 16384, 1024), idesc, k != 0);
     umma_commit(&bars[2]);
   }
@@ -196,13 +196,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const bool row_ok = row < p.S;
   const long long grow = static_cast<long long>(b) * p.S + row;
-  store_head_tile(lane_base, 128, p.out + grow * p.ldo + h * p.Dh, vc & 63, p.Dh, row_ok, 1.f / sum);
+  store_head_tile(lane_base, 0, p.out + grow * p.ldo + h * p.Dh, vc & 63, p.Dh, row_ok, 1.f / sum);
   if (row_ok) p.lse[static_cast<long long>(blockIdx.x) * 128 + row] = mx + logf(sum);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem);
+    tmem_dealloc<128>(tmem);
   }
 }
 
@@ -271,11 +271,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   const uint32_t idx0 = (static_cast<uint32_t>(blockIdx.x) * 128u + row) * 128u;
 
-  // pass 1: P~ -> smem, D = rowsum(P~ * dP)
+  // pass 1: P~ -> smem, D = rowsum(P~ * dP); the probabilities (bf16) and the dropout mask stay in registers
   float D = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < 128; c += 32) {
-    float e[32];
+  uint32_t pk[64], mbits[4];
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci) {
+    const int c = ci * 32;
+    float e[32], pr[32];
+    uint32_t mb = 0;
     if (c < p.S) {                        // warp-uniform: tcgen05.ld is .sync.aligned, row_ok only predicates the math
       uint32_t s[32], g[32];
       tmem_ld32(lane_base + c, s);
@@ -284,43 +287,45 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = c + j;
-        float x = 0.f;
+        float x = 0.f, mk = 1.f;
         if (col < p.S && row_ok) {
           x = exp2f((__uint_as_float(s[j]) * p.scale + (kb ? __ldg(kb + col) : 0.f) - lse) * LOG2E);
-          if (p.p_drop > 0.f) x *= drop_scale(seed, idx0 + col, p.p_drop, inv_keep);
-          D += x * __uint_as_float(g[j]);
+          if (p.p_drop > 0.f) mk = drop_scale(seed, idx0 + col, p.p_drop, inv_keep);
         }
+        pr[j] = x;
+        if (mk != 0.f) mb |= 1u << j;
+        x *= mk;
+        D += x * __uint_as_float(g[j]);
         e[j] = x;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) e[j] = 0.f;
+      for (int j = 0; j < 32; ++j) { e[j] = 0.f; pr[j] = 0.f; }
     }
+    mbits[ci] = mb;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[ci * 16 + j] = pack_bf16x2(pr[2 * j], pr[2 * j + 1]);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       *reinterpret_cast<uint4*>(sP + sw128_chunk(row, (c >> 3) + j)) =
           make_uint4(pack_bf16x2(e[8 * j], e[8 * j + 1]), pack_bf16x2(e[8 * j + 2], e[8 * j + 3]),
                      pack_bf16x2(e[8 * j + 4], e[8 * j + 5]), pack_bf16x2(e[8 * j + 6], e[8 * j + 7]));
   }
-  // pass 2: dS -> smem
-#pragma unroll 1
-  for (int c = 0; c < 128; c += 32) {
+  // pass 2: dS = P * (dP * mask - D) * scale -> smem   (no second exp / hash: P and the mask come from registers)
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci) {
+    const int c = ci * 32;
     float e[32];
     if (c < p.S) {
-      uint32_t s[32], g[32];
-      tmem_ld32(lane_base + c, s);
+      uint32_t g[32];
       tmem_ld32(lane_base + 128 + c, g);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int col = c + j;
-        float x = 0.f;
-        if (col < p.S && row_ok) {
-          const float pr = exp2f((__uint_as_float(s[j]) * p.scale + (kb ? __ldg(kb + col) : 0.f) - lse) * LOG2E);
-          const float mk = p.p_drop > 0.f ? drop_scale(seed, idx0 + col, p.p_drop, inv_keep) : 1.f;
-          x = pr * (__uint_as_float(g[j]) * mk - D) * p.scale;
-        }
-        e[j] = x;
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&pk[ci * 16 + (j >> 1)]);
+        const float prj = __bfloat162float((j & 1) ? h2.y : h2.x);
+        const float mk = ((mbits[ci] >> j) & 1u) ? inv_keep : 0.f;
+        e[j] = prj * (__uint_as_float(g[j]) * mk - D) * p.scale;
       }
     } else {
 #pragma unroll
@@ -556,6 +561,10 @@ typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled3 get_encode3() {
+  // cuTensorMapEncodeTiled is a driver call: it needs a context bound to *this* thread.  Autograd worker threads may
+  // reach us before any runtime call has bound the primary context (seen as CUresult 201) -> bind it once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { int d = 0; cudaGetDevice(&d); cudaSetDevice(d); ctx_bound = true; }   // capture-safe, unlike cudaFree(0)
   static PFN_encodeTiled3 fn = nullptr;
   if (!fn) {
     void* q = nullptr;

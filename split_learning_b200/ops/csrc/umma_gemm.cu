@@ -442,6 +442,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static PFN_encodeTiled get_encode() {
+  // cuTensorMapEncodeTiled is a driver call: it needs a context bound to *this* thread.  Autograd worker threads may
+  // reach us before any runtime call has bound the primary context (seen as CUresult 201) -> bind it once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { int d = 0; cudaGetDevice(&d); cudaSetDevice(d); ctx_bound = true; }   // capture-safe, unlike cudaFree(0)
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
     void* p = nullptr;
