@@ -57,3 +57,20 @@ def test_rank_assignment():
     assert rank_assignment([1, 1]) == [(1, 0, 0), (2, 0, 0)]
     r = rank_assignment([4, 4], [[2, 2], [2, 2]])
     assert len(r) == 8 and r[0] == (1, 0, 0) and r[2] == (2, 0, 0) and r[4] == (1, 1, 0)
+
+
+def test_shipped_example_configs_normalise():
+    """configs/*.yaml: one example per algorithm variant / model family / topology."""
+    import glob
+    import os
+    import yaml
+    from split_learning_b200.config import normalize
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "configs", "*.yaml")))
+    assert len(files) >= 12
+    algos = set()
+    for f in files:
+        cfg = normalize(yaml.safe_load(open(f)))
+        algos.add(cfg.b200.get("algorithm", "main"))
+        assert sum(cfg.clients) >= 2
+    assert algos == {"main", "vanilla_sl", "cluster_fsl", "dcsl", "flex", "2ls"}
