@@ -850,7 +850,8 @@ int slb_preload_elementwise() {
   SLB_PRELOAD(bn_relu_pool_fwd_kernel); SLB_PRELOAD(bn_bwd_reduce_kernel<true>); SLB_PRELOAD(bn_bwd_reduce_kernel<false>);
   SLB_PRELOAD(bn_bwd_apply_kernel<true>); SLB_PRELOAD(bn_bwd_apply_kernel<false>); SLB_PRELOAD(col_stats_kernel);
   SLB_PRELOAD(bn_bwd_fused_kernel<true>); SLB_PRELOAD(bn_bwd_fused_kernel<false>);
-  SLB_PRELOAD(conv_finalize_kernel); { auto k1 = conv3x3_small_fwd_kernel<3, 64>; SLB_PRELOAD(k1); auto k2 = conv3x3_small_fwd_kernel<1, 64>; SLB_PRELOAD(k2); }
+  SLB_PRELOAD(conv_finalize_kernel); { auto k1 = conv3x3_small_fwd_kernel<3, 64>; SLB_PRELOAD(k1); auto k2 = conv3x3_small_fwd_kernel<1, 64>; SLB_PRELOAD(k2);
+    auto k3 = conv3x3_small_fwd_kernel<3, 32>; SLB_PRELOAD(k3); auto k4 = conv3x3_small_fwd_kernel<1, 32>; SLB_PRELOAD(k4); }
   SLB_PRELOAD(conv3x3_small_wgrad_kernel<3>); SLB_PRELOAD(conv3x3_small_wgrad_kernel<1>); SLB_PRELOAD(linear_finalize_kernel);
   SLB_PRELOAD(linear_bwd_prep_kernel); SLB_PRELOAD(dropout_fwd_kernel); SLB_PRELOAD(dropout_bwd_kernel);
   SLB_PRELOAD(ce_fwd_bwd_kernel); SLB_PRELOAD(sgd_momentum_kernel); SLB_PRELOAD(adamw_kernel); SLB_PRELOAD(cast_f32_bf16_kernel);

@@ -66,9 +66,9 @@ class TorchExecutor(StageExecutor):
                  graphs: bool = False):
         self.model = model.to(device)       # parameters must sit on the device before the optimizer re-homes them
         self.native = bool(native)
-        if self.native:                     # token-model blocks -> fused sm_100a ops (train/token_native.py)
-            from .token_native import nativize
-            nativize(self.model)
+        if self.native:                     # blocks -> fused sm_100a ops (train/token_native.py, train/cnn_native.py)
+            from . import cnn_native, token_native
+            (cnn_native if cnn_native.supports(self.model) else token_native).nativize(self.model)
         self.model_name = model_name
         self.device = device
         self.is_first, self.is_last = is_first, is_last
@@ -266,8 +266,9 @@ def make_executor(model: SplitModel, model_name: str, learning: dict, device, is
         if supports(model):
             return B200Executor(model, model_name, learning, device=dev, is_first=is_first, is_last=is_last,
                                 recompute=bool(opts.get("recompute", True)))
+        from .cnn_native import supports as cnn_supports
         from .token_native import supports as token_supports
-        if token_supports(model) and opts.get("native-tokens", True):
+        if (token_supports(model) or cnn_supports(model)) and opts.get("native-tokens", True):
             return TorchExecutor(model, model_name, learning, device=dev, is_first=is_first, is_last=is_last,
                                  recompute=bool(opts.get("recompute", True)), clip_grad_norm=clip, native=True,
                                  graphs=bool(opts.get("token-graphs", True)))
