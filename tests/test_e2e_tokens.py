@@ -1,4 +1,4 @@
-"""Token-model families through the full control plane (REGISTER .. STOP): KWT / ViT with AdamW, BERT with LoRA
+"""Token-model families (and MobileNetv1) through the full control plane (REGISTER .. STOP): KWT / ViT with AdamW, BERT with LoRA
 wrapping + merge before upload (reference src/RpcClient.py:61-66,99-103,121-122).  CPU: torch executor; GPU: the
 native sm_100a blocks (``train/token_native.py``) — same config, same checkpoint layout."""
 import os
@@ -12,7 +12,8 @@ from split_learning_b200.config import normalize
 from split_learning_b200.runner import run_inproc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CASES = [("KWT", "SPEECHCOMMANDS", 8, 10, 4, 152), ("ViT", "CIFAR10", 6, 10, 4, 80), ("BERT", "AGNEWS", 6, 4, 2, 201)]
+CASES = [("KWT", "SPEECHCOMMANDS", 8, 10, 4, 152), ("ViT", "CIFAR10", 6, 10, 4, 80), ("BERT", "AGNEWS", 6, 4, 2, 201),
+         ("MobileNetv1", "CIFAR10", 15, 10, 4, 191)]
 
 
 def _raw(tmp, model, data, cut, labels, bs):
@@ -50,8 +51,8 @@ def test_token_family_round_native_gpu(tmp_path, model, data, cut, labels, bs, n
         made.append(self.native)
     monkeypatch.setattr(E.TorchExecutor, "__init__", spy)
     before = N.LAUNCHES
-    srv = run_inproc(normalize(_raw(tmp_path, model, data, cut, labels, 8)), devices=["cuda:0"], workdir=str(tmp_path),
-                     timeout=600)
+    srv = run_inproc(normalize(_raw(tmp_path, model, data, cut, labels, 32 if model == "MobileNetv1" else 8)),
+                     devices=["cuda:0"], workdir=str(tmp_path), timeout=600)
     assert srv.history and srv.history[0]["ok"]
     assert made and all(made), made                      # every stage ran the native blocks
     assert N.LAUNCHES - before > 100

@@ -1,4 +1,4 @@
-"""Step time of the token-model families, native sm_100a ops vs stock torch modules (same executor, same optimizer).
+"""Step time of the token-model families and MobileNetv1, native sm_100a ops vs stock torch modules (same executor, same optimizer).
 
     python tools/bench_tokens.py [--steps 30] [--warmup 10]
 
@@ -18,7 +18,8 @@ from split_learning_b200.models import get_model_class  # noqa: E402
 from split_learning_b200.ops import native as N  # noqa: E402
 from split_learning_b200.train.executor import TorchExecutor  # noqa: E402
 
-CASES = [("KWT", "SPEECHCOMMANDS", 8, 32), ("ViT", "CIFAR10", 6, 32), ("BERT", "AGNEWS", 6, 8), ("BERT", "EMOTION", 12, 8)]
+CASES = [("KWT", "SPEECHCOMMANDS", 8, 32), ("ViT", "CIFAR10", 6, 32), ("BERT", "AGNEWS", 6, 8), ("BERT", "EMOTION", 12, 8),
+         ("MobileNetv1", "CIFAR10", 15, 32)]
 
 
 def run(name, data, cut, batch, native, steps, warmup, graphs=False):
