@@ -5,10 +5,12 @@ through peer-memory mailboxes written by the stage kernels instead of broker que
 Wiring happens while handling START: every client allocates the mailboxes it *consumes*
 (activations from upstream, gradients from downstream), exports them with CUDA IPC and posts
 the 64-byte handles to its chain partner's ``ipc_{client_id}`` queue; partners are derived
-from the START ``peers`` table (stage s member i <-> stage s+1 member i — the static pairing of
-the reference's competing-consumer queue).  If replica counts differ between adjacent stages,
-or the stage has no native plan, the client silently keeps the host data plane — that is a
-*topology* fallback (documented), never a kernel fallback.
+from the START ``peers`` table.  Every first-stage client defines a *lane*; lane i is served at
+stage s by member ``i % n_s`` — the static counterpart of the reference's competing-consumer
+queue — so many-clients-few-servers topologies ([4,2], [2,1], [4,2,1]) run on the device plane
+with the downstream stage multiplexing its lanes on one executor (fan-in).  If a stage does not
+divide its predecessor, or the stage has no native plan, the client keeps the host data plane —
+a *topology* fallback (logged), never a kernel fallback.
 
 Only full microbatches go through the device plane (mailbox geometry is static): a trailing
 partial batch of the loader is dropped, which the reference's sample counts (multiples of the
@@ -47,21 +49,26 @@ class DeviceRpcClient(RpcClient):
             self.send_to_server(m)
 
     # ------------------------------------------------------------------
-    def _partners(self, msg: dict):
+    def _lanes(self, msg: dict):
+        """A *lane* is one first-stage client's chain through the stages.  Lane ``i`` is served at stage ``s`` by member
+        ``i % n_s`` (the deterministic counterpart of the reference's competing-consumer queue), which needs every
+        stage to divide its predecessor: [4,4], [4,2], [2,1], [4,2,1] ... A stage member serving several lanes
+        multiplexes them on its one executor (fan-in).  Returns [(lane, upstream id | None, downstream id | None)]."""
         members: Dict[int, list] = msg["peers"]["members"]
-        me = [cid for cid, _ in members[self.layer_id]].index(str(self.client_id))
-        up = down = None
-        if self.layer_id > 1:
-            ups = members[self.layer_id - 1]
-            if len(ups) != len(members[self.layer_id]):
-                raise RuntimeError("unequal replica counts between adjacent stages")
-            up = ups[me][0]
-        if self.layer_id < self.num_layers:
-            downs = members[self.layer_id + 1]
-            if len(downs) != len(members[self.layer_id]):
-                raise RuntimeError("unequal replica counts between adjacent stages")
-            down = downs[me][0]
-        return up, down
+        ids = {s: [cid for cid, _ in members[s]] for s in members}
+        n = {s: len(ids[s]) for s in ids}
+        for s in range(2, self.num_layers + 1):
+            if n[s] == 0 or n[s - 1] % n[s] != 0:
+                raise RuntimeError(f"replica counts {[n[k] for k in sorted(n)]}: stage {s} does not divide stage {s - 1}")
+        me = ids[self.layer_id].index(str(self.client_id))
+        lanes = []
+        for lane in range(n[1]):
+            if lane % n[self.layer_id] != me:
+                continue
+            up = ids[self.layer_id - 1][lane % n[self.layer_id - 1]] if self.layer_id > 1 else None
+            down = ids[self.layer_id + 1][lane % n[self.layer_id + 1]] if self.layer_id < self.num_layers else None
+            lanes.append((lane, up, down))
+        return lanes
 
     def _wire(self, msg: dict) -> None:
         from ..train.b200_executor import B200Executor
@@ -70,22 +77,28 @@ class DeviceRpcClient(RpcClient):
         ex = self.executor
         B = int(self.learning["batch-size"])
         depth = int(self.learning.get("control-count", 3))
-        up, down = self._partners(msg)
+        lanes = self._lanes(msg)
         dev = ex.device
-        fwd_in = grad_in = fwd_out = grad_out = None
         my_q = f"ipc_{self.client_id}"
         self.channel.queue_declare(my_q)
-        if up is not None:                                     # I consume activations
-            c, h, w = ex.in_shape
-            spec_in = MailboxSpec(depth, B, (B, h, w, c))
-            fwd_in, hdl = Mailbox.allocate_exportable(spec_in, dev)
-            self.channel.publish_obj(f"ipc_{up}", {"kind": "act", "handle": hdl, "shape": spec_in.payload_shape})
-        if down is not None:                                   # I consume gradients of my output
-            c, h, w = ex.out_shape
-            spec_out = MailboxSpec(depth, B, (B, h, w, c))
-            grad_in, hdl = Mailbox.allocate_exportable(spec_out, dev)
-            self.channel.publish_obj(f"ipc_{down}", {"kind": "grad", "handle": hdl, "shape": spec_out.payload_shape})
-        need = int(up is not None) + int(down is not None)
+        fwd_in: Dict[int, Mailbox] = {}
+        grad_in: Dict[int, Mailbox] = {}
+        for lane, up, down in lanes:
+            if up is not None:                                     # I consume this lane's activations
+                c, h, w = ex.in_shape
+                spec_in = MailboxSpec(depth, B, (B, h, w, c))
+                fwd_in[lane], hdl = Mailbox.allocate_exportable(spec_in, dev)
+                self.channel.publish_obj(f"ipc_{up}", {"kind": "act", "lane": lane, "handle": hdl,
+                                                       "shape": spec_in.payload_shape})
+            if down is not None:                                   # I consume the gradients of this lane's output
+                c, h, w = ex.out_shape
+                spec_out = MailboxSpec(depth, B, (B, h, w, c))
+                grad_in[lane], hdl = Mailbox.allocate_exportable(spec_out, dev)
+                self.channel.publish_obj(f"ipc_{down}", {"kind": "grad", "lane": lane, "handle": hdl,
+                                                         "shape": spec_out.payload_shape})
+        need = sum(int(up is not None) + int(down is not None) for _, up, down in lanes)
+        fwd_out: Dict[int, Mailbox] = {}
+        grad_out: Dict[int, Mailbox] = {}
         t0 = time.monotonic()
         while need:
             m = self.channel.get_obj(my_q, 0.25)
@@ -95,61 +108,91 @@ class DeviceRpcClient(RpcClient):
                 continue
             spec = MailboxSpec(depth, B, tuple(m["shape"]))
             mb = Mailbox.open_peer(spec, m["handle"], dev)
-            if m["kind"] == "act":                             # my downstream's activation ring: I produce into it
-                fwd_out = mb
-            else:                                              # my upstream's gradient ring
-                grad_out = mb
+            if m["kind"] == "act":                                 # downstream's activation ring: I produce into it
+                fwd_out[m["lane"]] = mb
+            else:                                                  # upstream's gradient ring
+                grad_out[m["lane"]] = mb
             need -= 1
-        self.dstage = DeviceStage(ex, B, depth, fwd_in=fwd_in, grad_in=grad_in, fwd_out=fwd_out, grad_out=grad_out)
-        self._down, self._up = down, up
+        multi = len(lanes) > 1
+        if multi:                                                  # all lanes' mailbox slots become the plan's input slots
+            ex.plan(B).bind_inputs([t for lane, _, _ in lanes for t in fwd_in[lane].payload])
+        self.dstages: Dict[int, DeviceStage] = {}
+        for k, (lane, up, down) in enumerate(lanes):
+            self.dstages[lane] = DeviceStage(ex, B, depth, fwd_in=fwd_in.get(lane), grad_in=grad_in.get(lane),
+                                             fwd_out=fwd_out.get(lane), grad_out=grad_out.get(lane),
+                                             slot_offset=k * depth if multi else 0, bind_inputs=not multi)
+        self._lane_info = lanes
+        self.dstage = self.dstages[lanes[0][0]]
 
     # ------------------------------------------------------------------
+    def _collect_plans(self, lanes) -> Dict[int, int]:
+        """Batch counts announced by the first-stage client of every lane I serve."""
+        plan_q = f"plan_{self.client_id}"
+        counts: Dict[int, int] = {}
+        t0 = time.monotonic()
+        while len(counts) < len(lanes):
+            m = self.channel.get_obj(plan_q, 0.25)
+            if m is None:
+                if time.monotonic() - t0 > self.watchdog:
+                    raise TimeoutError("upstream never announced its batch count")
+                continue
+            counts[int(m["lane"])] = int(m["batches"])
+        return counts
+
     def run_stage(self):
         if self.dstage is None:
             return super().run_stage()
-        st, B = self.dstage, self.dstage.B
+        lanes = self._lane_info
+        B = self.dstage.B
         ex = self.executor
-        plan_q = f"plan_{self.client_id}"
         if self.is_first:
+            lane, _, down = lanes[0]
+            st = self.dstages[lane]
             batches = []
             for batch in self.train_loader:
                 x, y = batch if not isinstance(batch, dict) else (batch["input_ids"], batch["labels"])
                 if x.shape[0] == B:
                     batches.append((x.float().pin_memory(), torch.as_tensor(y).long().pin_memory()))
             n = len(batches)
-            self.channel.publish_obj(f"plan_{self._down}", {"batches": n})
-        else:
-            t0 = time.monotonic()
-            while True:
-                m = self.channel.get_obj(plan_q, 0.25)
-                if m is not None:
-                    n = int(m["batches"])
-                    break
-                if time.monotonic() - t0 > self.watchdog:
-                    raise TimeoutError("upstream never announced its batch count")
-            if not self.is_last:
-                self.channel.publish_obj(f"plan_{self._down}", {"batches": n})
-        if self.is_last:
-            for it in range(n):
-                st.last(it)
-        else:
+            self.channel.publish_obj(f"plan_{down}", {"lane": lane, "batches": n})
             it_b = 0
             for it in range(n):
                 if it - it_b >= st.depth:
                     st.backward(it_b)
                     it_b += 1
-                if self.is_first:
-                    st.stage_input(it, *batches[it])
+                st.stage_input(it, *batches[it])
                 st.forward(it)
             while it_b < n:
                 st.backward(it_b)
                 it_b += 1
-        st.stream.synchronize()
-        st.check()
+            total = n
+        else:
+            counts = self._collect_plans(lanes)
+            if not self.is_last:
+                for lane, _, down in lanes:
+                    self.channel.publish_obj(f"plan_{down}", {"lane": lane, "batches": counts[lane]})
+            depth = self.dstage.depth
+            most = max(counts.values()) if counts else 0
+            # lanes are interleaved microbatch by microbatch (round-robin over the upstream replicas)
+            for it in range(most + (0 if self.is_last else depth)):
+                for lane, _, _ in lanes:
+                    st, n = self.dstages[lane], counts[lane]
+                    if self.is_last:
+                        if it < n:
+                            st.last(it)
+                    else:
+                        if 0 <= it - depth < n:
+                            st.backward(it - depth)
+                        if it < n:
+                            st.forward(it)
+            total = sum(counts.values())
+        self.dstage.stream.synchronize()
+        for st in self.dstages.values():
+            st.check()
         if self.is_first:
             self.send_to_server(M.notify(self.client_id, self.layer_id, self.cluster))
         self.trainer._wait_pause()
-        return (not ex.nan_detected()), n
+        return (not ex.nan_detected()), total
 
     # ------------------------------------------------------------------ round end
     def _replicas(self) -> List[str]:

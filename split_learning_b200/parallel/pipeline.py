@@ -42,8 +42,13 @@ class DeviceStage:
     def __init__(self, ex: B200Executor, batch: int, depth: int,
                  fwd_in: Optional[Mailbox] = None, grad_in: Optional[Mailbox] = None,
                  fwd_out: Optional[Mailbox] = None, grad_out: Optional[Mailbox] = None,
-                 stream: Optional[torch.cuda.Stream] = None, wait_spins: Optional[int] = None):
+                 stream: Optional[torch.cuda.Stream] = None, wait_spins: Optional[int] = None,
+                 slot_offset: int = 0, bind_inputs: bool = True):
+        """``slot_offset`` / ``bind_inputs=False``: one of several *lanes* multiplexed on the same executor (fan-in: a
+        stage fed by several upstream replicas).  The caller binds the plan's input slots to the concatenated mailbox
+        payloads of all lanes once; this lane's slot ``s`` is plan slot ``slot_offset + s``."""
         self.ex, self.B, self.depth = ex, batch, depth
+        self.off = int(slot_offset)
         self.fwd_in, self.grad_in, self.fwd_out, self.grad_out = fwd_in, grad_in, fwd_out, grad_out
         self.stream = stream or ex.stream
         self.plan = ex.plan(batch)
@@ -57,9 +62,9 @@ class DeviceStage:
         self.wait_spins = wait_spins if wait_spins is not None else int(os.environ.get("SLB200_WAIT_SPINS", str(1 << 28)))
         self._posted = {"F": 0, "B": 0, "L": 0}
         self.labels_slots = [torch.zeros(batch, dtype=torch.int64, device=dev) for _ in range(depth)]
-        if fwd_in is not None:                        # consume activations in place from my mailbox
+        if fwd_in is not None and bind_inputs:        # consume activations in place from my mailbox
             self.plan.bind_inputs(fwd_in.payload)
-        elif self.plan.n_slots < depth:
+        elif fwd_in is None and self.plan.n_slots < depth:
             raise RuntimeError("executor has fewer input slots than the pipeline depth")
         self.graphs: Dict[Tuple[str, int], torch.cuda.CUDAGraph] = {}
         self.use_graphs = ex.use_graphs
@@ -79,12 +84,12 @@ class DeviceStage:
             N.memcpy_async(self.fwd_out.labels[slot].data_ptr(), labels.data_ptr(), self.B * 8)
             out = self.fwd_out.payload[slot]
             pub = {"flag": self.fwd_out.flag_ptr(slot), "seq": self.seq_fwd.at(slot)}
-        self.plan._forward(slot, out_ptr_override=out, publish=pub)
+        self.plan._forward(self.off + slot, out_ptr_override=out, publish=pub)
 
     def _B(self, slot: int) -> None:
         N.wait_flag(self.grad_in.flag_ptr(slot), 0, self.exp_grad.at(slot), self.wait_spins, self.status)
         if self.ex.recompute:
-            self.plan._forward(slot)                  # faithful recompute with current weights, no publish
+            self.plan._forward(self.off + slot)       # faithful recompute with current weights, no publish
         gout = self.grad_out.payload[slot] if self.grad_out is not None else None
         self.plan._backward(self.grad_in.payload[slot], grad_out_override=gout)
         if self.grad_out is not None:
@@ -96,7 +101,7 @@ class DeviceStage:
             N.wait_flag(self.fwd_in.flag_ptr(slot), 0, self.exp_fwd.at(slot), self.wait_spins, self.status)
             labels = self.fwd_in.labels[slot]
         gout = self.grad_out.payload[slot] if self.grad_out is not None else None
-        self.plan._last(slot, labels=labels, grad_out_override=gout)
+        self.plan._last(self.off + slot, labels=labels, grad_out_override=gout)
         if self.grad_out is not None:
             N.set_flag(self.grad_out.flag_ptr(slot), 0, self.seq_grad.at(slot))
 

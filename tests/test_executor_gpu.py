@@ -235,6 +235,38 @@ def test_public_api_device_plane(tmp_path, monkeypatch):
     assert int(sd["layer2.num_batches_tracked"]) == 40                       # recomputing first stage: 2 forwards each
 
 
+@pytest.mark.parametrize("clients,cuts", [((2, 1), [7]), ((2, 2, 1), [5, 10])])
+def test_public_api_device_plane_fan_in(tmp_path, monkeypatch, clients, cuts):
+    """Many clients, fewer servers on the device plane: the downstream stage multiplexes one mailbox lane per upstream
+    replica on its executor (static round-robin in place of the reference's competing-consumer queue)."""
+    import yaml
+    monkeypatch.setenv("SLB200_WAIT_SPINS", str(1 << 23))
+    from split_learning_b200.checkpoint import load_checkpoint
+    from split_learning_b200.config import normalize
+    from split_learning_b200.parallel.device_client import DeviceRpcClient
+    from split_learning_b200.runner import run_inproc
+    raw = yaml.safe_load(open("config.yaml"))
+    raw["server"].update({"clients": list(clients), "global-round": 1, "validation": False})
+    raw["server"]["data-distribution"]["num-sample"] = 320
+    raw["server"]["manual"]["no-cluster"]["cut-layers"] = list(cuts)
+    raw["server"]["manual"]["cluster"] = {"num-cluster": 1, "cut-layers": [list(cuts)], "infor-cluster": [list(clients)]}
+    raw["log_path"] = str(tmp_path)
+    raw["learning"].update({"batch-size": 32, "control-count": 3, "learning-rate": 0.01})
+    raw["b200"] = {"synthetic-data": True, "data-plane": "device", "watchdog-seconds": 120}
+    srv = run_inproc(normalize(raw), devices=["cuda:0"], workdir=str(tmp_path), timeout=600)
+    assert [h["ok"] for h in srv.history] == [True]
+    cl = srv.clients_objs
+    assert all(isinstance(c, DeviceRpcClient) and c.dstage is not None for c in cl)
+    last = [c for c in cl if c.layer_id == len(clients)]
+    assert len(last) == 1 and len(last[0].dstages) == clients[0]              # one lane per first-stage client
+    sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    n_last_bn = "layer12" if len(clients) == 3 else "layer9"
+    # every first-stage client contributes 10 microbatches; the single last stage trains on all of them
+    assert len(sd) == 97 and int(sd[f"{n_last_bn}.num_batches_tracked"]) == 10 * clients[0]
+    assert int(sd["layer2.num_batches_tracked"]) == 20                         # per client: 10 forwards + 10 recomputes
+    assert all(torch.isfinite(v.float()).all() for v in sd.values())
+
+
 @pytest.mark.parametrize("model_name,kind", [("KWT", "adamw"), ("MobileNetv1", "sgd")])
 def test_flat_fused_optimizer_matches_torch(model_name, kind):
     """Torch-executed families on CUDA step through the fused flat optimizers (G9/G10)."""
