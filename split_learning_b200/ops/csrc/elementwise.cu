@@ -902,6 +902,9 @@ int slb_bn_relu_pool_bwd(const void* dout, const void* y, const float* gamma, co
                          const float* save_invstd, float* dgamma, float* dbeta, void* dy, int P, int C, int H, int W, int relu,
                          int pool, int identity, uint32_t* grid_bar, cudaStream_t st) {
   if (C % 8 || C > 2048) return -1;
+  // identity == 2: dgamma / dbeta already hold the reduction (done by the downstream dgrad epilogue) -> apply pass only
+  const bool skip_reduce = identity == 2;
+  if (skip_reduce) { identity = 0; grid_bar = nullptr; }
   BnBwdParams p = {reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(y), gamma, beta,
                    save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dy), P, C, H, W, relu, pool, identity};
   const int tx = C / 8;
@@ -928,10 +931,10 @@ int slb_bn_relu_pool_bwd(const void* dout, const void* y, const float* gamma, co
     return last_err();
   }
   if (pool) {
-    if (!identity) launch_k(bn_bwd_reduce_kernel<true>, grid, block, 2 * C * sizeof(float), st, p);
+    if (!identity && !skip_reduce) launch_k(bn_bwd_reduce_kernel<true>, grid, block, 2 * C * sizeof(float), st, p);
     launch_k(bn_bwd_apply_kernel<true>, grid, block, 0, st, p);
   } else {
-    if (!identity) launch_k(bn_bwd_reduce_kernel<false>, grid, block, 2 * C * sizeof(float), st, p);
+    if (!identity && !skip_reduce) launch_k(bn_bwd_reduce_kernel<false>, grid, block, 2 * C * sizeof(float), st, p);
     launch_k(bn_bwd_apply_kernel<false>, grid, block, 0, st, p);
   }
   return last_err();

@@ -48,6 +48,15 @@ struct GemmParams {
   uint32_t* tile_counters;   // [m_tiles * n_tiles], zero at rest (self-resetting)
   __nv_bfloat16* fin_out;    // bf16 destination [M][fin_ld]
   long long fin_ld;
+  // dgrad epilogue doubling as the BatchNorm-backward reduction of the *upstream* block (whose ReLU output this dX is
+  // the gradient of): col_sum += sum_p m*dX (dbeta), col_sumsq += sum_p m*dX*xhat (dgamma), m = ReLU mask recomputed
+  // from the saved conv output.  Removes one launch per conv block from the backward critical path.
+  const __nv_bfloat16* bnb_y;     // [M][N] saved pre-BN conv output of the upstream block, or nullptr
+  const float* bnb_mean;
+  const float* bnb_istd;
+  const float* bnb_gamma;
+  const float* bnb_beta;
+  int bnb_relu;
   // transformer epilogue (EPI_BF16, MODE_GEMM): out = act(acc + bias + residual); aux_out keeps the pre-activation
   int act;                        // 0 none, 1 ReLU, 2 GELU (erf), 3 tanh
   __nv_bfloat16* aux_out;         // [M][ldo] or nullptr
@@ -86,6 +95,47 @@ __device__ __forceinline__ float warp_col_reduce32(float (&v)[32]) {
     }
   }
   return v[0];
+}
+
+// Per-element terms of the two column reductions of an epilogue chunk (row = pixel, 32 consecutive channels):
+// BatchNorm forward statistics (x, x^2) or, with bnb_y, the BatchNorm backward sums of the upstream block.
+__device__ __forceinline__ void stat_terms(const GemmParams& p, int row, bool row_ok, int col0, const float (&f)[32],
+                                           float (&s1)[32], float (&s2)[32]) {
+  if (p.bnb_y == nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float r = row_ok ? __bfloat162float(__float2bfloat16(f[j])) : 0.f;   // statistics of the stored values
+      s1[j] = r;
+      s2[j] = r * r;
+    }
+    return;
+  }
+  if (!row_ok) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    return;
+  }
+  const uint4* y4 = reinterpret_cast<const uint4*>(p.bnb_y + static_cast<long long>(row) * p.N + col0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 u = __ldg(y4 + q);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 yy = __bfloat1622float2(h2[e]);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int j = 8 * q + 2 * e + t, c = col0 + j;
+        const float y = t ? yy.y : yy.x;
+        const float mean = __ldg(p.bnb_mean + c), istd = __ldg(p.bnb_istd + c);
+        const float sc = __ldg(p.bnb_gamma + c) * istd, sh = __ldg(p.bnb_beta + c) - mean * sc;
+        const float r = __bfloat162float(__float2bfloat16(f[j]));
+        const float dz = (p.bnb_relu && fmaf(y, sc, sh) <= 0.f) ? 0.f : r;          // same test as bn_dz()
+        s1[j] = dz;
+        s2[j] = dz * (y - mean) * istd;
+      }
+    }
+  }
 }
 
 template <int MODE, int BLOCK_N>
@@ -313,12 +363,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (want_stats) {
             // statistics of the bf16-rounded values that were stored (what the consumer normalises)
             float s1[32], s2[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float r = row_ok ? __bfloat162float(__float2bfloat16(f[j])) : 0.f;
-              s1[j] = r;
-              s2[j] = r * r;
-            }
+            stat_terms(p, row, row_ok, col0, f, s1, s2);
             const float c1 = warp_col_reduce32(s1);
             const float c2 = warp_col_reduce32(s2);
             atomicAdd(&s_stats[c + lane_id()], c1);
@@ -403,12 +448,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (want_stats) {
               float s1[32], s2[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float r = row_ok ? __bfloat162float(__float2bfloat16(f[j])) : 0.f;
-                s1[j] = r;
-                s2[j] = r * r;
-              }
+              stat_terms(p, row, row_ok, col0, f, s1, s2);
               const float c1 = warp_col_reduce32(s1);
               const float c2 = warp_col_reduce32(s2);
               atomicAdd(&s_stats[c + lane_id()], c1);
@@ -550,10 +590,36 @@ int slb_preload_gemm() {
 // x := dY [B,H,W,Cout_w], w as stored, out = dX[B,H,W,Cin_w]  (then Cin here means channels of A = Cout_w).
 // block_n in {64,128,256} (0 = auto); k_split > 1 accumulates fp32 partial sums into `acc` ([M][Nout], zeroed by the
 // caller) with vector red.add instead of writing y — the caller then runs slb_conv_finalize.
+struct BnbArgs { const void* y; const float *mean, *istd, *gamma, *beta; int relu; };
+static int conv_igemm_impl(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
+                           int B, int H, int W, int Ca, int Nout, int flip, int w_cin, int w_cout, int block_n, int k_split,
+                           float* acc, uint32_t* tile_counters, const BnbArgs* bnb, cudaStream_t st);
+
 int slb_conv3x3_igemm(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
                       int B, int H, int W, int Ca /*channels of A*/, int Nout /*output channels*/, int flip,
                       int w_cin /*Cin of the weight tensor*/, int w_cout, int block_n, int k_split, float* acc,
                       uint32_t* tile_counters, cudaStream_t st) {
+  return conv_igemm_impl(x, w, y, bias, col_sum, col_sumsq, B, H, W, Ca, Nout, flip, w_cin, w_cout, block_n, k_split, acc,
+                         tile_counters, nullptr, st);
+}
+
+// dgrad whose epilogue also reduces the BatchNorm backward sums of the upstream block: dbeta / dgamma (zeroed by the
+// caller) receive sum m*dX and sum m*dX*xhat; needs k_split == 1 or in-kernel finalisation (tile_counters).
+int slb_conv3x3_dgrad_bnstats(const void* dy, const void* w, void* dx, int B, int H, int W, int Ca, int Nout, int w_cin,
+                              int w_cout, int block_n, int k_split, float* acc, uint32_t* tile_counters,
+                              const void* up_y, const float* up_mean, const float* up_istd, const float* up_gamma,
+                              const float* up_beta, int up_relu, float* dbeta, float* dgamma, cudaStream_t st) {
+  if (k_split > 1 && tile_counters == nullptr) return -18;
+  BnbArgs b = {up_y, up_mean, up_istd, up_gamma, up_beta, up_relu};
+  return conv_igemm_impl(dy, w, dx, nullptr, dbeta, dgamma, B, H, W, Ca, Nout, 1, w_cin, w_cout, block_n, k_split, acc,
+                         tile_counters, &b, st);
+}
+
+}  // extern "C"
+
+static int conv_igemm_impl(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
+                           int B, int H, int W, int Ca, int Nout, int flip, int w_cin, int w_cout, int block_n, int k_split,
+                           float* acc, uint32_t* tile_counters, const BnbArgs* bnb, cudaStream_t st) {
   if (Ca % 64 != 0 || Nout % 64 != 0) return -10;
   const int M = B * H * W;
   if (128 % W != 0 && W % 128 != 0) return -11;
@@ -591,9 +657,15 @@ int slb_conv3x3_igemm(const void* x, const void* w, void* y, const float* bias, 
     p.bias = bias; p.col_sum = col_sum; p.col_sumsq = col_sumsq;
   }
   p.C = Ca; p.tw = tw; p.th = th; p.tb = tb; p.H = H; p.W = W; p.flip = flip; p.b_row_stride = w_cin;
+  if (bnb != nullptr) {
+    p.bnb_y = reinterpret_cast<const __nv_bfloat16*>(bnb->y);
+    p.bnb_mean = bnb->mean; p.bnb_istd = bnb->istd; p.bnb_gamma = bnb->gamma; p.bnb_beta = bnb->beta; p.bnb_relu = bnb->relu;
+  }
   dim3 grid((M + 127) / 128, Nout / bn, k_split);
   return dispatch_bn<MODE_CONV>(bn, ta, tbm, p, grid, st);
 }
+
+extern "C" {
 
 // dw[Cout][3][3][Cin] (fp32, accumulated with red.add; caller zeroes) += sum_pixels dy (x) x
 int slb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int k_split,

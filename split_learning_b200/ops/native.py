@@ -141,13 +141,24 @@ def conv3x3_fwd(x, w_bf16, y, bias=None, col_sum=None, col_sumsq=None, acc=None,
         conv_finalize(acc, bias, y, col_sum, col_sumsq)
 
 
-def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None):
-    """dy [B,H,W,Cout] bf16, w [Cout,3,3,Cin] bf16 -> dx [B,H,W,Cin] bf16."""
+def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None, bn_stats=None):
+    """dy [B,H,W,Cout] bf16, w [Cout,3,3,Cin] bf16 -> dx [B,H,W,Cin] bf16.
+    ``bn_stats``: (y, mean, invstd, gamma, beta, relu, dgamma, dbeta) of the *upstream* ConvBlock (BN + ReLU, no pool)
+    whose output gradient is dx: the epilogue then also reduces that block's BatchNorm-backward sums."""
     B, H, W, Cout = dy.shape
     Cin = w_bf16.shape[3]
     bn, ks = tiling or conv_tiling(B * H * W, Cin, Cout, flip=1)
     if acc is None:
         ks = 1
+    if bn_stats is not None:
+        if ks > 1 and counters is None:
+            raise NativeError("conv3x3_dgrad(bn_stats=) needs in-kernel split-K finalisation (counters)")
+        uy, mean, istd, gamma, beta, relu, dgamma, dbeta = bn_stats
+        _check(lib().slb_conv3x3_dgrad_bnstats(_p(dy), _p(w_bf16), _p(dx), c_int(B), c_int(H), c_int(W), c_int(Cout), c_int(Cin),
+                                               c_int(Cin), c_int(Cout), c_int(bn), c_int(ks), _p(acc), _p(counters), _p(uy),
+                                               _p(mean), _p(istd), _p(gamma), _p(beta), c_int(int(relu)), _p(dbeta), _p(dgamma),
+                                               _stream()), "conv3x3_dgrad_bnstats")
+        return
     _check(lib().slb_conv3x3_igemm(_p(dy), _p(w_bf16), _p(dx), _p(None), _p(None), _p(None), c_int(B), c_int(H), c_int(W),
                                    c_int(Cout), c_int(Cin), c_int(1), c_int(Cin), c_int(Cout), c_int(bn), c_int(ks), _p(acc),
                                    _p(counters), _stream()), "conv3x3_dgrad")
@@ -261,9 +272,12 @@ def bn_relu_pool_fwd(y, col_sum, col_sumsq, gamma, beta, running_mean, running_v
 
 
 def bn_relu_pool_bwd(dout, y, gamma, beta, save_mean, save_invstd, dgamma, dbeta, dy, H, W, relu, pool, identity=False,
-                     grid_bar=None):
-    """``grid_bar`` (3+ zeroed int32 owned by the call site) selects the single-launch reduce->barrier->apply kernel."""
+                     grid_bar=None, reduced=False):
+    """``grid_bar`` (3+ zeroed int32 owned by the call site) selects the single-launch reduce->barrier->apply kernel.
+    ``reduced``: dgamma / dbeta were already produced by ``conv3x3_dgrad(..., bn_stats=)`` -> apply pass only."""
     P, C = y.shape[0] * y.shape[1] * y.shape[2], y.shape[3]
+    if reduced:
+        identity, grid_bar = 2, None
     _check(lib().slb_bn_relu_pool_bwd(_p(dout), _p(y), _p(gamma), _p(beta), _p(save_mean), _p(save_invstd), _p(dgamma),
                                       _p(dbeta), _p(dy), c_int(P), c_int(C), c_int(H), c_int(W), c_int(int(relu)),
                                       c_int(int(pool)), c_int(int(identity)), _p(grid_bar), _stream()), "bn_relu_pool_bwd",

@@ -181,6 +181,8 @@ class B200Executor(StageExecutor):
         # single-launch BN backward (reduce -> grid barrier -> apply): measured SLOWER than two PDL-chained launches
         # (L pass 825 us vs 776 us) — a software grid barrier costs more than a kernel boundary here.  Off by default.
         self.fused_bn_bwd = os.environ.get("SLB200_FUSED_BN_BWD", "0") != "0"
+        # BatchNorm-backward reduction of block k-1 folded into the dgrad epilogue of block k (one launch less per pair)
+        self.fused_bn_stats = os.environ.get("SLB200_FUSED_BNSTATS", "1") != "0" and not self.fused_bn_bwd
         self.lr = float(learning.get("learning-rate", 0.01))
         self.mu = float(learning.get("momentum", 0.0))
         self.seed = seed
@@ -598,6 +600,7 @@ class _Plan:
                 fn()
             forked = True
 
+        bn_reduced = set()          # blocks whose dgamma / dbeta were produced by the downstream dgrad epilogue
         for bi in range(len(ex.blocks) - 1, -1, -1):
             b, a = ex.blocks[bi], self.act[bi]
             need_dx = not (bi == 0 and ex.is_first)
@@ -639,7 +642,7 @@ class _Plan:
                     N.bn_relu_pool_bwd(g, y, ex.view(ex.P, f"layer{b.bn}.weight"), ex.view(ex.P, f"layer{b.bn}.bias"),
                                        a["save_mean"], a["save_invstd"], ex.view(ex.G, f"layer{b.bn}.weight"),
                                        ex.view(ex.G, f"layer{b.bn}.bias"), dy, b.H, b.W, b.relu, b.pool,
-                                       grid_bar=a["bwd_bar"] if ex.fused_bn_bwd else None)
+                                       grid_bar=a["bwd_bar"] if ex.fused_bn_bwd else None, reduced=bi in bn_reduced)
                 else:
                     N.bn_relu_pool_bwd(g, y, None, None, a["save_mean"], a["save_invstd"], None, None, dy, b.H, b.W,
                                        b.relu, b.pool, identity=True)
@@ -655,7 +658,17 @@ class _Plan:
                         if need_dx:
                             dx = a["dx"] if not (bi == 0 and grad_out_override is not None) else grad_out_override
                             dacc = self.s(bi, "dacc") if (bi, "dacc") in self.soff else None
-                            N.conv3x3_dgrad(dy, ex.view(ex.PB, f"layer{b.conv}.weight"), dx, acc=dacc, counters=self.tile_counters)
+                            stats = None
+                            up = ex.blocks[bi - 1] if bi > 0 else None
+                            if (ex.fused_bn_stats and isinstance(up, ConvBlock) and up.conv is not None and up.bn is not None
+                                    and not up.pool and dx is a["dx"]):
+                                ua = self.act[bi - 1]
+                                stats = (ua["y_eff"], ua["save_mean"], ua["save_invstd"], ex.view(ex.P, f"layer{up.bn}.weight"),
+                                         ex.view(ex.P, f"layer{up.bn}.bias"), up.relu, ex.view(ex.G, f"layer{up.bn}.weight"),
+                                         ex.view(ex.G, f"layer{up.bn}.bias"))
+                                bn_reduced.add(bi - 1)
+                            N.conv3x3_dgrad(dy, ex.view(ex.PB, f"layer{b.conv}.weight"), dx, acc=dacc, counters=self.tile_counters,
+                                            bn_stats=stats)
                             g = dx
                 else:
                     g = dy

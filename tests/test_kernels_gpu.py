@@ -12,7 +12,7 @@ def selftest():
     return selftest
 
 
-@pytest.mark.parametrize("name", ["conv_fwd", "conv_dgrad", "conv_wgrad", "linear_all", "bn_fwd_bwd", "conv1_direct",
+@pytest.mark.parametrize("name", ["conv_fwd", "conv_dgrad", "conv_dgrad_bn_stats", "conv_wgrad", "linear_all", "bn_fwd_bwd", "conv1_direct",
                                   "ce_and_linear_epilogues", "optimizers_and_fedavg", "flags_and_peer"])
 def test_kernel(selftest, name):
     err, tol = selftest.CHECKS[name]()
