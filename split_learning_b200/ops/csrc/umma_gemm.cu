@@ -57,6 +57,8 @@ struct GemmParams {
   const float* bnb_gamma;
   const float* bnb_beta;
   int bnb_relu;
+  int bnb_pool;                   // 1: the upstream block ends in MaxPool2 — dX lives on the pooled grid (H x W here),
+                                  //    bnb_y on the 2H x 2W grid; the gradient goes to the window's (first) maximum
   // transformer epilogue (EPI_BF16, MODE_GEMM): out = act(acc + bias + residual); aux_out keeps the pre-activation
   int act;                        // 0 none, 1 ReLU, 2 GELU (erf), 3 tanh
   __nv_bfloat16* aux_out;         // [M][ldo] or nullptr
@@ -115,26 +117,66 @@ __device__ __forceinline__ void stat_terms(const GemmParams& p, int row, bool ro
     for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
     return;
   }
-  const uint4* y4 = reinterpret_cast<const uint4*>(p.bnb_y + static_cast<long long>(row) * p.N + col0);
+  if (!p.bnb_pool) {
+    const uint4* y4 = reinterpret_cast<const uint4*>(p.bnb_y + static_cast<long long>(row) * p.N + col0);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint4 u = __ldg(y4 + q);
-    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    for (int q = 0; q < 4; ++q) {
+      const uint4 u = __ldg(y4 + q);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 yy = __bfloat1622float2(h2[e]);
+      for (int e = 0; e < 4; ++e) {
+        const float2 yy = __bfloat1622float2(h2[e]);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int j = 8 * q + 2 * e + t, c = col0 + j;
-        const float y = t ? yy.y : yy.x;
-        const float mean = __ldg(p.bnb_mean + c), istd = __ldg(p.bnb_istd + c);
-        const float sc = __ldg(p.bnb_gamma + c) * istd, sh = __ldg(p.bnb_beta + c) - mean * sc;
-        const float r = __bfloat162float(__float2bfloat16(f[j]));
-        const float dz = (p.bnb_relu && fmaf(y, sc, sh) <= 0.f) ? 0.f : r;          // same test as bn_dz()
-        s1[j] = dz;
-        s2[j] = dz * (y - mean) * istd;
+        for (int t = 0; t < 2; ++t) {
+          const int j = 8 * q + 2 * e + t, c = col0 + j;
+          const float y = t ? yy.y : yy.x;
+          const float mean = __ldg(p.bnb_mean + c), istd = __ldg(p.bnb_istd + c);
+          const float sc = __ldg(p.bnb_gamma + c) * istd, sh = __ldg(p.bnb_beta + c) - mean * sc;
+          const float r = __bfloat162float(__float2bfloat16(f[j]));
+          const float dz = (p.bnb_relu && fmaf(y, sc, sh) <= 0.f) ? 0.f : r;          // same test as bn_dz()
+          s1[j] = dz;
+          s2[j] = dz * (y - mean) * istd;
+        }
       }
     }
+    return;
+  }
+  // pooled upstream block: row = (b, oh, ow) on the H x W grid of this dgrad; window = 2x2 pixels of the 2H x 2W grid
+  const int ow = row % p.W, t0 = row / p.W, oh = t0 % p.H, bb = t0 / p.H;
+  const long long base = (static_cast<long long>(bb) * (2 * p.H) + 2 * oh) * (2 * p.W) + 2 * ow;
+  float best[32], ybest[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { best[j] = -INFINITY; ybest[j] = 0.f; }
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    const long long ip = base + (q >> 1) * (2 * p.W) + (q & 1);
+    const uint4* y4 = reinterpret_cast<const uint4*>(p.bnb_y + ip * p.N + col0);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const uint4 u = __ldg(y4 + v);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 yy = __bfloat1622float2(h2[e]);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int j = 8 * v + 2 * e + t, c = col0 + j;
+          const float y = t ? yy.y : yy.x;
+          const float istd = __ldg(p.bnb_istd + c), sc = __ldg(p.bnb_gamma + c) * istd;
+          float z = fmaf(y, sc, __ldg(p.bnb_beta + c) - __ldg(p.bnb_mean + c) * sc);
+          if (p.bnb_relu) z = fmaxf(z, 0.f);
+          if (z > best[j]) { best[j] = z; ybest[j] = y; }                            // first maximum wins, like bn_dz()
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = col0 + j;
+    const float r = __bfloat162float(__float2bfloat16(f[j]));
+    const float dz = (p.bnb_relu && best[j] <= 0.f) ? 0.f : r;
+    s1[j] = dz;
+    s2[j] = dz * (ybest[j] - __ldg(p.bnb_mean + c)) * __ldg(p.bnb_istd + c);
   }
 }
 
@@ -590,7 +632,7 @@ int slb_preload_gemm() {
 // x := dY [B,H,W,Cout_w], w as stored, out = dX[B,H,W,Cin_w]  (then Cin here means channels of A = Cout_w).
 // block_n in {64,128,256} (0 = auto); k_split > 1 accumulates fp32 partial sums into `acc` ([M][Nout], zeroed by the
 // caller) with vector red.add instead of writing y — the caller then runs slb_conv_finalize.
-struct BnbArgs { const void* y; const float *mean, *istd, *gamma, *beta; int relu; };
+struct BnbArgs { const void* y; const float *mean, *istd, *gamma, *beta; int relu, pool; };
 static int conv_igemm_impl(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
                            int B, int H, int W, int Ca, int Nout, int flip, int w_cin, int w_cout, int block_n, int k_split,
                            float* acc, uint32_t* tile_counters, const BnbArgs* bnb, cudaStream_t st);
@@ -608,9 +650,9 @@ int slb_conv3x3_igemm(const void* x, const void* w, void* y, const float* bias, 
 int slb_conv3x3_dgrad_bnstats(const void* dy, const void* w, void* dx, int B, int H, int W, int Ca, int Nout, int w_cin,
                               int w_cout, int block_n, int k_split, float* acc, uint32_t* tile_counters,
                               const void* up_y, const float* up_mean, const float* up_istd, const float* up_gamma,
-                              const float* up_beta, int up_relu, float* dbeta, float* dgamma, cudaStream_t st) {
+                              const float* up_beta, int up_relu, int up_pool, float* dbeta, float* dgamma, cudaStream_t st) {
   if (k_split > 1 && tile_counters == nullptr) return -18;
-  BnbArgs b = {up_y, up_mean, up_istd, up_gamma, up_beta, up_relu};
+  BnbArgs b = {up_y, up_mean, up_istd, up_gamma, up_beta, up_relu, up_pool};
   return conv_igemm_impl(dy, w, dx, nullptr, dbeta, dgamma, B, H, W, Ca, Nout, 1, w_cin, w_cout, block_n, k_split, acc,
                          tile_counters, &b, st);
 }
@@ -659,7 +701,7 @@ static int conv_igemm_impl(const void* x, const void* w, void* y, const float* b
   p.C = Ca; p.tw = tw; p.th = th; p.tb = tb; p.H = H; p.W = W; p.flip = flip; p.b_row_stride = w_cin;
   if (bnb != nullptr) {
     p.bnb_y = reinterpret_cast<const __nv_bfloat16*>(bnb->y);
-    p.bnb_mean = bnb->mean; p.bnb_istd = bnb->istd; p.bnb_gamma = bnb->gamma; p.bnb_beta = bnb->beta; p.bnb_relu = bnb->relu;
+    p.bnb_mean = bnb->mean; p.bnb_istd = bnb->istd; p.bnb_gamma = bnb->gamma; p.bnb_beta = bnb->beta; p.bnb_relu = bnb->relu; p.bnb_pool = bnb->pool;
   }
   dim3 grid((M + 127) / 128, Nout / bn, k_split);
   return dispatch_bn<MODE_CONV>(bn, ta, tbm, p, grid, st);

@@ -143,8 +143,8 @@ def conv3x3_fwd(x, w_bf16, y, bias=None, col_sum=None, col_sumsq=None, acc=None,
 
 def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None, bn_stats=None):
     """dy [B,H,W,Cout] bf16, w [Cout,3,3,Cin] bf16 -> dx [B,H,W,Cin] bf16.
-    ``bn_stats``: (y, mean, invstd, gamma, beta, relu, dgamma, dbeta) of the *upstream* ConvBlock (BN + ReLU, no pool)
-    whose output gradient is dx: the epilogue then also reduces that block's BatchNorm-backward sums."""
+    ``bn_stats``: (y, mean, invstd, gamma, beta, relu, pool, dgamma, dbeta) of the *upstream* ConvBlock (BN + ReLU
+    [+ MaxPool2]) whose output gradient is dx: the epilogue then also reduces that block's BatchNorm-backward sums."""
     B, H, W, Cout = dy.shape
     Cin = w_bf16.shape[3]
     bn, ks = tiling or conv_tiling(B * H * W, Cin, Cout, flip=1)
@@ -153,10 +153,10 @@ def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None, bn_stats
     if bn_stats is not None:
         if ks > 1 and counters is None:
             raise NativeError("conv3x3_dgrad(bn_stats=) needs in-kernel split-K finalisation (counters)")
-        uy, mean, istd, gamma, beta, relu, dgamma, dbeta = bn_stats
+        uy, mean, istd, gamma, beta, relu, pool, dgamma, dbeta = bn_stats
         _check(lib().slb_conv3x3_dgrad_bnstats(_p(dy), _p(w_bf16), _p(dx), c_int(B), c_int(H), c_int(W), c_int(Cout), c_int(Cin),
                                                c_int(Cin), c_int(Cout), c_int(bn), c_int(ks), _p(acc), _p(counters), _p(uy),
-                                               _p(mean), _p(istd), _p(gamma), _p(beta), c_int(int(relu)), _p(dbeta), _p(dgamma),
+                                               _p(mean), _p(istd), _p(gamma), _p(beta), c_int(int(relu)), c_int(int(pool)), _p(dbeta), _p(dgamma),
                                                _stream()), "conv3x3_dgrad_bnstats")
         return
     _check(lib().slb_conv3x3_igemm(_p(dy), _p(w_bf16), _p(dx), _p(None), _p(None), _p(None), c_int(B), c_int(H), c_int(W),

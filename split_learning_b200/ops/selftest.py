@@ -107,35 +107,39 @@ def conv_dgrad():
 
 @check
 def conv_dgrad_bn_stats():
-    """dgrad epilogue that also reduces the upstream block's BatchNorm-backward sums == the stand-alone reduce kernel."""
+    """dgrad epilogue that also reduces the upstream block's BatchNorm-backward sums == the stand-alone reduce kernel
+    (upstream block with and without MaxPool2)."""
     worst = 0.0
     for (B, H, W, Cin, Cout) in CONV_SHAPES:
-        x, w, _ = _conv_case(B, H, W, Cin, Cout)
-        dy = _bf(torch.randn(B, H, W, Cout, device="cuda"))
-        up_y = _bf(torch.randn(B, H, W, Cin, device="cuda") * 1.5 + 0.2)         # saved conv output of the upstream block
-        mean = up_y.float().mean((0, 1, 2))
-        istd = (up_y.float().var((0, 1, 2), unbiased=False) + 1e-5).rsqrt()
-        gamma = torch.rand(Cin, device="cuda") + 0.5
-        beta = torch.randn(Cin, device="cuda") * 0.3
-        bn_, ks_ = N.conv_tiling(B * H * W, Cin, Cout, flip=1)
-        acc = torch.zeros(B * H * W, Cin, device="cuda") if ks_ > 1 else None
-        ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)
-        dx = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.bfloat16)
-        dgamma, dbeta = torch.zeros(Cin, device="cuda"), torch.zeros(Cin, device="cuda")
-        N.conv3x3_dgrad(dy, w, dx, acc=acc, counters=ctr, bn_stats=(up_y, mean, istd, gamma, beta, True, dgamma, dbeta))
-        # oracle: plain dgrad + the two-kernel BN backward on its output
-        dx2 = torch.empty_like(dx)
-        acc2 = torch.zeros_like(acc) if acc is not None else None
-        N.conv3x3_dgrad(dy, w, dx2, acc=acc2, counters=ctr)
-        g2, b2 = torch.zeros(Cin, device="cuda"), torch.zeros(Cin, device="cuda")
-        dyy = torch.empty_like(up_y)
-        N.bn_relu_pool_bwd(dx2, up_y, gamma, beta, mean, istd, g2, b2, dyy, H, W, True, False)
-        dyy3 = torch.empty_like(up_y)
-        N.bn_relu_pool_bwd(dx, up_y, gamma, beta, mean, istd, dgamma, dbeta, dyy3, H, W, True, False, reduced=True)
-        torch.cuda.synchronize()
-        e = max(_rel(dx, dx2), _rel(dgamma, g2), _rel(dbeta, b2), _rel(dyy3, dyy))
-        print(f"  conv_dgrad_bn_stats {B}x{H}x{W} {Cin}<-{Cout}: {e:.2e}")
-        worst = max(worst, e)
+        for pool in (False, True):
+            x, w, _ = _conv_case(B, H, W, Cin, Cout)
+            dy = _bf(torch.randn(B, H, W, Cout, device="cuda"))
+            uh, uw = (2 * H, 2 * W) if pool else (H, W)
+            up_y = _bf(torch.randn(B, uh, uw, Cin, device="cuda") * 1.5 + 0.2)       # saved conv output of the upstream block
+            mean = up_y.float().mean((0, 1, 2))
+            istd = (up_y.float().var((0, 1, 2), unbiased=False) + 1e-5).rsqrt()
+            gamma = torch.rand(Cin, device="cuda") + 0.5
+            beta = torch.randn(Cin, device="cuda") * 0.3
+            bn_, ks_ = N.conv_tiling(B * H * W, Cin, Cout, flip=1)
+            acc = torch.zeros(B * H * W, Cin, device="cuda") if ks_ > 1 else None
+            ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)
+            dx = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.bfloat16)
+            dgamma, dbeta = torch.zeros(Cin, device="cuda"), torch.zeros(Cin, device="cuda")
+            N.conv3x3_dgrad(dy, w, dx, acc=acc, counters=ctr,
+                            bn_stats=(up_y, mean, istd, gamma, beta, True, pool, dgamma, dbeta))
+            # oracle: plain dgrad + the two-kernel BN backward on its output
+            dx2 = torch.empty_like(dx)
+            acc2 = torch.zeros_like(acc) if acc is not None else None
+            N.conv3x3_dgrad(dy, w, dx2, acc=acc2, counters=ctr)
+            g2, b2 = torch.zeros(Cin, device="cuda"), torch.zeros(Cin, device="cuda")
+            dyy = torch.empty_like(up_y)
+            N.bn_relu_pool_bwd(dx2, up_y, gamma, beta, mean, istd, g2, b2, dyy, uh, uw, True, pool)
+            dyy3 = torch.empty_like(up_y)
+            N.bn_relu_pool_bwd(dx, up_y, gamma, beta, mean, istd, dgamma, dbeta, dyy3, uh, uw, True, pool, reduced=True)
+            torch.cuda.synchronize()
+            e = max(_rel(dx, dx2), _rel(dgamma, g2), _rel(dbeta, b2), _rel(dyy3, dyy))
+            print(f"  conv_dgrad_bn_stats {B}x{H}x{W} {Cin}<-{Cout} pool={int(pool)}: {e:.2e}")
+            worst = max(worst, e)
     return worst, 2e-3
 
 

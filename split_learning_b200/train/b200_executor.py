@@ -182,7 +182,10 @@ class B200Executor(StageExecutor):
         # (L pass 825 us vs 776 us) — a software grid barrier costs more than a kernel boundary here.  Off by default.
         self.fused_bn_bwd = os.environ.get("SLB200_FUSED_BN_BWD", "0") != "0"
         # BatchNorm-backward reduction of block k-1 folded into the dgrad epilogue of block k (one launch less per pair)
-        self.fused_bn_stats = os.environ.get("SLB200_FUSED_BNSTATS", "1") != "0" and not self.fused_bn_bwd
+        # SLB200_FUSED_BNSTATS: 0 off, 1 only upstream blocks without max-pool (default), 2 all.  Same-box A/B/C (N = 1,
+        # 400 steps, twice each): 35.57 k / 36.31 k / 35.64 k images/s — the pooled variant's 4x window loads in the
+        # epilogue cost more than the launch they save.
+        self.fused_bn_stats = 0 if self.fused_bn_bwd else int(os.environ.get("SLB200_FUSED_BNSTATS", "1"))
         self.lr = float(learning.get("learning-rate", 0.01))
         self.mu = float(learning.get("momentum", 0.0))
         self.seed = seed
@@ -661,10 +664,10 @@ class _Plan:
                             stats = None
                             up = ex.blocks[bi - 1] if bi > 0 else None
                             if (ex.fused_bn_stats and isinstance(up, ConvBlock) and up.conv is not None and up.bn is not None
-                                    and not up.pool and dx is a["dx"]):
+                                    and (ex.fused_bn_stats >= 2 or not up.pool) and dx is a["dx"]):
                                 ua = self.act[bi - 1]
                                 stats = (ua["y_eff"], ua["save_mean"], ua["save_invstd"], ex.view(ex.P, f"layer{up.bn}.weight"),
-                                         ex.view(ex.P, f"layer{up.bn}.bias"), up.relu, ex.view(ex.G, f"layer{up.bn}.weight"),
+                                         ex.view(ex.P, f"layer{up.bn}.bias"), up.relu, up.pool, ex.view(ex.G, f"layer{up.bn}.weight"),
                                          ex.view(ex.G, f"layer{up.bn}.bias"))
                                 bn_reduced.add(bi - 1)
                             N.conv3x3_dgrad(dy, ex.view(ex.PB, f"layer{b.conv}.weight"), dx, acc=dacc, counters=self.tile_counters,
