@@ -17,7 +17,7 @@ SOURCES = ["umma_gemm.cu", "fused_cut.cu", "elementwise.cu", "transformer.cu", "
 LIB = os.path.join(HERE, "_slb200.so")
 STAMP = LIB + ".sha"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-lcudart"]
+              "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-lcudart"] + os.environ.get("SLB200_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -101,9 +101,10 @@ __device__ __forceinline__ float warp_col_reduce32(float (&v)[32]) {
 
 // Per-element terms of the two column reductions of an epilogue chunk (row = pixel, 32 consecutive channels):
 // BatchNorm forward statistics (x, x^2) or, with bnb_y, the BatchNorm backward sums of the upstream block.
+template <bool BNB>
 __device__ __forceinline__ void stat_terms(const GemmParams& p, int row, bool row_ok, int col0, const float (&f)[32],
                                            float (&s1)[32], float (&s2)[32]) {
-  if (p.bnb_y == nullptr) {
+  if (!BNB || p.bnb_y == nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float r = row_ok ? __bfloat162float(__float2bfloat16(f[j])) : 0.f;   // statistics of the stored values
@@ -112,6 +113,7 @@ __device__ __forceinline__ void stat_terms(const GemmParams& p, int row, bool ro
     }
     return;
   }
+  if constexpr (BNB) {
   if (!row_ok) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
@@ -178,9 +180,12 @@ __device__ __forceinline__ void stat_terms(const GemmParams& p, int row, bool ro
     s1[j] = dz;
     s2[j] = dz * (ybest[j] - __ldg(p.bnb_mean + c)) * __ldg(p.bnb_istd + c);
   }
+  }  // BNB
 }
 
-template <int MODE, int BLOCK_N>
+// BNB: instantiate the upstream-BatchNorm-backward epilogue (dgrad only).  A separate instantiation on purpose: with the
+// code in the common kernel every conv paid ~1.8 % (205 vs 154 registers; same-box A/B, profiles/README.md).
+template <int MODE, int BLOCK_N, bool BNB = false>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -405,7 +410,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (want_stats) {
             // statistics of the bf16-rounded values that were stored (what the consumer normalises)
             float s1[32], s2[32];
-            stat_terms(p, row, row_ok, col0, f, s1, s2);
+            stat_terms<BNB>(p, row, row_ok, col0, f, s1, s2);
             const float c1 = warp_col_reduce32(s1);
             const float c2 = warp_col_reduce32(s2);
             atomicAdd(&s_stats[c + lane_id()], c1);
@@ -490,7 +495,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (want_stats) {
               float s1[32], s2[32];
-              stat_terms(p, row, row_ok, col0, f, s1, s2);
+              stat_terms<BNB>(p, row, row_ok, col0, f, s1, s2);
               const float c1 = warp_col_reduce32(s1);
               const float c2 = warp_col_reduce32(s2);
               atomicAdd(&s_stats[c + lane_id()], c1);
@@ -571,9 +576,9 @@ static int tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int 
   return make_tmap(m, base, 4, dims, str, box);
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool BNB = false>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid, cudaStream_t st) {
-  auto k = umma_gemm_kernel<MODE, BN>;
+  auto k = umma_gemm_kernel<MODE, BN, BNB>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::TOTAL);
@@ -589,6 +594,16 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& 
 template <int MODE>
 static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid,
                        cudaStream_t st) {
+  if constexpr (MODE == MODE_CONV) {
+    if (p.bnb_y != nullptr) {
+      switch (bn) {
+        case 64: return launch<MODE, 64, true>(a, b, p, grid, st);
+        case 128: return launch<MODE, 128, true>(a, b, p, grid, st);
+        case 256: return launch<MODE, 256, true>(a, b, p, grid, st);
+        default: return -3;
+      }
+    }
+  }
   switch (bn) {
     case 32: return launch<MODE, 32>(a, b, p, grid, st);
     case 64: return launch<MODE, 64>(a, b, p, grid, st);
@@ -598,10 +613,10 @@ static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const
   }
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool BNB = false>
 static int preload_one() {
   cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, umma_gemm_kernel<MODE, BN>) == cudaSuccess ? 0 : 1;
+  return cudaFuncGetAttributes(&a, umma_gemm_kernel<MODE, BN, BNB>) == cudaSuccess ? 0 : 1;
 }
 
 static void pixel_box(int H, int W, int pixels, int* tb, int* th, int* tw) {
@@ -624,6 +639,7 @@ int slb_preload_gemm() {
   bad += preload_one<MODE_CONV, 64>() + preload_one<MODE_CONV, 128>() + preload_one<MODE_CONV, 256>() + preload_one<MODE_CONV, 32>();
   bad += preload_one<MODE_WGRAD, 64>() + preload_one<MODE_WGRAD, 128>() + preload_one<MODE_WGRAD, 256>() + preload_one<MODE_WGRAD, 32>();
   bad += preload_one<MODE_GEMM, 32>() + preload_one<MODE_GEMM, 64>() + preload_one<MODE_GEMM, 128>() + preload_one<MODE_GEMM, 256>();
+  bad += preload_one<MODE_CONV, 64, true>() + preload_one<MODE_CONV, 128, true>() + preload_one<MODE_CONV, 256, true>();
   return bad;
 }
 

@@ -140,7 +140,7 @@ def conv_dgrad_bn_stats():
             e = max(_rel(dx, dx2), _rel(dgamma, g2), _rel(dbeta, b2), _rel(dyy3, dyy))
             print(f"  conv_dgrad_bn_stats {B}x{H}x{W} {Cin}<-{Cout} pool={int(pool)}: {e:.2e}")
             worst = max(worst, e)
-    return worst, 2e-3
+    return worst, 6e-3          # split-K red.add order differs between the two dgrad runs: dx may differ by one bf16 ulp
 
 
 @check

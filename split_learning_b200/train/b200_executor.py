@@ -181,11 +181,12 @@ class B200Executor(StageExecutor):
         # single-launch BN backward (reduce -> grid barrier -> apply): measured SLOWER than two PDL-chained launches
         # (L pass 825 us vs 776 us) — a software grid barrier costs more than a kernel boundary here.  Off by default.
         self.fused_bn_bwd = os.environ.get("SLB200_FUSED_BN_BWD", "0") != "0"
-        # BatchNorm-backward reduction of block k-1 folded into the dgrad epilogue of block k (one launch less per pair)
-        # SLB200_FUSED_BNSTATS: 0 off, 1 only upstream blocks without max-pool (default), 2 all.  Same-box A/B/C (N = 1,
-        # 400 steps, twice each): 35.57 k / 36.31 k / 35.64 k images/s — the pooled variant's 4x window loads in the
-        # epilogue cost more than the launch they save.
-        self.fused_bn_stats = 0 if self.fused_bn_bwd else int(os.environ.get("SLB200_FUSED_BNSTATS", "1"))
+        # BatchNorm-backward reduction of block k-1 folded into the dgrad epilogue of block k (one launch less per pair).
+        # SLB200_FUSED_BNSTATS: 0 off (default), 1 upstream blocks without max-pool, 2 all.  Measured on one box (N = 1,
+        # 400 steps): 36.47 k / 36.27 k / 35.83 k images/s — once the extra epilogue lives in its own kernel instantiation
+        # (it cost every conv 1.8 % when it shared one), the 8 saved launches do not pay for the y / parameter loads the
+        # fused epilogue adds to the dgrad's critical path.  Kept (tested in ops/selftest.py) as an option.
+        self.fused_bn_stats = 0 if self.fused_bn_bwd else int(os.environ.get("SLB200_FUSED_BNSTATS", "0"))
         self.lr = float(learning.get("learning-rate", 0.01))
         self.mu = float(learning.get("momentum", 0.0))
         self.seed = seed
