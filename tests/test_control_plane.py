@@ -102,3 +102,26 @@ def test_broker_comm_allgather_and_barrier():
     assert set(out) == set(members)
     for me, (r1, r2, idx) in out.items():
         assert [d["me"] for d in r1] == ["a", "b", "c"] and r2 == ["A", "B", "C"] and sorted(members)[idx] == me
+
+
+def test_device_plane_lane_mapping():
+    """Lane i (first-stage client i) is served at stage s by member i % n_s; non-dividing topologies are refused
+    (-> host data plane)."""
+    import pytest
+    from split_learning_b200.parallel.device_client import DeviceRpcClient
+
+    def lanes(counts, layer, member):
+        members = {s + 1: [(f"c{s + 1}_{j}", 0) for j in range(n)] for s, n in enumerate(counts)}
+        c = DeviceRpcClient.__new__(DeviceRpcClient)
+        c.client_id, c.layer_id, c.num_layers = f"c{layer}_{member}", layer, len(counts)
+        return c._lanes({"peers": {"members": members}})
+
+    assert lanes([4, 2, 1], 1, 3) == [(3, None, "c2_1")]
+    assert lanes([4, 2, 1], 2, 1) == [(1, "c1_1", "c3_0"), (3, "c1_3", "c3_0")]
+    assert [l for l, _, _ in lanes([4, 2, 1], 3, 0)] == [0, 1, 2, 3]
+    assert lanes([4, 2, 1], 3, 0)[2] == (2, "c2_0", None)
+    assert lanes([2, 2], 2, 1) == [(1, "c1_1", None)]
+    with pytest.raises(RuntimeError):
+        lanes([3, 2], 1, 0)
+    with pytest.raises(RuntimeError):
+        lanes([1, 2], 2, 0)
