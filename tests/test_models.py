@@ -94,3 +94,29 @@ def test_lora_roundtrip():
     merge_lora(m)
     assert list(m.state_dict()) == keys
     assert torch.allclose(m(x), y, atol=1e-5)
+
+
+def test_native_rebinding_keeps_module_tree():
+    """``nativize`` only re-binds ``forward`` attributes (state-dict keys, LoRA wrapping / merging unaffected);
+    ``cnn_native._program`` groups conv / BN / ReLU / pool runs of any cut correctly."""
+    from split_learning_b200.models.lora import LoraConfig, apply_lora, merge_lora
+    from split_learning_b200.train import cnn_native, token_native
+    m = BERT_AGNEWS(12, 15)
+    keys = list(m.state_dict())
+    apply_lora(m, LoraConfig(), keep_trainable=("layer15",))
+    token_native.nativize(m)
+    assert any("lora_A" in k for k in m.state_dict())
+    merge_lora(m)
+    assert list(m.state_dict()) == keys
+    token_native.denativize(m)
+    assert m(torch.randn(1, 128, 768)).shape == (1, 4)               # stock forward restored (CPU)
+    k = KWT_SPEECHCOMMANDS(0, 17)
+    token_native.nativize(k)
+    assert "forward" in k.layer4.__dict__ and "forward" in k.layer16.__dict__ and list(k.state_dict()) == list(
+        KWT_SPEECHCOMMANDS(0, 17).state_dict())
+    assert cnn_native.supports(MobileNetv1_CIFAR10(0, 3)) and not cnn_native.supports(k)
+    prog = cnn_native._program(MobileNetv1_CIFAR10(0, 84))
+    assert prog[0] == ("stem", 1) and prog[1] == ("bn", 2, True, False) and prog[-3:] == [("bn", 80, True, True), ("flatten",),
+                                                                                           ("linear", 84)]
+    assert sum(1 for op in prog if op[0] == "conv3") == 13 and sum(1 for op in prog if op[0] == "conv1") == 13
+    assert cnn_native._program(MobileNetv1_CIFAR10(2, 5)) == [("relu",), ("conv3", 4), ("bn", 5, False, False)]
