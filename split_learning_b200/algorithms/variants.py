@@ -495,7 +495,8 @@ class TwoLSClient(RpcClient):
 
     def make_dataplane(self, msg: dict):
         self.idx = msg.get("idx", 0)
-        return HostDataPlane(self.channel, self.client_id, self.layer_id, self.cluster, QueueGrammar("2ls"), device=self.device)
+        return HostDataPlane(self.channel, self.client_id, self.layer_id, self.cluster, QueueGrammar("2ls"), device=self.device,
+                             wire=str(self.opts.get("wire", "host")))
 
     def run_stage(self):
         t = self.trainer

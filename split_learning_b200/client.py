@@ -123,7 +123,8 @@ class RpcClient:
 
     def make_dataplane(self, msg: dict):
         grammar = QueueGrammar(self.algorithm())
-        return HostDataPlane(self.channel, self.client_id, self.layer_id, self.cluster, grammar, device=self.device)
+        return HostDataPlane(self.channel, self.client_id, self.layer_id, self.cluster, grammar, device=self.device,
+                             wire=str(self.opts.get("wire", "host")))
 
     def run_stage(self):
         t = self.trainer
