@@ -88,7 +88,7 @@ class HostDataPlane:
         # consumer is another process on this box: CUDA IPC handle (torch's reducer keeps the block alive until the
         # consumer has released it); producer-side kernels must be complete before the handle is usable
         from multiprocessing.reduction import ForkingPickler
-        import torch.multiprocessing  # noqa: F401  (registers the CUDA tensor reducers)
+        import torch.multiprocessing as _tmp  # noqa: F401  (registers the CUDA tensor reducers)
         torch.cuda.current_stream(t.device).synchronize()
         buf = io.BytesIO()
         ForkingPickler(buf, pickle.HIGHEST_PROTOCOL).dump(t.contiguous())
