@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """``python server.py`` — coordinator entry point (reference server.py:1-31).
 
-Reads ``config.yaml`` from the CWD, starts the in-box broker on ``b200.port`` (this replaces
-the external RabbitMQ server), purges stale queues, installs the SIGINT handler and serves.
+Reads ``config.yaml`` from the CWD, starts the in-box broker on ``b200.port`` (the native ``slb_broker`` daemon; this
+replaces the external RabbitMQ server), purges stale queues, installs the SIGINT handler and serves.
 """
 import argparse
 import signal
@@ -10,7 +10,7 @@ import sys
 
 from split_learning_b200.algorithms import server_class
 from split_learning_b200.config import load_config
-from split_learning_b200.transport import TcpBroker
+from split_learning_b200.transport import make_broker
 from split_learning_b200.transport.broker import delete_old_queues
 
 parser = argparse.ArgumentParser(description="Split learning framework with controller.")
@@ -23,7 +23,8 @@ def main():
     cfg = load_config(args.config)
     if args.algorithm:
         cfg.b200["algorithm"] = args.algorithm
-    broker = TcpBroker(cfg.raw.get("rabbit", {}).get("address", "127.0.0.1"), int(cfg.b200.get("port", 29777)))
+    broker = make_broker(cfg.raw.get("rabbit", {}).get("address", "127.0.0.1"), int(cfg.b200.get("port", 29777)),
+                         str(cfg.b200.get("broker", "native")))
     channel = broker.channel()
 
     def on_sigint(sig, frame):

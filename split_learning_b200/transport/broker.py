@@ -1,9 +1,12 @@
 from __future__ import annotations
 
 import collections
+import os
 import pickle
+import shutil
 import socket
 import struct
+import subprocess
 import threading
 import time
 from typing import Deque, Dict, Optional
@@ -82,10 +85,14 @@ class InProcBroker(Channel):
 
 
 # ---------------------------------------------------------------------------
-# TCP broker: frame = u32 length | pickle((op, queue, arg))
+# TCP brokers.  One binary wire protocol (little endian), spoken by the native daemon
+# (transport/csrc/slb_broker.cpp) and by the Python fallback below:
+#   request : u8 op | u32 queue_len | u64 arg_len | queue bytes | arg bytes
+#   reply   : u8 status | u64 len | payload            (no reply for PUB)
 # ---------------------------------------------------------------------------
-def _send_frame(sock: socket.socket, payload: bytes) -> None:
-    sock.sendall(struct.pack("<Q", len(payload)) + payload)
+OP_PUB, OP_GET, OP_DECLARE, OP_DELETE, OP_PURGE, OP_DEPTH, OP_LIST, OP_PING, OP_SHUTDOWN = range(1, 10)
+_REQ = struct.Struct("<BIQ")
+_REP = struct.Struct("<BQ")
 
 
 def _recv_exact(sock: socket.socket, n: int) -> bytes:
@@ -100,13 +107,22 @@ def _recv_exact(sock: socket.socket, n: int) -> bytes:
     return bytes(buf)
 
 
-def _recv_frame(sock: socket.socket) -> bytes:
-    (n,) = struct.unpack("<Q", _recv_exact(sock, 8))
-    return _recv_exact(sock, n)
+def _send_request(sock: socket.socket, op: int, queue: str, arg: bytes = b"") -> None:
+    q = queue.encode()
+    sock.sendall(_REQ.pack(op, len(q), len(arg)) + q)
+    if arg:
+        sock.sendall(arg)
+
+
+def _recv_reply(sock: socket.socket):
+    status, n = _REP.unpack(_recv_exact(sock, _REP.size))
+    return status, (_recv_exact(sock, n) if n else b"")
 
 
 class TcpBroker:
-    """Broker thread(s) serving an InProcBroker over loopback TCP."""
+    """Python fallback broker: thread(s) serving an InProcBroker over loopback TCP (same protocol as slb_broker)."""
+
+    kind = "python"
 
     def __init__(self, host: str = "127.0.0.1", port: int = 29777):
         self.store = InProcBroker()
@@ -133,28 +149,41 @@ class TcpBroker:
 
     def _serve(self, conn: socket.socket):
         s = self.store
+
+        def reply(status: int, payload: bytes = b""):
+            conn.sendall(_REP.pack(status, len(payload)) + payload)
         try:
             while True:
-                op, queue, arg = pickle.loads(_recv_frame(conn))
-                if op == "pub":
-                    s.basic_publish(queue, arg)
-                    continue                      # fire-and-forget, like basic_publish
-                if op == "get":
-                    res = s.basic_get(queue, arg)
-                elif op == "declare":
-                    res = s.queue_declare(queue)
-                elif op == "delete":
-                    res = s.queue_delete(queue)
-                elif op == "purge":
-                    res = s.queue_purge(queue)
-                elif op == "depth":
-                    res = s.queue_depth(queue)
-                elif op == "list":
-                    res = s.list_queues()
+                op, qlen, alen = _REQ.unpack(_recv_exact(conn, _REQ.size))
+                queue = _recv_exact(conn, qlen).decode() if qlen else ""
+                arg = _recv_exact(conn, alen) if alen else b""
+                if op == OP_PUB:
+                    s.basic_publish(queue, arg)           # fire-and-forget, like basic_publish
+                elif op == OP_GET:
+                    body = s.basic_get(queue, struct.unpack("<d", arg)[0] if len(arg) == 8 else 0.0)
+                    reply(0 if body is None else 1, body or b"")
+                elif op == OP_DECLARE:
+                    s.queue_declare(queue)
+                    reply(1)
+                elif op == OP_DELETE:
+                    s.queue_delete(queue)
+                    reply(1)
+                elif op == OP_PURGE:
+                    s.queue_purge(queue)
+                    reply(1)
+                elif op == OP_DEPTH:
+                    reply(1, struct.pack("<Q", s.queue_depth(queue)))
+                elif op == OP_LIST:
+                    reply(1, "\n".join(s.list_queues()).encode())
+                elif op == OP_PING:
+                    reply(1)
+                elif op == OP_SHUTDOWN:
+                    reply(1)
+                    self.close()
+                    return
                 else:
-                    res = None
-                _send_frame(conn, pickle.dumps(res, protocol=pickle.HIGHEST_PROTOCOL))
-        except (ConnectionError, OSError, EOFError):
+                    return
+        except (ConnectionError, OSError, EOFError, struct.error):
             pass
         finally:
             conn.close()
@@ -188,38 +217,115 @@ class TcpChannel(Channel):
         self._sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
         self._lock = threading.Lock()
 
-    def _call(self, op, queue, arg=None, reply=True):
+    def _call(self, op: int, queue: str, arg: bytes = b"", reply: bool = True):
         with self._lock:
-            _send_frame(self._sock, pickle.dumps((op, queue, arg), protocol=pickle.HIGHEST_PROTOCOL))
+            _send_request(self._sock, op, queue, arg)
             if reply:
-                return pickle.loads(_recv_frame(self._sock))
+                return _recv_reply(self._sock)
 
     def queue_declare(self, queue, durable=False):
-        self._call("declare", queue)
+        self._call(OP_DECLARE, queue)
 
     def basic_publish(self, routing_key, body, exchange=""):
-        self._call("pub", routing_key, body, reply=False)
+        self._call(OP_PUB, routing_key, bytes(body), reply=False)
 
     def basic_get(self, queue, timeout=0.0):
-        return self._call("get", queue, timeout)
+        status, body = self._call(OP_GET, queue, struct.pack("<d", float(timeout)))
+        return body if status == 1 else None
 
     def queue_delete(self, queue):
-        self._call("delete", queue)
+        self._call(OP_DELETE, queue)
 
     def queue_purge(self, queue):
-        self._call("purge", queue)
+        self._call(OP_PURGE, queue)
 
     def queue_depth(self, queue):
-        return self._call("depth", queue)
+        return struct.unpack("<Q", self._call(OP_DEPTH, queue)[1])[0]
 
     def list_queues(self):
-        return self._call("list", "")
+        names = self._call(OP_LIST, "")[1].decode()
+        return names.split("\n") if names else []
+
+    def ping(self) -> bool:
+        return self._call(OP_PING, "")[0] == 1
+
+    def shutdown_broker(self) -> None:
+        try:
+            self._call(OP_SHUTDOWN, "")
+        except (ConnectionError, OSError, struct.error):
+            pass
 
     def close(self):
         try:
             self._sock.close()
         except OSError:
             pass
+
+
+# ---------------------------------------------------------------------------
+# Native broker daemon (C++): built in-tree with g++, started as a child process
+# ---------------------------------------------------------------------------
+_HERE = os.path.dirname(os.path.abspath(__file__))
+BROKER_SRC = os.path.join(_HERE, "csrc", "slb_broker.cpp")
+BROKER_BIN = os.path.join(_HERE, "slb_broker")
+
+
+def build_native_broker(force: bool = False) -> str:
+    """g++ -O2 the daemon into transport/slb_broker (about a second); returns the binary path."""
+    if not force and os.path.exists(BROKER_BIN) and os.path.getmtime(BROKER_BIN) >= os.path.getmtime(BROKER_SRC):
+        return BROKER_BIN
+    cxx = os.environ.get("CXX") or shutil.which("g++") or shutil.which("c++")
+    if not cxx:
+        raise RuntimeError("no C++ compiler for slb_broker")
+    res = subprocess.run([cxx, "-O2", "-std=c++17", "-pthread", "-o", BROKER_BIN, BROKER_SRC], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building slb_broker failed:\n" + res.stderr[-2000:])
+    return BROKER_BIN
+
+
+class NativeBroker:
+    """``slb_broker`` as a child process (dies with this process).  ``channel()`` is a TCP channel like any client's."""
+
+    kind = "native"
+
+    def __init__(self, host: str = "127.0.0.1", port: int = 29777):
+        exe = build_native_broker()
+        self._proc = subprocess.Popen([exe, "--host", host, "--port", str(port)], stdout=subprocess.PIPE, text=True)
+        line = self._proc.stdout.readline()
+        if not line.startswith("SLB_BROKER_READY"):
+            self._proc.kill()
+            raise RuntimeError(f"slb_broker did not start on {host}:{port} (port in use?)")
+        self.host, self.port = host, int(line.split()[1])
+        self._channels = []
+
+    def channel(self) -> TcpChannel:
+        ch = TcpChannel(self.host, self.port, retry_seconds=5.0)
+        self._channels.append(ch)
+        return ch
+
+    def close(self):
+        if self._proc.poll() is None:
+            try:
+                TcpChannel(self.host, self.port, retry_seconds=1.0).shutdown_broker()
+            except (ConnectionError, OSError):
+                pass
+            try:
+                self._proc.wait(2.0)
+            except subprocess.TimeoutExpired:
+                self._proc.kill()
+        for ch in self._channels:
+            ch.close()
+
+
+def make_broker(host: str = "127.0.0.1", port: int = 29777, kind: str = "native"):
+    """The box-local broker replacing RabbitMQ: the C++ daemon, or the Python thread broker when asked for / when no
+    compiler is available (both speak the same protocol, clients do not care)."""
+    if kind == "native":
+        try:
+            return NativeBroker(host, port)
+        except (RuntimeError, OSError) as e:
+            print(f"[broker] native daemon unavailable ({e}); using the Python broker", flush=True)
+    return TcpBroker(host, port)
 
 
 def connect(address: str = "127.0.0.1", port: int = 29777, retry_seconds: float = 60.0) -> TcpChannel:

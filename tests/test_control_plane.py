@@ -24,8 +24,11 @@ def test_inproc_broker_fifo_and_blocking_get():
     assert [b.get_obj("q") for _ in range(5)] == list(range(5))
 
 
-def test_tcp_broker_roundtrip_and_hygiene():
-    srv = TcpBroker(port=0)
+@pytest.mark.parametrize("kind", ["native", "python"])
+def test_tcp_broker_roundtrip_and_hygiene(kind):
+    """Both brokers — the C++ daemon (transport/csrc/slb_broker.cpp) and the Python fallback — behind one protocol."""
+    from split_learning_b200.transport import NativeBroker
+    srv = NativeBroker(port=0) if kind == "native" else TcpBroker(port=0)
     try:
         c1, c2 = TcpChannel(port=srv.port), TcpChannel(port=srv.port)
         payload = b"x" * (3 << 20)                         # multi-MB frames (a state-dict sized message)
@@ -37,6 +40,16 @@ def test_tcp_broker_roundtrip_and_hygiene():
         assert c2.queue_depth("keepme") == 1
         delete_old_queues(c2)                              # reply*/rpc_queue* deleted, everything else purged
         assert c2.queue_depth("keepme") == 0 and "reply_abc" not in c2.list_queues()
+        # blocking get: times out empty-handed, wakes up as soon as another connection publishes
+        t0 = time.monotonic()
+        assert c2.basic_get("later", 0.2) is None and 0.15 < time.monotonic() - t0 < 2.0
+        threading.Timer(0.1, lambda: c1.publish_obj("later", "hello")).start()
+        t0 = time.monotonic()
+        assert c2.get_obj("later", 5.0) == "hello" and time.monotonic() - t0 < 2.0
+        assert c1.ping()
+        own = srv.channel()                                # the server's own channel
+        own.publish_obj("fifo", 1), own.publish_obj("fifo", 2)
+        assert [c2.get_obj("fifo", 1.0), c2.get_obj("fifo", 1.0)] == [1, 2]
         c1.close(), c2.close()
     finally:
         srv.close()
