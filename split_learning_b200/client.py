@@ -116,7 +116,8 @@ class RpcClient:
         self.trainer.data_count = 0
         if is_first and (self.train_loader is None or msg.get("refresh", True)):
             self.train_loader = data_loader(self.data_name, int(self.learning["batch-size"]), self.label_count,
-                                            train=True, synthetic=True if self.opts.get("synthetic-data") else None)
+                                            train=True, synthetic=True if self.opts.get("synthetic-data") else None,
+                                            device=self.device, gpu_loader=bool(self.opts.get("gpu-loader", False)))
         self.is_first, self.is_last = is_first, is_last
         self.start_msg = msg
         self.send_to_server(M.ready(self.client_id, self.layer_id))

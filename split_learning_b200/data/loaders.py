@@ -135,14 +135,49 @@ def real_data_available(data_name: str, root: str = "./data") -> bool:
     return bool(marker) and os.path.exists(os.path.join(root, marker))
 
 
+def gpu_image_loader(name: str, batch_size: int, distribution: Sequence[int], device, synthetic: bool, root: str = "./data",
+                     seed: int = 0):
+    """Training loader whose dataset lives on the GPU and whose microbatches are built by one kernel
+    (``data/gpu_loader.py``): CIFAR10 (crop + flip + normalise, the reference recipe) and MNIST (normalise)."""
+    from .gpu_loader import CIFAR_MEAN, CIFAR_STD, MNIST_MEAN, MNIST_STD, GpuImageLoader
+    shape, _, ncls, _ = DATASET_SHAPES[name]
+    c, h, w = shape
+    if synthetic:
+        labels: List[int] = []
+        for lbl, cnt in enumerate(distribution):
+            labels += [lbl % ncls] * int(cnt)
+        y = torch.tensor(labels, dtype=torch.long)
+        g = torch.Generator().manual_seed(seed)
+        img = torch.randn(len(labels), h, w, c, generator=g) * 40.0 + 128.0 + (y.float().view(-1, 1, 1, 1) - (ncls - 1) / 2) * 10.0
+        images = img.clamp_(0, 255).to(torch.uint8)
+    else:
+        import numpy as np
+        import torchvision
+        if name == "CIFAR10":
+            ds = torchvision.datasets.CIFAR10(root=root, train=True, download=False)
+            data, targets = ds.data, list(ds.targets)                       # uint8 [N, 32, 32, 3]
+        else:
+            ds = torchvision.datasets.MNIST(root=root, train=True, download=False)
+            data, targets = ds.data.numpy()[..., None], ds.targets.tolist()  # uint8 [N, 28, 28, 1]
+        pick = _select_by_label(targets, distribution)
+        images = torch.from_numpy(np.ascontiguousarray(data[pick]))
+        y = torch.tensor([targets[i] for i in pick], dtype=torch.long)
+    mean, std = (CIFAR_MEAN, CIFAR_STD) if name == "CIFAR10" else (MNIST_MEAN, MNIST_STD)
+    return GpuImageLoader(images, y, batch_size, device, mean, std, augment=(name == "CIFAR10"), seed=seed)
+
+
 def data_loader(data_name: Optional[str] = None, batch_size: Optional[int] = None,
                 distribution: Optional[Sequence[int]] = None, train: bool = True,
-                synthetic: Optional[bool] = None, root: str = "./data", seed: int = 0) -> DataLoader:
+                synthetic: Optional[bool] = None, root: str = "./data", seed: int = 0, device=None,
+                gpu_loader: bool = False) -> DataLoader:
     name = str(data_name).upper()
     if name not in DATASET_SHAPES:
         raise ValueError(f"Dataset {data_name} not supported.")
     if synthetic is None:
         synthetic = os.environ.get("SLB200_SYNTHETIC", "0") == "1" or not real_data_available(name, root)
+    if (gpu_loader and train and name in ("CIFAR10", "MNIST") and device is not None and torch.device(device).type == "cuda"
+            and distribution is not None and len(distribution) > 0):
+        return gpu_image_loader(name, int(batch_size), distribution, device, bool(synthetic), root, seed)
     if synthetic or name not in _REAL:
         shape, dtype, ncls, test_bs = DATASET_SHAPES[name]
         if distribution is None or len(distribution) == 0:

@@ -800,6 +800,34 @@ __global__ void cast_f32_bf16_kernel(const float4* x, uint2* y, long long n4) {
   }
 }
 
+// ============================================================================ GPU-resident image loader
+// One training microbatch straight from a uint8 dataset that lives in HBM (reference recipe,
+// src/dataset/dataloader.py:61-84: RandomCrop(32, padding 4) + RandomHorizontalFlip + ToTensor + Normalize):
+//   out[b][c][y][x] = (img[idx[b]][y + dy[b]][x' + dx[b]][c] / 255 - mean[c]) / std[c],  x' = flip[b] ? W-1-x : x,
+// zero outside the image (the padding is applied to the raw image, i.e. it normalises to -mean/std).
+// data: [N][H][W][C] uint8 (torchvision's layout), out: [B][C][H][W] fp32 (the stage input).
+__global__ void __launch_bounds__(256)
+image_batch_kernel(const uint8_t* __restrict__ data, const long long* __restrict__ idx, const int* __restrict__ dx,
+                   const int* __restrict__ dy, const int* __restrict__ flip, float* __restrict__ out, int B, int C, int H,
+                   int W, float m0, float m1, float m2, float s0, float s1, float s2) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = static_cast<long long>(B) * C * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const int y = static_cast<int>((i / W) % H);
+    const int c = static_cast<int>((i / (static_cast<long long>(W) * H)) % C);
+    const int b = static_cast<int>(i / (static_cast<long long>(W) * H * C));
+    const int sx = (flip[b] ? W - 1 - x : x) + dx[b], sy = y + dy[b];
+    float v = 0.f;
+    if (sx >= 0 && sx < W && sy >= 0 && sy < H)
+      v = static_cast<float>(data[((idx[b] * H + sy) * W + sx) * C + c]) * (1.f / 255.f);
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    out[i] = (v - mean) / sd;
+  }
+}
+
 // ============================================================================ FedAvg n-ary weighted reduction
 // out[i] = sum_r coef[r] * nan_to_num(src[r][i]) ; src pointers may be peer (NVLink) addresses.  
 struct FedAvgParams {
@@ -855,7 +883,7 @@ int slb_preload_elementwise() {
   SLB_PRELOAD(conv3x3_small_wgrad_kernel<3>); SLB_PRELOAD(conv3x3_small_wgrad_kernel<1>); SLB_PRELOAD(linear_finalize_kernel);
   SLB_PRELOAD(linear_bwd_prep_kernel); SLB_PRELOAD(dropout_fwd_kernel); SLB_PRELOAD(dropout_bwd_kernel);
   SLB_PRELOAD(ce_fwd_bwd_kernel); SLB_PRELOAD(sgd_momentum_kernel); SLB_PRELOAD(adamw_kernel); SLB_PRELOAD(cast_f32_bf16_kernel);
-  SLB_PRELOAD(fedavg_kernel);
+  SLB_PRELOAD(fedavg_kernel); SLB_PRELOAD(image_batch_kernel);
 #undef SLB_PRELOAD
   return bad;
 }
@@ -1026,6 +1054,14 @@ int slb_adamw(float* p, float* g, float* m, float* v, void* p_bf16, long long n,
   launch_k(adamw_kernel, grid_for(n / 4, 256, 148 * 16), 256, 0, st, reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g),
                                                               reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
                                                               reinterpret_cast<uint2*>(p_bf16), n / 4, lr, b1, b2, eps, wd, bc1, bc2, step_ptr);
+  return last_err();
+}
+int slb_image_batch(const void* data, const long long* idx, const int* dx, const int* dy, const int* flip, float* out, int B,
+                    int C, int H, int W, const float* mean3, const float* std3, cudaStream_t st) {
+  if (C < 1 || C > 3) return -1;
+  const long long total = (long long)B * C * H * W;
+  launch_k(image_batch_kernel, grid_for(total, 256, 148 * 8), 256, 0, st, reinterpret_cast<const uint8_t*>(data), idx, dx, dy,
+           flip, out, B, C, H, W, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
   return last_err();
 }
 int slb_cast_f32_bf16(const float* x, void* y, long long n, cudaStream_t st) {

@@ -464,3 +464,14 @@ def embed3_fwd(ids, tts, word, pos, typ, out, tokens, S, D):
 def embed3_bwd(ids, tts, g, dword, dpos, dtyp, tokens, S, D, pad_id=-1):
     _check(lib().slb_embed3_bwd(_p(ids), _p(tts), _p(g), _p(dword), _p(dpos), _p(dtyp), c_int(tokens), c_int(S), c_int(D),
                                 c_longlong(pad_id), _stream()), "embed3_bwd")
+
+
+# ------------------------------------------------------------------ GPU-resident image loader
+def image_batch(data_u8, idx, dx, dy, flip, out, mean, std):
+    """out[B, C, H, W] fp32 = normalise(crop/flip(data_u8[idx])); data_u8: [N, H, W, C] uint8 on the GPU,
+    idx int64 [B], dx / dy / flip int32 [B] (device)."""
+    B, C, H, W = out.shape
+    m = (c_float * 3)(*([float(v) for v in mean] + [0.0] * (3 - len(mean))))
+    sd = (c_float * 3)(*([float(v) for v in std] + [1.0] * (3 - len(std))))
+    _check(lib().slb_image_batch(_p(data_u8), _p(idx), _p(dx), _p(dy), _p(flip), _p(out), c_int(B), c_int(C), c_int(H), c_int(W),
+                                 m, sd, _stream()), "image_batch")

@@ -152,7 +152,10 @@ class DeviceRpcClient(RpcClient):
             for batch in self.train_loader:
                 x, y = batch if not isinstance(batch, dict) else (batch["input_ids"], batch["labels"])
                 if x.shape[0] == B:
-                    batches.append((x.float().pin_memory(), torch.as_tensor(y).long().pin_memory()))
+                    if x.is_cuda:                       # GPU-resident loader: the microbatch already lives in HBM
+                        batches.append((x.float(), torch.as_tensor(y).long()))
+                    else:
+                        batches.append((x.float().pin_memory(), torch.as_tensor(y).long().pin_memory()))
             n = len(batches)
             self.channel.publish_obj(f"plan_{down}", {"lane": lane, "batches": n})
             it_b = 0

@@ -235,6 +235,30 @@ def test_public_api_device_plane(tmp_path, monkeypatch):
     assert int(sd["layer2.num_batches_tracked"]) == 40                       # recomputing first stage: 2 forwards each
 
 
+@pytest.mark.parametrize("plane", ["host", "device"])
+def test_public_api_gpu_resident_loader(tmp_path, monkeypatch, plane):
+    """``b200.gpu-loader``: the training subset lives in HBM, each microbatch is one augmentation kernel — through both
+    data planes."""
+    import yaml
+    monkeypatch.setenv("SLB200_WAIT_SPINS", str(1 << 23))
+    from split_learning_b200.checkpoint import load_checkpoint
+    from split_learning_b200.config import normalize
+    from split_learning_b200.data.gpu_loader import GpuImageLoader
+    from split_learning_b200.runner import run_inproc
+    raw = yaml.safe_load(open("config.yaml"))
+    raw["server"].update({"clients": [1, 1], "global-round": 1, "validation": False})
+    raw["server"]["data-distribution"]["num-sample"] = 320
+    raw["log_path"] = str(tmp_path)
+    raw["learning"].update({"batch-size": 32, "control-count": 3, "learning-rate": 0.01})
+    raw["b200"] = {"synthetic-data": True, "data-plane": plane, "gpu-loader": True, "watchdog-seconds": 120}
+    srv = run_inproc(normalize(raw), devices=["cuda:0"], workdir=str(tmp_path), timeout=600)
+    assert [h["ok"] for h in srv.history] == [True]
+    first = [c for c in srv.clients_objs if c.layer_id == 1][0]
+    assert isinstance(first.train_loader, GpuImageLoader) and first.train_loader.images.is_cuda
+    sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    assert int(sd["layer9.num_batches_tracked"]) == 10 and all(torch.isfinite(v.float()).all() for v in sd.values())
+
+
 @pytest.mark.parametrize("clients,cuts", [((2, 1), [7]), ((2, 2, 1), [5, 10])])
 def test_public_api_device_plane_fan_in(tmp_path, monkeypatch, clients, cuts):
     """Many clients, fewer servers on the device plane: the downstream stage multiplexes one mailbox lane per upstream
