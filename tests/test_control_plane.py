@@ -164,8 +164,8 @@ def test_broker_competing_consumers_exactly_once(kind):
                     break
                 got[c].append(m)
             ch.close()
-        ts = [threading.Thread(target=produce, args=(p,)) for p in range(n_prod)] + \\
-             [threading.Thread(target=consume, args=(c,)) for c in range(n_cons)]
+        ts = [threading.Thread(target=produce, args=(p,)) for p in range(n_prod)]
+        ts += [threading.Thread(target=consume, args=(c,)) for c in range(n_cons)]
         [t.start() for t in ts]
         [t.join(60) for t in ts]
         flat = [m for g in got for m in g]
