@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--depth", type=int, default=3, help="control-count (microbatches in flight)")
     ap.add_argument("--cut", type=int, default=7)
+    ap.add_argument("--cuts", default=None, help="N=1 only: comma list for an N-stage pipeline on one GPU, e.g. 5,10")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--timeout", type=float, default=1500.0)
     ap.add_argument("--breakdown", action="store_true", help="also report device time per stage program (F / L / B)")
@@ -121,9 +122,11 @@ def run_ours(args) -> dict:
     torch.manual_seed(0)
     learning = {"learning-rate": 0.0005, "momentum": 0.5, "batch-size": args.batch, "control-count": args.depth}
     W, K, B = args.warmup, args.steps, args.batch
-    ex1 = B200Executor(VGG16_CIFAR10(0, args.cut), "VGG16", learning, dev, is_first=True, use_graphs=not args.no_graphs)
-    ex2 = B200Executor(VGG16_CIFAR10(args.cut, 52), "VGG16", learning, dev, is_last=True, use_graphs=not args.no_graphs)
-    pipe = LocalPipeline([ex1, ex2], B, args.depth, overlap=not (args.no_overlap or args.breakdown))
+    cuts = [int(c) for c in args.cuts.split(",")] if args.cuts else [args.cut]
+    bounds = [0] + cuts + [52]
+    exs = [B200Executor(VGG16_CIFAR10(bounds[i], bounds[i + 1]), "VGG16", learning, dev, is_first=(i == 0),
+                        is_last=(i == len(bounds) - 2), use_graphs=not args.no_graphs) for i in range(len(bounds) - 1)]
+    pipe = LocalPipeline(exs, B, args.depth, overlap=not (args.no_overlap or args.breakdown))
     pool = synthetic_batches(16, B, seed=1)
     loss_host = torch.zeros(4).pin_memory()
 
@@ -214,8 +217,9 @@ def run_ours(args) -> dict:
         "metric": "VGG16/CIFAR10 split images/sec", "value": value, "unit": "images/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"model": "VGG16_CIFAR10", "global_batch": B, "microbatch": B, "seq_len": None, "cut_layers": [args.cut],
-                   "clients": [1, 1], "control_count": args.depth, "parallelism": "pp2 (both stages on one GPU, one stream per stage)",
+        "config": {"model": "VGG16_CIFAR10", "global_batch": B, "microbatch": B, "seq_len": None, "cut_layers": cuts,
+                   "clients": [1] * (len(cuts) + 1), "control_count": args.depth,
+                   "parallelism": f"pp{len(cuts) + 1} (all stages on one GPU, one stream per stage)",
                    "optimizer": "SGD lr=5e-4 momentum=0.5, step per microbatch", "recompute": True,
                    "cuda_graphs": not args.no_graphs,
                    "l2": "per-step working set ~470 MB (fp32 master+momentum+grad+bf16 shadow) > 126 MB L2; no flush needed"},
