@@ -28,6 +28,7 @@
 #include <cstring>
 #include <deque>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -81,8 +82,14 @@ void serve(int fd) {
     uint64_t alen;
     std::memcpy(&qlen, hdr + 1, 4);
     std::memcpy(&alen, hdr + 5, 8);
-    if (qlen > (1u << 16) || alen > (1ull << 36)) break;          // corrupt frame
-    std::string queue(qlen, '\0'), arg(alen, '\0');
+    if (qlen > (1u << 16) || alen > (1ull << 33)) break;          // corrupt frame (largest real payload: a ~140 MB state-dict)
+    std::string queue, arg;
+    try {
+      queue.assign(qlen, '\0');
+      arg.assign(alen, '\0');
+    } catch (const std::bad_alloc&) {
+      break;
+    }
     if (qlen && !read_exact(fd, &queue[0], qlen)) break;
     if (alen && !read_exact(fd, &arg[0], alen)) break;
     bool ok = true;
