@@ -76,3 +76,33 @@ def test_two_ls_fedasync(tmp_path):
                             dict(layer_id=2, idx=0, in_cluster=0, out_cluster=0)], workdir=str(tmp_path))
     assert srv.history[0]["ok"] and sorted(srv.out_ids) == [0, 1]
     assert len(load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))) == 97
+
+
+def test_vanilla_sl_limited_time_mode(tmp_path):
+    """``limited-time``: the first stage keeps looping epochs until the wall-clock budget is spent
+    (other/Vanilla_SL/src/Scheduler.py:68-69,77,108-115), instead of exactly one pass."""
+    raw = _base(tmp_path, "vanilla_sl", (1, 1), **{"limited-time": {"enable": True, "epoch": 50, "time": 4.0}})
+    raw["server"]["validation"] = False
+    cfg = normalize(raw)
+    assert cfg.limited_time == {"enable": True, "epoch": 50, "time": 4.0}
+    srv = run_variant(cfg, [dict(layer_id=1), dict(layer_id=2)], workdir=str(tmp_path))
+    assert srv.history[0]["ok"]
+    sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    one_epoch = 32 // 8                                   # 32 samples / batch 8
+    assert int(sd["layer9.num_batches_tracked"]) > one_epoch          # more than one pass fitted into the budget
+    assert int(sd["layer9.num_batches_tracked"]) % one_epoch == 0     # the budget is checked at epoch boundaries
+
+
+def test_flex_unselected_device_is_dropped(tmp_path):
+    """FLEX ``--s 0``: an un-selected first-stage device is rejected at registration (other/FLEX/src/Server.py:270-285);
+    the round runs with the remaining devices."""
+    raw = _base(tmp_path, "flex", (2, 1), **{"t-g": 1, "t-c": 1, "num-cluster": 1, "cut-layer": [7]})
+    del raw["server"]["no-cluster"]
+    cfg = normalize(raw)
+    srv = run_variant(cfg, [dict(layer_id=1, cluster=0, select=1), dict(layer_id=1, cluster=0, select=0),
+                            dict(layer_id=2, cluster=0)], workdir=str(tmp_path))
+    assert srv.history and srv.history[0]["ok"]
+    assert srv.total_clients[0] == 1
+    trained = [c for c in srv.clients if c.layer_id == 1 and c.train]
+    assert len(trained) == 1 and sum(trained[0].label_counts) > 0
+    assert len(load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))) == 97
