@@ -133,3 +133,23 @@ def test_flex_speed_profile(tmp_path):
     assert set(info) == {"speed"} and info["speed"] > 0
     info = write_speed_profile("VGG16", 2, str(tmp_path / "p2.json"), "CIFAR10", rounds=1)
     assert info["speed"] > 0
+
+
+def test_validation_gate_and_heartbeat_pump():
+    """``get_val``: the main tree always passes (src/val/get_val.py), the Vanilla_SL gate fails the round on a NaN / huge
+    loss (other/Vanilla_SL/src/Validation.py:46,55-56); ``pump`` is called every 5 batches (DCSL's heartbeat hook)."""
+    import math
+    import torch
+    from split_learning_b200.models import get_model_class
+    from split_learning_b200.validation import get_val
+    torch.manual_seed(0)
+    sd = get_model_class("KWT", "SPEECHCOMMANDS")().state_dict()
+    beats = []
+    ok, m = get_val("KWT", "SPEECHCOMMANDS", sd, strict=True, device="cpu", pump=lambda: beats.append(1), synthetic=True)
+    assert ok and m["val_total"] > 0 and 0.0 <= m["val_acc"] <= 100.0 and len(beats) == (m["val_total"] // 20) // 5
+    bad = {k: v.clone() for k, v in sd.items()}
+    bad["layer1.weight"][0, 0] = float("nan")
+    ok_main, m_main = get_val("KWT", "SPEECHCOMMANDS", bad, strict=False, device="cpu", synthetic=True)
+    ok_strict, _ = get_val("KWT", "SPEECHCOMMANDS", bad, strict=True, device="cpu", synthetic=True)
+    assert ok_main and math.isnan(m_main["val_loss"]) and not ok_strict
+    assert get_val("NOPE", "CIFAR10", {}, device="cpu") == (False, {})
