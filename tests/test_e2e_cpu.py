@@ -117,3 +117,39 @@ def test_world_size_2_processes_tcp(tmp_path):
             if p.poll() is None:
                 p.kill()
     assert (tmp_path / "VGG16_CIFAR10.pth").exists()
+
+
+def test_nan_round_is_counted_but_not_aggregated(tmp_path, monkeypatch):
+    """Reference semantics (src/Server.py:162-170,195-196): a round in which a client saw a NaN loss is not aggregated
+    or checkpointed, yet it still consumes one of the global rounds."""
+    from split_learning_b200.train import executor as E
+    calls = {"n": 0}
+    real = E.TorchExecutor.nan_detected
+
+    def flaky(self):
+        if self.is_last:
+            calls["n"] += 1
+            if calls["n"] == 1:              # last stage reports a NaN loss in round 1 only
+                return True
+        return real(self)
+    monkeypatch.setattr(E.TorchExecutor, "nan_detected", flaky)
+    raw = _raw(tmp_path, rounds=2)
+    raw["server"]["validation"] = False
+    srv = run_inproc(normalize(raw), workdir=str(tmp_path), timeout=300)
+    assert [h["ok"] for h in srv.history] == [False, True]
+    assert load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))          # written by the good round
+
+
+def test_duplicate_register_is_ignored(tmp_path):
+    """A client that REGISTERs twice is listed once (src/Server.py:119-120)."""
+    import uuid
+    from split_learning_b200 import messages as M
+    from split_learning_b200.server import Server
+    from split_learning_b200.transport import InProcBroker
+    cfg = normalize(_raw(tmp_path, clients=(2, 1)))
+    srv = Server(cfg, InProcBroker(), workdir=str(tmp_path))
+    cid = uuid.uuid4()
+    msg = M.register(cid, 1, {"speed": 1.0, "exe_time": [1.0] * 52, "size_data": [1.0] * 52, "network": 1.0}, -1)
+    srv.on_request(msg)
+    srv.on_request(msg)
+    assert len(srv.clients) == 1
