@@ -176,3 +176,16 @@ def test_broker_competing_consumers_exactly_once(kind):
                 assert seq == sorted(seq)
     finally:
         srv.close()
+
+
+def test_fedavg_control_messages_over_gloo_two_processes():
+    """world_size = 2 on CPU (gloo): the torch.distributed side of the peer-memory FedAvg (object all-gather, barrier,
+    rounded integer-state average)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29611", os.path.join(root, "tools", "check_dist_cpu.py")],
+                       capture_output=True, text=True, timeout=240, cwd=root, env=dict(os.environ, PYTHONPATH=root))
+    assert r.returncode == 0 and "DIST_CPU_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
