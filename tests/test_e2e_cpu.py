@@ -153,3 +153,24 @@ def test_duplicate_register_is_ignored(tmp_path):
     srv.on_request(msg)
     srv.on_request(msg)
     assert len(srv.clients) == 1
+
+
+def test_dead_client_becomes_an_error_not_a_deadlock(tmp_path, monkeypatch):
+    """Failure detection: the reference dead-locks when a client dies mid-round (no heartbeat / timeouts).
+    Here the peers' watchdogs turn the silence into a TimeoutError within ``watchdog-seconds``."""
+    import time
+    from split_learning_b200 import client as C
+    real = C.RpcClient.run_stage
+
+    def dying(self):
+        if self.layer_id == 2:
+            raise RuntimeError("simulated crash of the last-stage client")
+        return real(self)
+    monkeypatch.setattr(C.RpcClient, "run_stage", dying)
+    raw = _raw(tmp_path)
+    raw["server"]["validation"] = False
+    raw["b200"]["watchdog-seconds"] = 3
+    t0 = time.monotonic()
+    with pytest.raises((RuntimeError, TimeoutError)):
+        run_inproc(normalize(raw), workdir=str(tmp_path), timeout=60)
+    assert time.monotonic() - t0 < 60
