@@ -189,3 +189,28 @@ def test_fedavg_control_messages_over_gloo_two_processes():
                         "127.0.0.1", "--master-port", "29611", os.path.join(root, "tools", "check_dist_cpu.py")],
                        capture_output=True, text=True, timeout=240, cwd=root, env=dict(os.environ, PYTHONPATH=root))
     assert r.returncode == 0 and "DIST_CPU_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
+
+def test_queue_grammar_of_every_variant():
+    """forward / gradient queue names per algorithm variant, and a host data-plane round trip
+    (forward message -> gradient routed back to the originating client through ``trace``)."""
+    import torch
+    from split_learning_b200.train.dataplane import HostDataPlane, QueueGrammar
+    assert QueueGrammar("main").forward_queue(1, 0) == "intermediate_queue_1_0"
+    assert QueueGrammar("flex").forward_queue(1, 2) == "intermediate_queue_1_2"
+    assert QueueGrammar("vanilla_sl").forward_queue(1, 0) == QueueGrammar("cluster_fsl").forward_queue(1, 3) == "intermediate_queue_1"
+    assert QueueGrammar("dcsl").forward_queue(1, 0, target="dev7") == "intermediate_queue_dev7"
+    assert QueueGrammar("dcsl").forward_queue(1, 0) == "intermediate_queue_1"
+    assert QueueGrammar("2ls").forward_queue(1, 0, target=3) == "intermediate_queue_1_3"
+    for v in ("main", "vanilla_sl", "dcsl", "2ls", "flex"):
+        assert QueueGrammar(v).gradient_queue(1, "abc") == "gradient_queue_1_abc"
+    b = InProcBroker()
+    first = HostDataPlane(b, "c1", 1, cluster=0)
+    last = HostDataPlane(b, "c2", 2, cluster=0)
+    first.send_forward("id0", torch.arange(6.0).view(2, 3), torch.tensor([1, 0]))
+    m = last.recv_forward(1.0)
+    assert m["data_id"] == "id0" and m["trace"] == ["c1"] and m["data"].shape == (2, 3) and m["label"].tolist() == [1, 0]
+    last.send_gradient(m["data_id"], torch.ones(2, 3), m["trace"])
+    g = first.recv_gradient(1.0)
+    assert g["data_id"] == "id0" and g["trace"] == [] and torch.equal(g["data"], torch.ones(2, 3))
+    assert last.recv_forward(0.0) is None and first.recv_gradient(0.0) is None
