@@ -24,12 +24,25 @@ def main():
     ap.add_argument("--cpu", action="store_true", help="run every client on the CPU (plumbing / debugging)")
     ap.add_argument("--algorithm", default=None)
     ap.add_argument("--timeout", type=float, default=0.0)
+    ap.add_argument("--dry-run", action="store_true", help="print the rank -> (stage, cluster, device) plan and exit")
     args = ap.parse_args()
     cfg = load_config(args.config)
     info = cfg.infor_cluster if (cfg.cluster_mode and cfg.infor_cluster_given) else None
     ranks = rank_assignment(cfg.clients, info)
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     extra = ["--algorithm", args.algorithm] if args.algorithm else []
+    if args.dry_run:
+        try:
+            import torch
+            ngpu = torch.cuda.device_count()
+        except Exception:
+            ngpu = 0
+        print(f"model {cfg.model}/{cfg.data_name}  algorithm {args.algorithm or cfg.b200.get('algorithm', 'main')}  "
+              f"data-plane {cfg.b200.get('data-plane', 'host')}  clients {list(cfg.clients)}  cuts {cfg.cluster_cut_layers or cfg.cut_layers}")
+        for r, (layer_id, cluster, i) in enumerate(ranks):
+            dev = "cpu" if (args.cpu or ngpu == 0) else f"cuda:{r % ngpu}"
+            print(f"  rank {r}: stage {layer_id}  cluster {cluster}  member {i}  device {dev}")
+        return
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "server.py"), "--config", args.config] + extra, env=env)]
     time.sleep(0.5)
     try:
