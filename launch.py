@@ -38,7 +38,7 @@ def main():
         except Exception:
             ngpu = 0
         print(f"model {cfg.model}/{cfg.data_name}  algorithm {args.algorithm or cfg.b200.get('algorithm', 'main')}  "
-              f"data-plane {cfg.b200.get('data-plane', 'host')}  clients {list(cfg.clients)}  cuts {cfg.cluster_cut_layers or cfg.cut_layers}")
+              f"data-plane {cfg.b200.get('data-plane', 'host')}  clients {list(cfg.clients)}  cuts {cfg.cluster_cut_layers if cfg.cluster_mode else cfg.no_cluster_cut_layers}")
         for r, (layer_id, cluster, i) in enumerate(ranks):
             dev = "cpu" if (args.cpu or ngpu == 0) else f"cuda:{r % ngpu}"
             print(f"  rank {r}: stage {layer_id}  cluster {cluster}  member {i}  device {dev}")
