@@ -139,7 +139,10 @@ def _single_box_processes(args, cfg, port: int, W: int, K: int) -> float:
     return ms
 
 
-def main(args) -> dict:
+def main(args, transport: str = "broker") -> dict:
+    """``transport``: "broker" = pickled NumPy through the in-box broker (what the reference does over RabbitMQ);
+    "nccl" = the hot activation / gradient payloads over torch.distributed NCCL isend/recv (see shims/pika)."""
+    impl = "reference" if transport == "broker" else "reference-nccl"
     sys.path.insert(0, HERE)
     try:
         ref, outcome = _prepare_imports()
@@ -167,6 +170,8 @@ def main(args) -> dict:
     cfg = _config(n_first, n_last, batches)
     port = 29655 + (int(os.environ.get("MASTER_PORT", "0")) % 97)
 
+    if transport == "nccl" and world < 2:
+        return {"impl": impl, "unavailable": "NCCL p2p needs one rank per client (>= 2 GPUs); N=1 puts both clients on one GPU"}
     if world == 1:
         t_wall = time.perf_counter()
         ms_total = _single_box_processes(args, cfg, port, W, K)
@@ -182,6 +187,11 @@ def main(args) -> dict:
             pika.serve("127.0.0.1", port)
         dist.barrier()
         pika.use_remote("127.0.0.1", port)
+        if transport == "nccl":
+            pika.use_nccl(rank, n_first, n_last, device)
+            warm = torch.zeros(8, device=device)             # communicator setup outside the timed region
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
 
     # ---- delivery hook: time K steps between the W-th and (W+K)-th gradient delivery --------
     marks = {}
@@ -250,7 +260,13 @@ def main(args) -> dict:
         return {}
     if ms_total <= 0:
         return {"impl": "reference", "unavailable": "timing marks missing"}
-    return _result(n, n_first, n_last, K, W, ms_total, outcome, time.perf_counter() - t_wall, "one OS process (rank) per client")
+    res = _result(n, n_first, n_last, K, W, ms_total, outcome, time.perf_counter() - t_wall, "one OS process (rank) per client")
+    if transport == "nccl":
+        res["impl"] = impl
+        res["config"]["transport"] = ("torch.distributed NCCL isend/recv for intermediate_queue_* / gradient_queue_* payloads "
+                                      "(header + control verbs on the in-box broker); reference trainers unmodified")
+        res["nccl"] = pika.nccl_stats()
+    return res
 
 
 def _result(n, n_first, n_last, K, W, ms_total, outcome, wall, deployment) -> dict:

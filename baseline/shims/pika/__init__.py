@@ -8,6 +8,16 @@ Nothing of split_learning_b200 is imported here.
 
 Message-completion hook: ``on_get`` callbacks let the benchmark harness observe deliveries
 (to time K pipeline steps) without touching the reference's code.
+
+NCCL mode (``use_nccl``; ``bench.py --impl reference-nccl``) — the "reference's own NCCL build" that BASELINE.json names as
+the competitor: the tensors of the two HOT queues (``intermediate_queue_*`` activations, ``gradient_queue_*`` gradients,
+/root/reference/src/train/VGG16.py:20-53) travel GPU -> GPU with ``torch.distributed`` NCCL ``isend`` / ``recv``; only a small
+header (data_id, label, trace, shape) goes through the broker, and the control verbs stay on the broker as before.  The
+reference trainers are untouched: they still hand the shim a pickled dict with a CPU NumPy array and get one back, so the
+D2H / H2D copies at the trainer boundary remain (they are part of the reference's code), but the wire itself is NCCL p2p
+over NVLink instead of pickle-over-TCP.  Routing is static (first-stage rank r -> last-stage rank n_first + r % n_last; the
+gradient returns to the rank the activation came from), forward and backward use separate communicators so the 1F1B
+schedule cannot dead-lock on NCCL's per-communicator ordering.
 """
 import collections
 import os
@@ -40,6 +50,65 @@ class _Store:
     def delete(self, key):
         with self.cv:
             self.q.pop(key, None)
+
+
+_NCCL = None                # dict(rank, n_first, n_last, fwd, bwd, device, origin, pending) in NCCL mode
+
+
+def use_nccl(rank, n_first, n_last, device):
+    """Route the payload of the two hot queues over NCCL p2p.  Collective: every rank must call (creates two groups)."""
+    global _NCCL
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    fwd = dist.new_group(list(range(world)))
+    bwd = dist.new_group(list(range(world)))
+    _NCCL = {"rank": rank, "n_first": n_first, "n_last": n_last, "fwd": fwd, "bwd": bwd, "device": device,
+             "origin": {}, "pending": [], "sent": 0, "received": 0, "bytes": 0}
+
+
+def nccl_stats():
+    return None if _NCCL is None else {k: _NCCL[k] for k in ("sent", "received", "bytes")}
+
+
+def _nccl_publish(chan, routing_key, body):
+    import torch
+    import torch.distributed as dist
+    st = _NCCL
+    msg = pickle.loads(body)
+    arr = msg.pop("data")
+    t = torch.from_numpy(arr).to(st["device"])
+    if routing_key.startswith("intermediate_queue_"):
+        dst = st["n_first"] + st["rank"] % st["n_last"]
+        key, group = f"{routing_key}@{dst}", st["fwd"]
+    else:                                   # gradient_queue_{layer}_{client_id}: back to where the activation came from
+        dst = st["origin"][routing_key.split("_", 3)[3]]
+        key, group = routing_key, st["bwd"]
+    header = {"__nccl__": 1, "src": st["rank"], "shape": tuple(arr.shape), "dtype": str(arr.dtype), "rest": msg}
+    chan._pub(key, pickle.dumps(header, protocol=pickle.HIGHEST_PROTOCOL))
+    work = dist.isend(t, dst, group=group)
+    st["pending"].append((work, t))
+    st["pending"] = [(w, x) for (w, x) in st["pending"] if not w.is_completed()][-64:]
+    st["sent"] += 1
+    st["bytes"] += arr.nbytes
+
+
+def _nccl_receive(queue, body):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    st = _NCCL
+    h = pickle.loads(body)
+    if not (isinstance(h, dict) and h.get("__nccl__")):
+        return body
+    fwd = queue.startswith("intermediate_queue_")
+    buf = torch.empty(h["shape"], dtype=getattr(torch, h["dtype"]), device=st["device"])
+    dist.recv(buf, src=h["src"], group=st["fwd"] if fwd else st["bwd"])
+    msg = h["rest"]
+    if fwd and msg.get("trace"):
+        st["origin"][str(msg["trace"][-1])] = h["src"]
+    msg["data"] = buf.cpu().numpy()
+    st["received"] += 1
+    return pickle.dumps(msg, protocol=pickle.HIGHEST_PROTOCOL)
 
 
 _LOCAL = _Store()
@@ -151,12 +220,18 @@ class _Channel:
             _LOCAL.delete(queue)
 
     def basic_publish(self, exchange="", routing_key="", body=b"", properties=None, **k):
+        if _NCCL is not None and routing_key.startswith(("intermediate_queue_", "gradient_queue_")):
+            return _nccl_publish(self, routing_key, body)
         self._pub(routing_key, body)
 
     def basic_get(self, queue=None, auto_ack=False):
-        body = self._get(queue)
+        hot = _NCCL is not None and queue.startswith(("intermediate_queue_", "gradient_queue_"))
+        key = f"{queue}@{_NCCL['rank']}" if (hot and queue.startswith("intermediate_queue_")) else queue
+        body = self._get(key)
         if body is None:
             return None, None, None
+        if hot:
+            body = _nccl_receive(queue, body)
         for cb in on_get:
             cb(queue, body)
         self._tag += 1

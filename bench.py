@@ -37,11 +37,14 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-nccl"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--depth", type=int, default=3, help="control-count (microbatches in flight)")
     ap.add_argument("--cut", type=int, default=7)
     ap.add_argument("--cuts", default=None, help="N=1 only: comma list for an N-stage pipeline on one GPU, e.g. 5,10")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16"],
+                    help="tf32 (default) = the reference's precision: fp32 tensors, tcgen05 kind::tf32 convolutions with fp32 "
+                         "accumulation, fp32 Linear/BN/SGD; bf16 = opt-in fast mode")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--timeout", type=float, default=1500.0)
     ap.add_argument("--breakdown", action="store_true", help="also report device time per stage program (F / L / B)")
@@ -95,6 +98,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+DTYPE_LABEL = {
+    "tf32": "fp32 tensors; conv = tcgen05 kind::tf32 with fp32 accumulate (the reference's cuDNN-TF32 default), "
+            "Linear/BN/CE/SGD = fp32",
+    "bf16": "bf16 activations + bf16 weight shadow, fp32 master/accumulate (opt-in fast mode)",
+}
+
+
 def synthetic_batches(n: int, batch: int, seed: int):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -120,7 +130,8 @@ def run_ours(args) -> dict:
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
-    learning = {"learning-rate": 0.0005, "momentum": 0.5, "batch-size": args.batch, "control-count": args.depth}
+    learning = {"learning-rate": 0.0005, "momentum": 0.5, "batch-size": args.batch, "control-count": args.depth,
+                "precision": args.precision}
     W, K, B = args.warmup, args.steps, args.batch
     cuts = [int(c) for c in args.cuts.split(",")] if args.cuts else [args.cut]
     bounds = [0] + cuts + [52]
@@ -215,7 +226,7 @@ def run_ours(args) -> dict:
     value = K * B / (ms_dev / 1e3)
     return {
         "metric": "VGG16/CIFAR10 split images/sec", "value": value, "unit": "images/s", "n_gpus": 1, "steps": K, "warmup": W,
-        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_LABEL[args.precision],
         "data": "synthetic",
         "config": {"model": "VGG16_CIFAR10", "global_batch": B, "microbatch": B, "seq_len": None, "cut_layers": cuts,
                    "clients": [1] * (len(cuts) + 1), "control_count": args.depth,
@@ -232,10 +243,10 @@ def run_ours(args) -> dict:
 
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.impl in ("reference", "reference-nccl"):
         sys.path.insert(0, os.path.join(ROOT, "baseline"))
         from run_reference import main as ref_main
-        out = ref_main(args)
+        out = ref_main(args, transport="nccl" if args.impl == "reference-nccl" else "broker")
     else:
         out = run_ours(args)
     if out and int(os.environ.get("RANK", "0")) == 0:

@@ -41,7 +41,9 @@ def main():
     else:
         device = args.device
     print(f"Using device: {device}")
-    channel = connect(cfg.raw.get("rabbit", {}).get("address", "127.0.0.1"), int(cfg.b200.get("port", 29777)))
+    from split_learning_b200.transport.broker import broker_token
+    channel = connect(cfg.raw.get("rabbit", {}).get("address", "127.0.0.1"), int(cfg.b200.get("port", 29777)),
+                      token=broker_token(cfg))
     client_id = uuid.uuid4()
     profile = dict(DEFAULT_PROFILE)
     if os.path.exists("profiling.json"):

@@ -11,7 +11,7 @@ import sys
 from split_learning_b200.algorithms import server_class
 from split_learning_b200.config import load_config
 from split_learning_b200.transport import make_broker
-from split_learning_b200.transport.broker import delete_old_queues
+from split_learning_b200.transport.broker import broker_token, delete_old_queues
 
 parser = argparse.ArgumentParser(description="Split learning framework with controller.")
 parser.add_argument("--config", default="config.yaml")
@@ -23,8 +23,9 @@ def main():
     cfg = load_config(args.config)
     if args.algorithm:
         cfg.b200["algorithm"] = args.algorithm
+    # a non-loopback ``rabbit.address`` needs ``b200.broker-token`` (or SLB200_BROKER_TOKEN): the broker refuses otherwise
     broker = make_broker(cfg.raw.get("rabbit", {}).get("address", "127.0.0.1"), int(cfg.b200.get("port", 29777)),
-                         str(cfg.b200.get("broker", "native")))
+                         str(cfg.b200.get("broker", "native")), token=broker_token(cfg))
     channel = broker.channel()
 
     def on_sigint(sig, frame):

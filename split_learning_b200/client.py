@@ -10,6 +10,7 @@ loop); no 0.5 s polling — the reply queue is a blocking get; LoR
 """
 from __future__ import annotations
 
+import threading
 import time
 from typing import Optional
 
@@ -44,7 +45,31 @@ class RpcClient:
         self.lora = False
         self.rounds_done = 0
         self.watchdog = float(self.opts.get("watchdog-seconds", 120.0))
+        self.heartbeat = float(self.opts.get("heartbeat-seconds", min(10.0, self.watchdog / 4)))
+        self._hb_stop = threading.Event()
+        self._hb_thread: Optional[threading.Thread] = None
+        self._stopped = False
         self.channel.queue_declare(M.reply_queue(client_id))
+
+    # ------------------------------------------------------------------ liveness
+    def start_heartbeat(self) -> None:
+        """Beacon to the server from a daemon thread (own channel) for as long as this client lives: the server's and the
+        peers' idle timers measure silence, not the length of a healthy round (sequential variants wait N epochs)."""
+        if self._hb_thread is not None or self.heartbeat <= 0:
+            return
+        ch = self.channel.clone()
+
+        def beat():
+            while not self._hb_stop.wait(self.heartbeat):
+                try:
+                    ch.publish_obj(M.RPC_QUEUE, M.heartbeat(self.client_id))
+                except Exception:
+                    return
+        self._hb_thread = threading.Thread(target=beat, daemon=True, name=f"slb200-heartbeat-{self.client_id}")
+        self._hb_thread.start()
+
+    def stop_heartbeat(self) -> None:
+        self._hb_stop.set()
 
     # ------------------------------------------------------------------
     def send_to_server(self, message) -> None:
@@ -52,6 +77,7 @@ class RpcClient:
 
     def register(self, profile: Optional[dict], cluster: int = -1, **extra) -> None:
         self.send_to_server(M.register(self.client_id, self.layer_id, profile, cluster, rank=self.rank, **extra))
+        self.start_heartbeat()
 
     def wait_response(self, idle_timeout: Optional[float] = None) -> None:
         last = time.monotonic()
@@ -63,7 +89,10 @@ class RpcClient:
                     raise TimeoutError(f"client {self.client_id}: server silent for {limit}s")
                 continue
             last = time.monotonic()
+            if m.get("action") == M.HEARTBEAT:          # the server (and through it every peer) is alive
+                continue
             if not self.response_message(m):
+                self.stop_heartbeat()
                 return
 
     # ------------------------------------------------------------------
@@ -76,7 +105,7 @@ class RpcClient:
             return True
         if action == M.SYN:
             self.on_syn(msg)
-            return True
+            return not self._stopped          # a STOP consumed inside the training loop ends the client too
         if action == M.PAUSE:          # stray PAUSE outside a training loop: ignore
             return True
         if action == M.STOP:
@@ -153,6 +182,9 @@ class RpcClient:
         result, size = self.run_stage()
         self.upload(result, size)
         self.rounds_done += 1
+        pm = getattr(self.trainer, "pause_msg", None)
+        if pm is not None and pm.get("action") == M.STOP:
+            self._stopped = True
 
     def upload(self, result: bool, size: int, send: bool = True) -> None:
         sd = None

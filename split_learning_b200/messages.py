@@ -11,8 +11,8 @@ from typing import Any, Dict, List, Optional
 
 RPC_QUEUE = "rpc_queue"
 
-REGISTER, START, SYN, NOTIFY, PAUSE, UPDATE, STOP, READY = (
-    "REGISTER", "START", "SYN", "NOTIFY", "PAUSE", "UPDATE", "STOP", "READY")
+REGISTER, START, SYN, NOTIFY, PAUSE, UPDATE, STOP, READY, HEARTBEAT = (
+    "REGISTER", "START", "SYN", "NOTIFY", "PAUSE", "UPDATE", "STOP", "READY", "HEARTBEAT")
 
 
 def reply_queue(client_id) -> str:
@@ -59,6 +59,14 @@ def update(client_id, layer_id: int, result: bool, size: int, cluster, parameter
 
 def stop(message: str = "Stop training!") -> Dict[str, Any]:
     return {"action": STOP, "message": message, "parameters": None}
+
+
+def heartbeat(client_id=None) -> Dict[str, Any]:
+    """Liveness beacon (no counterpart in the reference, where a dead peer is a silent deadlock): clients publish it to
+    ``rpc_queue`` every few seconds, the server relays one to every ``reply_{id}``.  Receivers only refresh their idle
+    timers — waits are bounded by *silence of the peer*, not by how long a healthy round takes."""
+    import time
+    return {"action": HEARTBEAT, "client_id": client_id, "message": "alive", "t": time.time()}
 
 
 def ready(client_id, layer_id: int) -> Dict[str, Any]:

@@ -24,6 +24,23 @@ __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
   return p;
 }
 
+// 8 consecutive channels of one pixel, activation-typed (bf16: one 16-byte access, fp32: two)
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) { unpack8(*reinterpret_cast<const bf16x8*>(p), f); }
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) { *reinterpret_cast<bf16x8*>(p) = pack8(f); }
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+
 // "last block done" publication of a mailbox flag: every block fences its (possibly peer) stores,
 // the last one to arrive releases the flag system-wide and re-arms the ticket counter.
 // The flag value is a per-slot sequence number kept in device memory (`seq`), so the same
@@ -85,8 +102,9 @@ __global__ void counter_inc_kernel(uint32_t* c) {
   pdl_wait(); *c += 1; }
 
 // ============================================================================ BN + ReLU + MaxPool forward
+template <typename T>
 struct BnFwdParams {
-  const __nv_bfloat16* y;   // [P][C] conv output (pre-BN)
+  const T* y;               // [P][C] conv output (pre-BN)
   const float* sum;         // [C]
   const float* sumsq;       // [C]
   const float* gamma;
@@ -96,7 +114,7 @@ struct BnFwdParams {
   long long* num_batches_tracked;
   float* save_mean;         // [C]
   float* save_invstd;       // [C]
-  __nv_bfloat16* out;       // [P or P/4][C]   (may be a peer pointer: cut-edge mailbox slot)
+  T* out;                   // [P or P/4][C]   (may be a peer pointer: cut-edge mailbox slot)
   int P, C, H, W;
   int relu, pool;
   float momentum, eps;
@@ -108,7 +126,8 @@ struct BnFwdParams {
   uint32_t* hint;
 };
 
-__global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const BnFwdParams p) {
+template <typename T>
+__global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const BnFwdParams<T> p) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float s_aff[];     // scale[C], shift[C]
@@ -148,7 +167,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const BnFwdParams
     for (int j = 0; j < 8; ++j) { sc[j] = s_scale[g * 8 + j]; sh[j] = s_shift[g * 8 + j]; }
     if (!p.pool) {
       float f[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(p.y + op * p.C + g * 8), f);
+      load8(p.y + op * p.C + g * 8, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float z = fmaf(f[j], sc[j], sh[j]);
@@ -166,7 +185,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const BnFwdParams
       for (int q = 0; q < 4; ++q) {
         const long long ip = base + (q >> 1) * p.W + (q & 1);
         float f[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(p.y + ip * p.C + g * 8), f);
+        load8(p.y + ip * p.C + g * 8, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float z = fmaf(f[j], sc[j], sh[j]);
@@ -175,36 +194,37 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const BnFwdParams
         }
       }
     }
-    *reinterpret_cast<bf16x8*>(p.out + op * p.C + g * 8) = pack8(r);
+    store8(p.out + op * p.C + g * 8, r);
   }
   publish_flag(p.ticket, p.flag, p.seq, p.hint);
 }
 
 // ============================================================================ BN + ReLU + MaxPool backward
+template <typename T>
 struct BnBwdParams {
-  const __nv_bfloat16* dout;   // [P or P/4][C] gradient w.r.t. the (pooled) activation  (may be a mailbox slot)
-  const __nv_bfloat16* y;      // [P][C] saved conv output
+  const T* dout;               // [P or P/4][C] gradient w.r.t. the (pooled) activation  (may be a mailbox slot)
+  const T* y;                  // [P][C] saved conv output
   const float* gamma;
   const float* beta;
   const float* save_mean;
   const float* save_invstd;
   float* dgamma;               // [C] (zeroed by caller; accumulated)
   float* dbeta;                // [C]
-  __nv_bfloat16* dy;           // [P][C] gradient w.r.t. conv output
+  T* dy;                       // [P][C] gradient w.r.t. conv output
   int P, C, H, W;
   int relu, pool;
   int identity;
 };
 
 // dz for the 1 (no pool) or 4 (pool) input pixels of output position `op`, 8 channels.
-template <bool POOL>
-__device__ __forceinline__ void bn_dz(const BnBwdParams& p, long long op, int g, const float (&sc)[8], const float (&sh)[8],
+template <bool POOL, typename T>
+__device__ __forceinline__ void bn_dz(const BnBwdParams<T>& p, long long op, int g, const float (&sc)[8], const float (&sh)[8],
                                       float (&yv)[POOL ? 4 : 1][8], float (&dz)[POOL ? 4 : 1][8], long long (&ip)[POOL ? 4 : 1]) {
   float d[8];
-  unpack8(*reinterpret_cast<const bf16x8*>(p.dout + op * p.C + g * 8), d);
+  load8(p.dout + op * p.C + g * 8, d);
   if constexpr (!POOL) {
     ip[0] = op;
-    unpack8(*reinterpret_cast<const bf16x8*>(p.y + op * p.C + g * 8), yv[0]);
+    load8(p.y + op * p.C + g * 8, yv[0]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float z = fmaf(yv[0][j], sc[j], sh[j]);
@@ -224,7 +244,7 @@ __device__ __forceinline__ void bn_dz(const BnBwdParams& p, long long op, int g,
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       ip[q] = base + (q >> 1) * p.W + (q & 1);
-      unpack8(*reinterpret_cast<const bf16x8*>(p.y + ip[q] * p.C + g * 8), yv[q]);
+      load8(p.y + ip[q] * p.C + g * 8, yv[q]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float z = fmaf(yv[q][j], sc[j], sh[j]);
@@ -240,8 +260,8 @@ __device__ __forceinline__ void bn_dz(const BnBwdParams& p, long long op, int g,
 }
 
 // pass 1: dgamma / dbeta.  blockDim = (C/8, 256/(C/8)); grid-stride over output positions.
-template <bool POOL>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
+template <bool POOL, typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams<T> p) {
   pdl_trigger();
   pdl_wait();
   constexpr int NP = POOL ? 4 : 1;
@@ -260,7 +280,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
   for (long long op = blockIdx.x * (long long)blockDim.y + threadIdx.y; op < outP; op += (long long)gridDim.x * blockDim.y) {
     float yv[NP][8], dz[NP][8];
     long long ip[NP];
-    bn_dz<POOL>(p, op, g, sc, sh, yv, dz, ip);
+    bn_dz<POOL, T>(p, op, g, sc, sh, yv, dz, ip);
 #pragma unroll
     for (int q = 0; q < NP; ++q)
 #pragma unroll
@@ -285,8 +305,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
 }
 
 // pass 2: dy = gamma*invstd*(dz - dbeta/P - xhat*dgamma/P)
-template <bool POOL>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
+template <bool POOL, typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams<T> p) {
   pdl_trigger();
   pdl_wait();
   constexpr int NP = POOL ? 4 : 1;
@@ -308,7 +328,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
   for (long long op = blockIdx.x * (long long)blockDim.y + threadIdx.y; op < outP; op += (long long)gridDim.x * blockDim.y) {
     float yv[NP][8], dz[NP][8];
     long long ip[NP];
-    bn_dz<POOL>(p, op, g, sc, sh, yv, dz, ip);
+    bn_dz<POOL, T>(p, op, g, sc, sh, yv, dz, ip);
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
       float r[8];
@@ -317,7 +337,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
         const float xhat = (yv[q][j] - mean[j]) * istd[j];
         r[j] = sc[j] * (dz[q][j] - k1[j] - xhat * k2[j]);
       }
-      *reinterpret_cast<bf16x8*>(p.dy + ip[q] * p.C + g * 8) = pack8(r);
+      store8(p.dy + ip[q] * p.C + g * 8, r);
     }
   }
 }
@@ -326,8 +346,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
 // is co-resident (<= 296 blocks of 256 threads, a few KB of smem: 8 fit per SM), so the barrier cannot dead-lock; kernels
 // of other streams that may share the SMs always terminate on their own.  grid_bar: [0] arrivals (monotonic),
 // [1] generation, [2] finish ticket — owned by one call site, zero-initialised.
-template <bool POOL>
-__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const BnBwdParams p, uint32_t* grid_bar) {
+template <bool POOL, typename T>
+__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const BnBwdParams<T> p, uint32_t* grid_bar) {
   pdl_trigger();
   pdl_wait();
   constexpr int NP = POOL ? 4 : 1;
@@ -350,7 +370,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const BnBwdParams 
   for (long long op = blockIdx.x * (long long)blockDim.y + threadIdx.y; op < outP; op += (long long)gridDim.x * blockDim.y) {
     float yv[NP][8], dz[NP][8];
     long long ip[NP];
-    bn_dz<POOL>(p, op, g, sc, sh, yv, dz, ip);
+    bn_dz<POOL, T>(p, op, g, sc, sh, yv, dz, ip);
 #pragma unroll
     for (int q = 0; q < NP; ++q)
 #pragma unroll
@@ -396,7 +416,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const BnBwdParams 
   for (long long op = blockIdx.x * (long long)blockDim.y + threadIdx.y; op < outP; op += (long long)gridDim.x * blockDim.y) {
     float yv[NP][8], dz[NP][8];
     long long ip[NP];
-    bn_dz<POOL>(p, op, g, sc, sh, yv, dz, ip);
+    bn_dz<POOL, T>(p, op, g, sc, sh, yv, dz, ip);
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
       float r[8];
@@ -405,7 +425,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const BnBwdParams 
         const float xhat = (yv[q][j] - mean[j]) * istd[j];
         r[j] = sc[j] * (dz[q][j] - k1[j] - xhat * k2[j]);
       }
-      *reinterpret_cast<bf16x8*>(p.dy + ip[q] * p.C + g * 8) = pack8(r);
+      store8(p.dy + ip[q] * p.C + g * 8, r);
     }
   }
   __syncthreads();
@@ -419,8 +439,9 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const BnBwdParams 
   }
 }
 
-// Column sums / sums of squares of a bf16 [P][C] matrix (BN statistics fallback, bias gradients).
-__global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* y, float* sum, float* sumsq, long long P, int C) {
+// Column sums / sums of squares of an activation-typed [P][C] matrix (BN statistics fallback, bias gradients).
+template <typename T>
+__global__ void __launch_bounds__(256) col_stats_kernel(const T* y, float* sum, float* sumsq, long long P, int C) {
   pdl_trigger();
   pdl_wait();
   const int g = threadIdx.x;
@@ -429,7 +450,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* y, 
   for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
   for (long long r = blockIdx.x * (long long)blockDim.y + threadIdx.y; r < P; r += (long long)gridDim.x * blockDim.y) {
     float f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(y + r * C + g * 8), f);
+    load8(y + r * C + g * 8, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a[j] += f[j]; b[j] += f[j] * f[j]; }
   }
@@ -450,7 +471,8 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* y, 
 
 // Split-K epilogue of the tcgen05 conv: y = bf16(acc + bias) and the BN statistics of the rounded values
 // (acc: fp32 [P][C] partial-sum buffer filled with red.add by the K-slices).  bias/y/sum may be null.
-__global__ void __launch_bounds__(256) conv_finalize_kernel(const float* acc, const float* bias, __nv_bfloat16* y, float* sum,
+template <typename T>
+__global__ void __launch_bounds__(256) conv_finalize_kernel(const float* acc, const float* bias, T* y, float* sum,
                                                            float* sumsq, long long P, int C) {
   pdl_trigger();
   pdl_wait();
@@ -462,11 +484,11 @@ __global__ void __launch_bounds__(256) conv_finalize_kernel(const float* acc, co
     const float4 v0 = *reinterpret_cast<const float4*>(acc + r * C + g * 8);
     const float4 v1 = *reinterpret_cast<const float4*>(acc + r * C + g * 8 + 4);
     float f[8] = {v0.x + bs[0], v0.y + bs[1], v0.z + bs[2], v0.w + bs[3], v1.x + bs[4], v1.y + bs[5], v1.z + bs[6], v1.w + bs[7]};
-    const bf16x8 pk = pack8(f);
-    *reinterpret_cast<bf16x8*>(y + r * C + g * 8) = pk;
+    store8(y + r * C + g * 8, f);
     if (sum) {
       float q[8];
-      unpack8(pk, q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[j] = to_f32(from_f32<T>(f[j]));      // statistics of the stored values
 #pragma unroll
       for (int j = 0; j < 8; ++j) { a[j] += q[j]; b[j] += q[j] * q[j]; }
     }
@@ -506,9 +528,9 @@ __device__ __forceinline__ float warp_col_reduce32e(float (&v)[32]) {
   return v[0];
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, typename T>
 __global__ void __launch_bounds__(128) conv3x3_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                               const float* __restrict__ bias, __nv_bfloat16* y,
+                                                               const float* __restrict__ bias, T* y,
                                                                float* sum, float* sumsq, int B, int H, int W) {
   pdl_trigger();
   pdl_wait();
@@ -549,18 +571,12 @@ __global__ void __launch_bounds__(128) conv3x3_small_fwd_kernel(const float* __r
       for (int k = 0; k < KK; ++k) a = fmaf(patch[k], wr[k], a);
       acc[o] = a;
     }
-    if (ok) {
-      uint4* o4 = reinterpret_cast<uint4*>(y + pix * COUT + c0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        o4[j] = make_uint4(pack_bf16x2(acc[8 * j], acc[8 * j + 1]), pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]),
-                           pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]), pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]));
-    }
+    if (ok) store_row32(y + pix * COUT + c0, acc);
     if (sum) {
       float s1[32], s2[32];
 #pragma unroll
       for (int o = 0; o < 32; ++o) {
-        const float r = ok ? __bfloat162float(__float2bfloat16(acc[o])) : 0.f;
+        const float r = ok ? stored_value(acc[o], static_cast<const T*>(nullptr)) : 0.f;
         s1[o] = r;
         s2[o] = r * r;
       }
@@ -581,8 +597,8 @@ __global__ void __launch_bounds__(128) conv3x3_small_fwd_kernel(const float* __r
 
 // dw[Cout][9*CIN] += sum_pix dy[pix][Cout] * patch[pix][9*CIN].  A block walks several 128-pixel chunks and keeps its
 // partial sums in registers, so the global reds are per block, not per chunk.
-template <int CIN>
-__global__ void __launch_bounds__(256) conv3x3_small_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+template <int CIN, typename T>
+__global__ void __launch_bounds__(256) conv3x3_small_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                                  float* dw, int B, int H, int W, int Cout) {
   pdl_trigger();
   pdl_wait();
@@ -613,7 +629,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_wgrad_kernel(const float* _
     }
     for (int i = threadIdx.x; i < 128 * Cout; i += blockDim.x) {
       const long long pix = pix0 + i / Cout;
-      s_dy[i] = pix < P ? __bfloat162float(dy[pix * Cout + (i % Cout)]) : 0.f;
+      s_dy[i] = pix < P ? to_f32(dy[pix * Cout + (i % Cout)]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -641,8 +657,9 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t a, uint32_t b, uint32_t c)
   h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
   return h;
 }
-// out[b][n] = dropout(relu(acc[b][n] + bias[n]))  -> bf16 (ld = ldo) ; also keeps fp32 logits when out_f32 != null
-__global__ void linear_finalize_kernel(const float* acc, const float* bias, __nv_bfloat16* out, float* out_f32, uint8_t* mask,
+// out[b][n] = dropout(relu(acc[b][n] + bias[n]))  -> activation type (ld = ldo) ; also keeps fp32 logits when out_f32 != null
+template <typename T>
+__global__ void linear_finalize_kernel(const float* acc, const float* bias, T* out, float* out_f32, uint8_t* mask,
                                        int B, int N, int ldo, int relu, float drop_p, uint32_t seed, const uint32_t* step_ptr) {
   pdl_trigger();
   pdl_wait();
@@ -659,14 +676,15 @@ __global__ void linear_finalize_kernel(const float* acc, const float* bias, __nv
       mask[i] = keep ? 1 : 0;
       v = keep ? v * keep_scale : 0.f;
     }
-    if (out) out[(long long)b * ldo + n] = __float2bfloat16(v);
+    if (out) out[(long long)b * ldo + n] = from_f32<T>(v);
     if (out_f32) out_f32[i] = v;
   }
 }
 // dz[b][n] = dy[b][n] * dropmask * (relu ? y>0 : 1)  (bf16, ld = ldz) ; db[n] = sum_b dz[b][n] (bf16-rounded values)
 // blockDim = (32 columns, 8 row groups): rows are split over threadIdx.y, the bias gradient is combined in smem
-__global__ void __launch_bounds__(256) linear_bwd_prep_kernel(const float* dacc, const __nv_bfloat16* yout, const uint8_t* mask,
-                                                             __nv_bfloat16* dz, float* dbias, int B, int N, int ldy, int ldz,
+template <typename T>
+__global__ void __launch_bounds__(256) linear_bwd_prep_kernel(const float* dacc, const T* yout, const uint8_t* mask,
+                                                             T* dz, float* dbias, int B, int N, int ldy, int ldz,
                                                              int relu, float drop_p) {
   pdl_trigger();
   pdl_wait();
@@ -678,10 +696,10 @@ __global__ void __launch_bounds__(256) linear_bwd_prep_kernel(const float* dacc,
     for (int b = threadIdx.y; b < B; b += 8) {
       float g = dacc[(long long)b * N + n];
       if (drop_p > 0.f) g = mask[(long long)b * N + n] ? g * keep_scale : 0.f;
-      if (relu && !(__bfloat162float(yout[(long long)b * ldy + n]) > 0.f)) g = 0.f;
-      const __nv_bfloat16 r = __float2bfloat16(g);
+      if (relu && !(to_f32(yout[(long long)b * ldy + n]) > 0.f)) g = 0.f;
+      const T r = from_f32<T>(g);
       dz[(long long)b * ldz + n] = r;
-      s += __bfloat162float(r);
+      s += to_f32(r);
     }
   }
   s_part[threadIdx.y][threadIdx.x] = s;
@@ -693,8 +711,9 @@ __global__ void __launch_bounds__(256) linear_bwd_prep_kernel(const float* dacc,
     dbias[n] = t;
   }
 }
-// bf16 dropout on a dense activation (VGG layer 46) and its backward
-__global__ void dropout_fwd_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* mask, long long n, float p, uint32_t seed,
+// dropout on a dense activation (VGG layer 46) and its backward
+template <typename T>
+__global__ void dropout_fwd_kernel(const T* x, T* y, uint8_t* mask, long long n, float p, uint32_t seed,
                                    const uint32_t* step_ptr) {
   pdl_trigger();
   pdl_wait();
@@ -704,15 +723,250 @@ __global__ void dropout_fwd_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, uin
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const bool keep = hash_u32(seed, step, static_cast<uint32_t>(i)) >= thresh;
     mask[i] = keep ? 1 : 0;
-    y[i] = __float2bfloat16(keep ? __bfloat162float(x[i]) * ks : 0.f);
+    y[i] = from_f32<T>(keep ? to_f32(x[i]) * ks : 0.f);
   }
 }
-__global__ void dropout_bwd_kernel(const float* dacc, const uint8_t* mask, __nv_bfloat16* dx, long long n, float p) {
+template <typename T>
+__global__ void dropout_bwd_kernel(const float* dacc, const uint8_t* mask, T* dx, long long n, float p) {
   pdl_trigger();
   pdl_wait();
   const float ks = 1.f / (1.f - p);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dx[i] = __float2bfloat16((mask == nullptr || mask[i]) ? dacc[i] * (mask ? ks : 1.f) : 0.f);
+    dx[i] = from_f32<T>((mask == nullptr || mask[i]) ? dacc[i] * (mask ? ks : 1.f) : 0.f);
+}
+
+
+// ============================================================================ fp32 Linear on the CUDA cores (parity mode)
+// The reference runs nn.Linear as a plain fp32 cuBLAS GEMM (PyTorch keeps TF32 off for matmuls, SURVEY §2.7 note), so
+// the parity mode computes the classifier with IEEE fp32 FMAs.  At microbatch 32 these layers are weight-streaming ops
+// (16 FLOP per weight byte): the kernels below read every weight exactly once with 16-byte coalesced loads and keep the
+// whole batch tile in registers / shared memory.
+
+// acc[b][n] (+)= sum_{k in slice} x[b][k] * w[n][k]            grid (ceil(N/32), ceil(K/kc), ceil(B/32)), 256 threads
+// warp = (feature group of 8) x (batch half of 16); lanes stride K in float4 steps; partial sums are reduced across the
+// warp with the register butterfly and added to `acc` (zeroed by the caller) with one atomic per (b, n) per slice.
+__global__ void __launch_bounds__(256) linear_fwd_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            float* acc, int B, int N, int K, int ldx, int ldw, int lda, int kc) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) float s_x[32 * 128];                 // [b][128 k] of the current step
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int fg = warp >> 1, bh = warp & 1;
+  const int n0 = blockIdx.x * 32 + fg * 8;
+  const int k_begin = blockIdx.y * kc, k_end = min(K, k_begin + kc);
+  const int b0 = blockIdx.z * 32;
+  float a[4][32];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[q][j] = 0.f;
+  const int steps = (k_end - k_begin + 127) / 128;
+  float4 xr[4], wr[8];
+  auto fetch = [&](int step) {
+    const int kb = k_begin + step * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = threadIdx.x + i * 256, b = e >> 5, c = (e & 31) * 4;
+      xr[i] = (b0 + b < B && kb + c < k_end) ? __ldg(reinterpret_cast<const float4*>(x + (long long)(b0 + b) * ldx + kb + c))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int f = 0; f < 8; ++f)
+      wr[f] = (n0 + f < N && kb + 4 * lane < k_end) ? __ldcs(reinterpret_cast<const float4*>(w + (long long)(n0 + f) * ldw + kb + 4 * lane))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  if (steps > 0) fetch(0);
+  for (int step = 0; step < steps; ++step) {
+    __syncthreads();                                             // previous step's readers are done with s_x
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = threadIdx.x + i * 256;
+      *reinterpret_cast<float4*>(s_x + (e >> 5) * 128 + (e & 31) * 4) = xr[i];
+    }
+    float4 wc[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) wc[f] = wr[f];
+    __syncthreads();
+    if (step + 1 < steps) fetch(step + 1);                       // next step's global loads fly during the FMAs
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      const float4 xv = *reinterpret_cast<const float4*>(s_x + (bh * 16 + b) * 128 + 4 * lane);
+#pragma unroll
+      for (int f = 0; f < 8; ++f) {
+        float t = a[f >> 1][(f & 1) * 16 + b];
+        t = fmaf(wc[f].x, xv.x, t); t = fmaf(wc[f].y, xv.y, t); t = fmaf(wc[f].z, xv.z, t); t = fmaf(wc[f].w, xv.w, t);
+        a[f >> 1][(f & 1) * 16 + b] = t;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float v = warp_col_reduce32e(a[q]);                    // lane j: sum over lanes of a[q][j]
+    const int f = 2 * q + (lane >> 4), b = b0 + bh * 16 + (lane & 15);
+    if (n0 + f < N && b < B) atomicAdd(acc + (long long)b * lda + n0 + f, v);
+  }
+}
+
+// dacc[b][k] += sum_{n in slice} dz[b][n] * w[n][k]            grid (ceil(K/(4*T)), ceil(N/nc), ceil(B/32)), T threads
+// a thread owns 4 consecutive k for the whole batch tile (128 accumulators); the dz slice sits in shared memory as
+// [n][32 b] and is read with warp-broadcast 16-byte loads; weights stream through with coalesced float4 loads.
+__global__ void __launch_bounds__(128) linear_dgrad_f32_kernel(const float* __restrict__ dz, const float* __restrict__ w, float* dacc,
+                                                              int B, int N, int K, int lddz, int ldw, int ldd, int nc) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float s_dz[];                  // [nc][32]
+  const int n_begin = blockIdx.y * nc, n_cnt = min(nc, N - n_begin);
+  const int b0 = blockIdx.z * 32;
+  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  for (int i = threadIdx.x; i < nc * 32; i += blockDim.x) {
+    const int nn = i >> 5, b = i & 31;
+    s_dz[i] = (nn < n_cnt && b0 + b < B) ? dz[(long long)(b0 + b) * lddz + n_begin + nn] : 0.f;
+  }
+  __syncthreads();
+  if (k0 >= K) return;
+  float a[32][4];
+#pragma unroll
+  for (int b = 0; b < 32; ++b) { a[b][0] = a[b][1] = a[b][2] = a[b][3] = 0.f; }
+  const float* wp = w + (long long)n_begin * ldw + k0;
+  int nn = 0;
+  for (; nn + 4 <= n_cnt; nn += 4) {
+    float4 wv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) wv[u] = __ldcs(reinterpret_cast<const float4*>(wp + (long long)(nn + u) * ldw));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 d = *reinterpret_cast<const float4*>(s_dz + (nn + u) * 32 + q * 4);
+        const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          a[q * 4 + t][0] = fmaf(dd[t], wv[u].x, a[q * 4 + t][0]);
+          a[q * 4 + t][1] = fmaf(dd[t], wv[u].y, a[q * 4 + t][1]);
+          a[q * 4 + t][2] = fmaf(dd[t], wv[u].z, a[q * 4 + t][2]);
+          a[q * 4 + t][3] = fmaf(dd[t], wv[u].w, a[q * 4 + t][3]);
+        }
+      }
+    }
+  }
+  for (; nn < n_cnt; ++nn) {
+    const float4 wv = __ldcs(reinterpret_cast<const float4*>(wp + (long long)nn * ldw));
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const float d = s_dz[nn * 32 + b];
+      a[b][0] = fmaf(d, wv.x, a[b][0]); a[b][1] = fmaf(d, wv.y, a[b][1]);
+      a[b][2] = fmaf(d, wv.z, a[b][2]); a[b][3] = fmaf(d, wv.w, a[b][3]);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 32; ++b)
+    if (b0 + b < B)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dacc + (long long)(b0 + b) * ldd + k0), "f"(a[b][0]),
+                   "f"(a[b][1]), "f"(a[b][2]), "f"(a[b][3])
+                   : "memory");
+}
+
+// g[n][k] = sum_b dz[b][n] * x[b][k]  (K = batch: the weight gradient is written exactly once, so the optimizer step
+// rides on it).  A thread owns 4 consecutive k, keeps x[32 b][4 k] in registers and walks `nr` rows n.
+//   mode 0: G[n][k]  = g          mode 1: G[n][k] += g        (plain gradient, e.g. for clip-grad-norm / batch > 32)
+//   mode 2: m = mu*m + g ; p -= lr*m   — fused SGD-momentum (torch.optim.SGD semantics); G is not touched at all,
+//           which removes the gradient write + the optimizer's gradient read/zero from the 134 MB classifier update.
+// The bias rows of the block (gradient produced by linear_bwd_prep) are updated by the blockIdx.x == 0 column in mode 2.
+__global__ void __launch_bounds__(128) linear_wgrad_f32_kernel(const float* __restrict__ dz, const float* __restrict__ x, float* G,
+                                                              float* P, float* M, float* bias_p, float* bias_m, float* bias_g,
+                                                              int B, int b0, int N, int K, int lddz, int ldx, int ld, int nr,
+                                                              int mode, float lr, float mu) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float s_dz[];                  // [nr][32]
+  const int n_begin = blockIdx.y * nr, n_cnt = min(nr, N - n_begin);
+  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  for (int i = threadIdx.x; i < nr * 32; i += blockDim.x) {
+    const int nn = i >> 5, b = i & 31;
+    s_dz[i] = (nn < n_cnt && b0 + b < B) ? dz[(long long)(b0 + b) * lddz + n_begin + nn] : 0.f;
+  }
+  if (mode == 2 && blockIdx.x == 0 && bias_p != nullptr && threadIdx.x < n_cnt) {
+    const int n = n_begin + threadIdx.x;
+    const float mb = __fadd_rn(__fmul_rn(mu, bias_m[n]), bias_g[n]);
+    bias_m[n] = mb;
+    bias_p[n] = __fmaf_rn(-lr, mb, bias_p[n]);
+    bias_g[n] = 0.f;
+  }
+  __syncthreads();
+  if (k0 >= K) return;
+  float4 xv[32];
+#pragma unroll
+  for (int b = 0; b < 32; ++b)
+    xv[b] = (b0 + b < B) ? __ldg(reinterpret_cast<const float4*>(x + (long long)(b0 + b) * ldx + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long base = (long long)n_begin * ld + k0;
+  float4 pc = make_float4(0.f, 0.f, 0.f, 0.f), mc = pc;
+  if (mode == 2 && n_cnt > 0) { pc = *reinterpret_cast<const float4*>(P + base); mc = *reinterpret_cast<const float4*>(M + base); }
+  if (mode == 1 && n_cnt > 0) pc = *reinterpret_cast<const float4*>(G + base);
+  for (int nn = 0; nn < n_cnt; ++nn) {
+    const long long off = base + (long long)nn * ld;
+    float4 pn = pc, mn = mc;
+    if (nn + 1 < n_cnt) {                                         // next row's optimizer state is in flight during the FMAs
+      if (mode == 2) { pn = *reinterpret_cast<const float4*>(P + off + ld); mn = *reinterpret_cast<const float4*>(M + off + ld); }
+      if (mode == 1) pn = *reinterpret_cast<const float4*>(G + off + ld);
+    }
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 d = *reinterpret_cast<const float4*>(s_dz + nn * 32 + q * 4);
+      const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        g.x = fmaf(dd[t], xv[q * 4 + t].x, g.x); g.y = fmaf(dd[t], xv[q * 4 + t].y, g.y);
+        g.z = fmaf(dd[t], xv[q * 4 + t].z, g.z); g.w = fmaf(dd[t], xv[q * 4 + t].w, g.w);
+      }
+    }
+    if (mode == 2) {
+      mc.x = __fadd_rn(__fmul_rn(mu, mc.x), g.x); mc.y = __fadd_rn(__fmul_rn(mu, mc.y), g.y);      // same rounding
+      mc.z = __fadd_rn(__fmul_rn(mu, mc.z), g.z); mc.w = __fadd_rn(__fmul_rn(mu, mc.w), g.w);      // sequence as
+      pc.x = __fmaf_rn(-lr, mc.x, pc.x); pc.y = __fmaf_rn(-lr, mc.y, pc.y);                        // sgd_momentum_kernel
+      pc.z = __fmaf_rn(-lr, mc.z, pc.z); pc.w = __fmaf_rn(-lr, mc.w, pc.w);
+      *reinterpret_cast<float4*>(M + off) = mc;
+      *reinterpret_cast<float4*>(P + off) = pc;
+    } else if (mode == 1) {
+      *reinterpret_cast<float4*>(G + off) = make_float4(pc.x + g.x, pc.y + g.y, pc.z + g.z, pc.w + g.w);
+    } else {
+      *reinterpret_cast<float4*>(G + off) = g;
+    }
+    pc = pn; mc = mn;
+  }
+}
+
+// sum of squares of a flat fp32 buffer (gradient norm for clip-grad-norm), accumulated into *out (zeroed by the caller)
+__global__ void __launch_bounds__(256) sumsq_kernel(const float4* g, long long n4, float* out) {
+  pdl_trigger();
+  pdl_wait();
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = g[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k];
+    atomicAdd(out, t);
+  }
+}
+// g *= min(1, max_norm / (sqrt(*sumsq) + 1e-6))   (torch.nn.utils.clip_grad_norm_)
+__global__ void __launch_bounds__(256) clip_scale_kernel(float4* g, long long n4, const float* sumsq, float max_norm) {
+  pdl_trigger();
+  pdl_wait();
+  const float c = fminf(1.f, max_norm / (sqrtf(*sumsq) + 1e-6f));
+  if (c >= 1.f) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = g[i];
+    v.x *= c; v.y *= c; v.z *= c; v.w *= c;
+    g[i] = v;
+  }
 }
 
 // ============================================================================ cross-entropy forward + backward
@@ -754,9 +1008,15 @@ __global__ void sgd_momentum_kernel(float4* p, float4* g, float4* m, uint2* p_bf
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 gi = g[i];
     float4 mi = m[i], pi = p[i];
+    // Rounding sequence of torch.optim.SGD (foreach): buf.mul_(mu) [rounded], buf.add_(g) [rounded], p.add_(buf, alpha=-lr)
+    // [one fused multiply-add] -> the update is bitwise identical to the reference optimizer.
     if (first_step) { mi = gi; }            // torch initialises the buffer with the first gradient
-    else { mi.x = fmaf(mu, mi.x, gi.x); mi.y = fmaf(mu, mi.y, gi.y); mi.z = fmaf(mu, mi.z, gi.z); mi.w = fmaf(mu, mi.w, gi.w); }
-    pi.x -= lr * mi.x; pi.y -= lr * mi.y; pi.z -= lr * mi.z; pi.w -= lr * mi.w;
+    else {
+      mi.x = __fadd_rn(__fmul_rn(mu, mi.x), gi.x); mi.y = __fadd_rn(__fmul_rn(mu, mi.y), gi.y);
+      mi.z = __fadd_rn(__fmul_rn(mu, mi.z), gi.z); mi.w = __fadd_rn(__fmul_rn(mu, mi.w), gi.w);
+    }
+    pi.x = __fmaf_rn(-lr, mi.x, pi.x); pi.y = __fmaf_rn(-lr, mi.y, pi.y);
+    pi.z = __fmaf_rn(-lr, mi.z, pi.z); pi.w = __fmaf_rn(-lr, mi.w, pi.w);
     m[i] = mi;
     p[i] = pi;
     g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -871,19 +1131,29 @@ using namespace slb;
 extern "C" {
 
 int slb_preload_elementwise() {
+  using bf = __nv_bfloat16;
   cudaFuncAttributes a;
   int bad = 0;
 #define SLB_PRELOAD(k) bad += (cudaFuncGetAttributes(&a, k) != cudaSuccess)
+#define SLB_PRELOAD_T(T) \
+  { auto k = bn_relu_pool_fwd_kernel<T>; SLB_PRELOAD(k); } \
+  { auto k = bn_bwd_reduce_kernel<true, T>; SLB_PRELOAD(k); } { auto k = bn_bwd_reduce_kernel<false, T>; SLB_PRELOAD(k); } \
+  { auto k = bn_bwd_apply_kernel<true, T>; SLB_PRELOAD(k); } { auto k = bn_bwd_apply_kernel<false, T>; SLB_PRELOAD(k); } \
+  { auto k = bn_bwd_fused_kernel<true, T>; SLB_PRELOAD(k); } { auto k = bn_bwd_fused_kernel<false, T>; SLB_PRELOAD(k); } \
+  { auto k = col_stats_kernel<T>; SLB_PRELOAD(k); } { auto k = conv_finalize_kernel<T>; SLB_PRELOAD(k); } \
+  { auto k = conv3x3_small_fwd_kernel<3, 64, T>; SLB_PRELOAD(k); } { auto k = conv3x3_small_fwd_kernel<1, 64, T>; SLB_PRELOAD(k); } \
+  { auto k = conv3x3_small_fwd_kernel<3, 32, T>; SLB_PRELOAD(k); } { auto k = conv3x3_small_fwd_kernel<1, 32, T>; SLB_PRELOAD(k); } \
+  { auto k = conv3x3_small_wgrad_kernel<3, T>; SLB_PRELOAD(k); } { auto k = conv3x3_small_wgrad_kernel<1, T>; SLB_PRELOAD(k); } \
+  { auto k = linear_finalize_kernel<T>; SLB_PRELOAD(k); } { auto k = linear_bwd_prep_kernel<T>; SLB_PRELOAD(k); } \
+  { auto k = dropout_fwd_kernel<T>; SLB_PRELOAD(k); } { auto k = dropout_bwd_kernel<T>; SLB_PRELOAD(k); }
+  SLB_PRELOAD_T(bf)
+  SLB_PRELOAD_T(float)
   SLB_PRELOAD(zero_kernel); SLB_PRELOAD(wait_flag_kernel); SLB_PRELOAD(set_flag_kernel); SLB_PRELOAD(counter_inc_kernel);
-  SLB_PRELOAD(bn_relu_pool_fwd_kernel); SLB_PRELOAD(bn_bwd_reduce_kernel<true>); SLB_PRELOAD(bn_bwd_reduce_kernel<false>);
-  SLB_PRELOAD(bn_bwd_apply_kernel<true>); SLB_PRELOAD(bn_bwd_apply_kernel<false>); SLB_PRELOAD(col_stats_kernel);
-  SLB_PRELOAD(bn_bwd_fused_kernel<true>); SLB_PRELOAD(bn_bwd_fused_kernel<false>);
-  SLB_PRELOAD(conv_finalize_kernel); { auto k1 = conv3x3_small_fwd_kernel<3, 64>; SLB_PRELOAD(k1); auto k2 = conv3x3_small_fwd_kernel<1, 64>; SLB_PRELOAD(k2);
-    auto k3 = conv3x3_small_fwd_kernel<3, 32>; SLB_PRELOAD(k3); auto k4 = conv3x3_small_fwd_kernel<1, 32>; SLB_PRELOAD(k4); }
-  SLB_PRELOAD(conv3x3_small_wgrad_kernel<3>); SLB_PRELOAD(conv3x3_small_wgrad_kernel<1>); SLB_PRELOAD(linear_finalize_kernel);
-  SLB_PRELOAD(linear_bwd_prep_kernel); SLB_PRELOAD(dropout_fwd_kernel); SLB_PRELOAD(dropout_bwd_kernel);
+  SLB_PRELOAD(linear_fwd_f32_kernel); SLB_PRELOAD(linear_dgrad_f32_kernel); SLB_PRELOAD(linear_wgrad_f32_kernel);
+  SLB_PRELOAD(sumsq_kernel); SLB_PRELOAD(clip_scale_kernel);
   SLB_PRELOAD(ce_fwd_bwd_kernel); SLB_PRELOAD(sgd_momentum_kernel); SLB_PRELOAD(adamw_kernel); SLB_PRELOAD(cast_f32_bf16_kernel);
   SLB_PRELOAD(fedavg_kernel); SLB_PRELOAD(image_batch_kernel);
+#undef SLB_PRELOAD_T
 #undef SLB_PRELOAD
   return bad;
 }
@@ -912,29 +1182,45 @@ int slb_counter_inc(uint32_t* c, cudaStream_t st) {
   return last_err();
 }
 
+// dtype everywhere below: 0 = bf16 activations, 1 = fp32 activations (parity mode)
+}  // extern "C"
+template <typename T>
+static int bn_fwd_t(const void* y, const float* sum, const float* sumsq, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* nbt, float* save_mean, float* save_invstd,
+                    void* out, int P, int C, int H, int W, int relu, int pool, float momentum, float eps,
+                    int update_running, int identity, uint32_t* ticket, uint32_t* flag, uint32_t* seq, uint32_t* hint,
+                    cudaStream_t st) {
+  BnFwdParams<T> p = {reinterpret_cast<const T*>(y), sum, sumsq, gamma, beta, running_mean, running_var, nbt,
+                      save_mean, save_invstd, reinterpret_cast<T*>(out), P, C, H, W, relu, pool, momentum, eps,
+                      update_running, identity, ticket, flag, seq, hint};
+  const long long work = (pool ? (long long)P / 4 : P) * (C / 8);
+  launch_k(bn_relu_pool_fwd_kernel<T>, grid_for(work, 256, 148 * 4), 256, 2 * C * sizeof(float), st, p);
+  return last_err();
+}
+extern "C" {
 int slb_bn_relu_pool_fwd(const void* y, const float* sum, const float* sumsq, const float* gamma, const float* beta,
                          float* running_mean, float* running_var, long long* nbt, float* save_mean, float* save_invstd,
                          void* out, int P, int C, int H, int W, int relu, int pool, float momentum, float eps,
                          int update_running, int identity, uint32_t* ticket, uint32_t* flag, uint32_t* seq, uint32_t* hint,
-                         cudaStream_t st) {
+                         int dtype, cudaStream_t st) {
   if (C % 8) return -1;
-  BnFwdParams p = {reinterpret_cast<const __nv_bfloat16*>(y), sum, sumsq, gamma, beta, running_mean, running_var, nbt,
-                   save_mean, save_invstd, reinterpret_cast<__nv_bfloat16*>(out), P, C, H, W, relu, pool, momentum, eps,
-                   update_running, identity, ticket, flag, seq, hint};
-  const long long work = (pool ? (long long)P / 4 : P) * (C / 8);
-  launch_k(bn_relu_pool_fwd_kernel, grid_for(work, 256, 148 * 4), 256, 2 * C * sizeof(float), st, p);
-  return last_err();
+  if (dtype == 1)
+    return bn_fwd_t<float>(y, sum, sumsq, gamma, beta, running_mean, running_var, nbt, save_mean, save_invstd, out, P, C, H, W,
+                           relu, pool, momentum, eps, update_running, identity, ticket, flag, seq, hint, st);
+  return bn_fwd_t<__nv_bfloat16>(y, sum, sumsq, gamma, beta, running_mean, running_var, nbt, save_mean, save_invstd, out, P, C,
+                                 H, W, relu, pool, momentum, eps, update_running, identity, ticket, flag, seq, hint, st);
 }
 
-int slb_bn_relu_pool_bwd(const void* dout, const void* y, const float* gamma, const float* beta, const float* save_mean,
-                         const float* save_invstd, float* dgamma, float* dbeta, void* dy, int P, int C, int H, int W, int relu,
-                         int pool, int identity, uint32_t* grid_bar, cudaStream_t st) {
-  if (C % 8 || C > 2048) return -1;
+}  // extern "C"
+template <typename T>
+static int bn_bwd_t(const void* dout, const void* y, const float* gamma, const float* beta, const float* save_mean,
+                    const float* save_invstd, float* dgamma, float* dbeta, void* dy, int P, int C, int H, int W, int relu,
+                    int pool, int identity, uint32_t* grid_bar, cudaStream_t st) {
   // identity == 2: dgamma / dbeta already hold the reduction (done by the downstream dgrad epilogue) -> apply pass only
   const bool skip_reduce = identity == 2;
   if (skip_reduce) { identity = 0; grid_bar = nullptr; }
-  BnBwdParams p = {reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(y), gamma, beta,
-                   save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dy), P, C, H, W, relu, pool, identity};
+  BnBwdParams<T> p = {reinterpret_cast<const T*>(dout), reinterpret_cast<const T*>(y), gamma, beta,
+                      save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<T*>(dy), P, C, H, W, relu, pool, identity};
   const int tx = C / 8;
   const int ty = tx >= 256 ? 1 : 256 / tx;
   dim3 block(tx, ty);
@@ -947,95 +1233,192 @@ int slb_bn_relu_pool_bwd(const void* dout, const void* y, const float* gamma, co
       int per_sm = 0, dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      if (pool) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<true>, 256, 2 * 2048 * sizeof(float));
-      else      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<false>, 256, 2 * 2048 * sizeof(float));
+      if (pool) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<true, T>, 256, 2 * 2048 * sizeof(float));
+      else      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<false, T>, 256, 2 * 2048 * sizeof(float));
       if (per_sm < 1) per_sm = 1;
       if (per_sm > 2) per_sm = 2;
       cap[pool ? 1 : 0] = (sms > 8 ? sms - 4 : sms) * per_sm;
     }
     const int g2 = grid < cap[pool ? 1 : 0] ? grid : cap[pool ? 1 : 0];
-    if (pool) launch_k(bn_bwd_fused_kernel<true>, g2, block, 2 * C * sizeof(float), st, p, grid_bar);
-    else      launch_k(bn_bwd_fused_kernel<false>, g2, block, 2 * C * sizeof(float), st, p, grid_bar);
+    if (pool) launch_k(bn_bwd_fused_kernel<true, T>, g2, block, 2 * C * sizeof(float), st, p, grid_bar);
+    else      launch_k(bn_bwd_fused_kernel<false, T>, g2, block, 2 * C * sizeof(float), st, p, grid_bar);
     return last_err();
   }
   if (pool) {
-    if (!identity && !skip_reduce) launch_k(bn_bwd_reduce_kernel<true>, grid, block, 2 * C * sizeof(float), st, p);
-    launch_k(bn_bwd_apply_kernel<true>, grid, block, 0, st, p);
+    if (!identity && !skip_reduce) launch_k(bn_bwd_reduce_kernel<true, T>, grid, block, 2 * C * sizeof(float), st, p);
+    launch_k(bn_bwd_apply_kernel<true, T>, grid, block, 0, st, p);
   } else {
-    if (!identity && !skip_reduce) launch_k(bn_bwd_reduce_kernel<false>, grid, block, 2 * C * sizeof(float), st, p);
-    launch_k(bn_bwd_apply_kernel<false>, grid, block, 0, st, p);
+    if (!identity && !skip_reduce) launch_k(bn_bwd_reduce_kernel<false, T>, grid, block, 2 * C * sizeof(float), st, p);
+    launch_k(bn_bwd_apply_kernel<false, T>, grid, block, 0, st, p);
   }
   return last_err();
 }
-
-int slb_conv_finalize(const float* acc, const float* bias, void* y, float* sum, float* sumsq, long long P, int C, cudaStream_t st) {
-  if (C % 8) return -1;
-  const int tx = C / 8, ty = tx >= 256 ? 1 : 256 / tx;
-  launch_k(conv_finalize_kernel, grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st, 
-      acc, bias, reinterpret_cast<__nv_bfloat16*>(y), sum, sumsq, P, C);
-  return last_err();
-}
-int slb_col_stats(const void* y, float* sum, float* sumsq, long long P, int C, cudaStream_t st) {
-  if (C % 8) return -1;
-  const int tx = C / 8, ty = tx >= 256 ? 1 : 256 / tx;
-  launch_k(col_stats_kernel, grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st, 
-      reinterpret_cast<const __nv_bfloat16*>(y), sum, sumsq, P, C);
-  return last_err();
+extern "C" {
+int slb_bn_relu_pool_bwd(const void* dout, const void* y, const float* gamma, const float* beta, const float* save_mean,
+                         const float* save_invstd, float* dgamma, float* dbeta, void* dy, int P, int C, int H, int W, int relu,
+                         int pool, int identity, uint32_t* grid_bar, int dtype, cudaStream_t st) {
+  if (C % 8 || C > 2048) return -1;
+  if (dtype == 1)
+    return bn_bwd_t<float>(dout, y, gamma, beta, save_mean, save_invstd, dgamma, dbeta, dy, P, C, H, W, relu, pool, identity, grid_bar, st);
+  return bn_bwd_t<__nv_bfloat16>(dout, y, gamma, beta, save_mean, save_invstd, dgamma, dbeta, dy, P, C, H, W, relu, pool, identity, grid_bar, st);
 }
 
-int slb_conv3x3_small_fwd(const float* x, const float* w, const float* bias, void* y, float* sum, float* sumsq, int B, int Cin,
-                          int H, int W, int Cout, cudaStream_t st) {
+int slb_conv_finalize(const float* acc, const float* bias, void* y, float* sum, float* sumsq, long long P, int C, int dtype,
+                      cudaStream_t st) {
+  if (C % 8) return -1;
+  const int tx = C / 8, ty = tx >= 256 ? 1 : 256 / tx;
+  if (dtype == 1)
+    launch_k(conv_finalize_kernel<float>, grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st, acc, bias,
+             reinterpret_cast<float*>(y), sum, sumsq, P, C);
+  else
+    launch_k(conv_finalize_kernel<__nv_bfloat16>, grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st, acc, bias,
+             reinterpret_cast<__nv_bfloat16*>(y), sum, sumsq, P, C);
+  return last_err();
+}
+int slb_col_stats(const void* y, float* sum, float* sumsq, long long P, int C, int dtype, cudaStream_t st) {
+  if (C % 8) return -1;
+  const int tx = C / 8, ty = tx >= 256 ? 1 : 256 / tx;
+  if (dtype == 1)
+    launch_k(col_stats_kernel<float>, grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st,
+             reinterpret_cast<const float*>(y), sum, sumsq, P, C);
+  else
+    launch_k(col_stats_kernel<__nv_bfloat16>, grid_for(P, ty, 148 * 2), dim3(tx, ty), 2 * C * sizeof(float), st,
+             reinterpret_cast<const __nv_bfloat16*>(y), sum, sumsq, P, C);
+  return last_err();
+}
+
+}  // extern "C"
+template <typename T>
+static int small_fwd_t(const float* x, const float* w, const float* bias, void* y, float* sum, float* sumsq, int B, int Cin,
+                       int H, int W, int Cout, cudaStream_t st) {
   const long long P = (long long)B * H * W;
   const int grid = static_cast<int>((P + 127) / 128);
-  __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
-  if (Cin == 3 && Cout == 64) launch_k(conv3x3_small_fwd_kernel<3, 64>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
-  else if (Cin == 3 && Cout == 32) launch_k(conv3x3_small_fwd_kernel<3, 32>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
-  else if (Cin == 1 && Cout == 64) launch_k(conv3x3_small_fwd_kernel<1, 64>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
-  else if (Cin == 1 && Cout == 32) launch_k(conv3x3_small_fwd_kernel<1, 32>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
+  T* yy = reinterpret_cast<T*>(y);
+  if (Cin == 3 && Cout == 64) launch_k(conv3x3_small_fwd_kernel<3, 64, T>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
+  else if (Cin == 3 && Cout == 32) launch_k(conv3x3_small_fwd_kernel<3, 32, T>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
+  else if (Cin == 1 && Cout == 64) launch_k(conv3x3_small_fwd_kernel<1, 64, T>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
+  else if (Cin == 1 && Cout == 32) launch_k(conv3x3_small_fwd_kernel<1, 32, T>, grid, 128, 0, st, x, w, bias, yy, sum, sumsq, B, H, W);
   else return -2;
   return last_err();
 }
-int slb_conv3x3_small_wgrad(const float* x, const void* dy, float* dw, int B, int Cin, int H, int W, int Cout, cudaStream_t st) {
+extern "C" {
+int slb_conv3x3_small_fwd(const float* x, const float* w, const float* bias, void* y, float* sum, float* sumsq, int B, int Cin,
+                          int H, int W, int Cout, int dtype, cudaStream_t st) {
+  return dtype == 1 ? small_fwd_t<float>(x, w, bias, y, sum, sumsq, B, Cin, H, W, Cout, st)
+                    : small_fwd_t<__nv_bfloat16>(x, w, bias, y, sum, sumsq, B, Cin, H, W, Cout, st);
+}
+}  // extern "C"
+template <typename T>
+static int small_wgrad_t(const float* x, const void* dy, float* dw, int B, int Cin, int H, int W, int Cout, cudaStream_t st) {
   if (Cout * 9 * Cin > 2048) return -3;
   const size_t smem = (size_t)(128 * 9 * Cin + 128 * Cout) * sizeof(float);
   const long long chunks = ((long long)B * H * W + 127) / 128;
   const int grid = static_cast<int>(chunks < 74 ? chunks : 74);
-  const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(dy);
+  const T* d = reinterpret_cast<const T*>(dy);
   if (Cin == 3) {
     static bool done3 = false;
-    if (!done3) { cudaFuncSetAttribute(conv3x3_small_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done3 = true; }
-    launch_k(conv3x3_small_wgrad_kernel<3>, grid, 256, smem, st, x, d, dw, B, H, W, Cout);
+    if (!done3) { cudaFuncSetAttribute(conv3x3_small_wgrad_kernel<3, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done3 = true; }
+    launch_k(conv3x3_small_wgrad_kernel<3, T>, grid, 256, smem, st, x, d, dw, B, H, W, Cout);
   } else if (Cin == 1) {
     static bool done1 = false;
-    if (!done1) { cudaFuncSetAttribute(conv3x3_small_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done1 = true; }
-    launch_k(conv3x3_small_wgrad_kernel<1>, grid, 256, smem, st, x, d, dw, B, H, W, Cout);
+    if (!done1) { cudaFuncSetAttribute(conv3x3_small_wgrad_kernel<1, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done1 = true; }
+    launch_k(conv3x3_small_wgrad_kernel<1, T>, grid, 256, smem, st, x, d, dw, B, H, W, Cout);
   } else return -2;
   return last_err();
 }
+extern "C" {
+int slb_conv3x3_small_wgrad(const float* x, const void* dy, float* dw, int B, int Cin, int H, int W, int Cout, int dtype,
+                            cudaStream_t st) {
+  return dtype == 1 ? small_wgrad_t<float>(x, dy, dw, B, Cin, H, W, Cout, st)
+                    : small_wgrad_t<__nv_bfloat16>(x, dy, dw, B, Cin, H, W, Cout, st);
+}
 
 int slb_linear_finalize(const float* acc, const float* bias, void* out, float* out_f32, uint8_t* mask, int B, int N, int ldo,
-                        int relu, float drop_p, uint32_t seed, const uint32_t* step_ptr, cudaStream_t st) {
-  launch_k(linear_finalize_kernel, grid_for((long long)B * N, 256), 256, 0, st, acc, bias, reinterpret_cast<__nv_bfloat16*>(out), out_f32,
-                                                                         mask, B, N, ldo, relu, drop_p, seed, step_ptr);
+                        int relu, float drop_p, uint32_t seed, const uint32_t* step_ptr, int dtype, cudaStream_t st) {
+  if (dtype == 1)
+    launch_k(linear_finalize_kernel<float>, grid_for((long long)B * N, 256), 256, 0, st, acc, bias, reinterpret_cast<float*>(out),
+             out_f32, mask, B, N, ldo, relu, drop_p, seed, step_ptr);
+  else
+    launch_k(linear_finalize_kernel<__nv_bfloat16>, grid_for((long long)B * N, 256), 256, 0, st, acc, bias,
+             reinterpret_cast<__nv_bfloat16*>(out), out_f32, mask, B, N, ldo, relu, drop_p, seed, step_ptr);
   return last_err();
 }
 int slb_linear_bwd_prep(const float* dacc, const void* yout, const uint8_t* mask, void* dz, float* dbias, int B, int N, int ldy,
-                        int ldz, int relu, float drop_p, cudaStream_t st) {
-  launch_k(linear_bwd_prep_kernel, (N + 31) / 32, dim3(32, 8), 0, st, dacc, reinterpret_cast<const __nv_bfloat16*>(yout), mask,
-                                                               reinterpret_cast<__nv_bfloat16*>(dz), dbias, B, N, ldy, ldz, relu,
-                                                               drop_p);
+                        int ldz, int relu, float drop_p, int dtype, cudaStream_t st) {
+  if (dtype == 1)
+    launch_k(linear_bwd_prep_kernel<float>, (N + 31) / 32, dim3(32, 8), 0, st, dacc, reinterpret_cast<const float*>(yout), mask,
+             reinterpret_cast<float*>(dz), dbias, B, N, ldy, ldz, relu, drop_p);
+  else
+    launch_k(linear_bwd_prep_kernel<__nv_bfloat16>, (N + 31) / 32, dim3(32, 8), 0, st, dacc,
+             reinterpret_cast<const __nv_bfloat16*>(yout), mask, reinterpret_cast<__nv_bfloat16*>(dz), dbias, B, N, ldy, ldz, relu,
+             drop_p);
   return last_err();
 }
 int slb_dropout_fwd(const void* x, void* y, uint8_t* mask, long long n, float p, uint32_t seed, const uint32_t* step_ptr,
-                    cudaStream_t st) {
-  launch_k(dropout_fwd_kernel, grid_for(n, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
-                                                      mask, n, p, seed, step_ptr);
+                    int dtype, cudaStream_t st) {
+  if (dtype == 1)
+    launch_k(dropout_fwd_kernel<float>, grid_for(n, 256), 256, 0, st, reinterpret_cast<const float*>(x), reinterpret_cast<float*>(y),
+             mask, n, p, seed, step_ptr);
+  else
+    launch_k(dropout_fwd_kernel<__nv_bfloat16>, grid_for(n, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(x),
+             reinterpret_cast<__nv_bfloat16*>(y), mask, n, p, seed, step_ptr);
   return last_err();
 }
-int slb_dropout_bwd(const float* dacc, const uint8_t* mask, void* dx, long long n, float p, cudaStream_t st) {
-  launch_k(dropout_bwd_kernel, grid_for(n, 256), 256, 0, st, dacc, mask, reinterpret_cast<__nv_bfloat16*>(dx), n, p);
+int slb_dropout_bwd(const float* dacc, const uint8_t* mask, void* dx, long long n, float p, int dtype, cudaStream_t st) {
+  if (dtype == 1) launch_k(dropout_bwd_kernel<float>, grid_for(n, 256), 256, 0, st, dacc, mask, reinterpret_cast<float*>(dx), n, p);
+  else launch_k(dropout_bwd_kernel<__nv_bfloat16>, grid_for(n, 256), 256, 0, st, dacc, mask, reinterpret_cast<__nv_bfloat16*>(dx), n, p);
   return last_err();
 }
+
+// ---- fp32 Linear (CUDA cores).  K % 4 == 0 and 16-byte aligned rows required.
+int slb_linear_fwd_f32(const float* x, const float* w, float* acc, int B, int N, int K, int ldx, int ldw, int lda, cudaStream_t st) {
+  if (K % 4 || ldx % 4 || ldw % 4) return -1;
+  // K slices: enough CTAs for >= 2 waves when the layer allows, at least 128 k per slice
+  const int fgroups = (N + 31) / 32;
+  int kc = 1024;
+  while (kc > 128 && fgroups * ((K + kc - 1) / kc) < 296) kc >>= 1;
+  dim3 grid(fgroups, (K + kc - 1) / kc, (B + 31) / 32);
+  launch_k(linear_fwd_f32_kernel, grid, dim3(256), 0, st, x, w, acc, B, N, K, ldx, ldw, lda, kc);
+  return last_err();
+}
+int slb_linear_dgrad_f32(const float* dz, const float* w, float* dacc, int B, int N, int K, int lddz, int ldw, int ldd,
+                         cudaStream_t st) {
+  if (K % 4 || ldw % 4 || ldd % 4) return -1;
+  const int threads = K >= 512 ? 128 : 64;
+  const int ktiles = (K / 4 + threads - 1) / threads;
+  int nc = 256;
+  while (nc > 32 && ktiles * ((N + nc - 1) / nc) < 296) nc >>= 1;
+  dim3 grid(ktiles, (N + nc - 1) / nc, (B + 31) / 32);
+  launch_k(linear_dgrad_f32_kernel, grid, dim3(threads), (size_t)nc * 32 * sizeof(float), st, dz, w, dacc, B, N, K, lddz, ldw, ldd, nc);
+  return last_err();
+}
+// mode 0: G = g, 1: G += g, 2: fused SGD-momentum on (P, M) [+ bias rows].  Batches > 32 are looped here (mode 2 needs B <= 32).
+int slb_linear_wgrad_f32(const float* dz, const float* x, float* G, float* P, float* M, float* bias_p, float* bias_m,
+                         float* bias_g, int B, int N, int K, int lddz, int ldx, int ld, int mode, float lr, float mu,
+                         cudaStream_t st) {
+  if (K % 4 || ldx % 4 || ld % 4) return -1;
+  if (mode == 2 && B > 32) return -2;
+  const int threads = K >= 512 ? 128 : 64;
+  const int nr = 32;
+  dim3 grid((K / 4 + threads - 1) / threads, (N + nr - 1) / nr, 1);
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int m = (mode == 2) ? 2 : ((mode == 1 || b0 > 0) ? 1 : 0);
+    launch_k(linear_wgrad_f32_kernel, grid, dim3(threads), (size_t)nr * 32 * sizeof(float), st, dz, x, G, P, M, bias_p, bias_m,
+             bias_g, B, b0, N, K, lddz, ldx, ld, nr, m, lr, mu);
+  }
+  return last_err();
+}
+int slb_sumsq(const float* g, long long n, float* out, cudaStream_t st) {
+  if (n % 4) return -1;
+  launch_k(sumsq_kernel, grid_for(n / 4, 256, 148 * 8), 256, 0, st, reinterpret_cast<const float4*>(g), n / 4, out);
+  return last_err();
+}
+int slb_clip_scale(float* g, long long n, const float* sumsq, float max_norm, cudaStream_t st) {
+  if (n % 4) return -1;
+  launch_k(clip_scale_kernel, grid_for(n / 4, 256, 148 * 8), 256, 0, st, reinterpret_cast<float4*>(g), n / 4, sumsq, max_norm);
+  return last_err();
+}
+
 int slb_ce_fwd_bwd(const float* logits, const long long* labels, float* dlogits, float* loss_sum, int* nan_flag, int B, int C,
                    int ldd, cudaStream_t st) {
   launch_k(ce_fwd_bwd_kernel, (B * 32 + 127) / 128, 128, 0, st, logits, labels, dlogits, loss_sum, nan_flag, B, C, ldd);

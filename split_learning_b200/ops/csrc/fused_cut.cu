@@ -31,8 +31,8 @@ struct FusedCutParams {
   float* save_invstd;
   float* sum;               // [N] zeroed by the caller
   float* sumsq;
-  __nv_bfloat16* y;         // optional local copy of the pre-BN conv output (needed when not recomputing)
-  __nv_bfloat16* out;       // [M or M/4][N]  — mailbox slot (may be a peer pointer)
+  void* y;                  // optional local copy of the pre-BN conv output (needed when not recomputing)
+  void* out;                // [M or M/4][N]  — mailbox slot (may be a peer pointer); activation-typed (bf16 / fp32)
   int relu, pool;
   float momentum, eps;
   int update_running;
@@ -70,11 +70,13 @@ __device__ __forceinline__ float warp_col_reduce32f(float (&v)[32]) {
   return v[0];
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, typename T>
 __global__ void __launch_bounds__(192, 1)
 conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const FusedCutParams p) {
   using L = FusedSmem<BLOCK_N>;
+  using OT = OperandTraits<T>;
+  constexpr int KE = OT::KE;          // K elements (channels) per 128-byte pipeline stage: 64 bf16 / 32 tf32
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -91,7 +93,7 @@ conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int total_tiles = p.tiles_m * p.tiles_n;
   int my_tiles = 0;
   for (int t = blockIdx.x; t < total_tiles; t += G) ++my_tiles;
-  const int k_iters = 9 * (p.C >> 6);
+  const int k_iters = 9 * (p.C / KE);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -114,7 +116,7 @@ conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const int kc_per_tap = p.C >> 6;
+      const int kc_per_tap = p.C / KE;
       const int pix_per_img = p.H * p.W;
       for (int j = 0; j < my_tiles; ++j) {
         const int t = blockIdx.x + j * G;
@@ -126,15 +128,15 @@ conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           const int tap = it / kc_per_tap, kc = it - tap * kc_per_tap;
-          tma_load_4d(sa, &tmA, &full_bar[stage], kc * 64, tap % 3 - 1, h0 + tap / 3 - 1, b0);
-          tma_load_2d(sa + L::A_BYTES, &tmB, &full_bar[stage], tap * p.C + kc * 64, n0);
+          tma_load_4d(sa, &tmA, &full_bar[stage], kc * KE, tap % 3 - 1, h0 + tap / 3 - 1, b0);
+          tma_load_2d(sa + L::A_BYTES, &tmB, &full_bar[stage], tap * p.C + kc * KE, n0);
           if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    const uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, false, false);
+    const uint32_t idesc = umma_idesc(128, BLOCK_N, false, false, OT::FMT);
     int stage = 0;
     uint32_t phase = 0;
     for (int j = 0; j < my_tiles; ++j) {
@@ -146,8 +148,8 @@ conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const uint32_t b_base = a_base + L::A_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + j * BLOCK_N, umma_desc_sw128(a_base + k * 32, 16, 1024),
-                      umma_desc_sw128(b_base + k * 32, 16, 1024), idesc, (it | k) != 0 ? 1u : 0u);
+            umma_issue<T>(tmem_base + j * BLOCK_N, umma_desc_sw128(a_base + k * 32, 16, 1024),
+                          umma_desc_sw128(b_base + k * 32, 16, 1024), idesc, (it | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (it == k_iters - 1) umma_commit(&accum_bar[j]);
         }
@@ -182,13 +184,8 @@ conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           s1[i] = x;
           s2[i] = x * x;
         }
-        if (p.y != nullptr && row_ok) {
-          uint4* o4 = reinterpret_cast<uint4*>(p.y + static_cast<long long>(row) * p.N + n0 + c);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            o4[i] = make_uint4(pack_bf16x2(s1[8 * i], s1[8 * i + 1]), pack_bf16x2(s1[8 * i + 2], s1[8 * i + 3]),
-                               pack_bf16x2(s1[8 * i + 4], s1[8 * i + 5]), pack_bf16x2(s1[8 * i + 6], s1[8 * i + 7]));
-        }
+        if (p.y != nullptr && row_ok)
+          store_row32(reinterpret_cast<T*>(p.y) + static_cast<long long>(row) * p.N + n0 + c, s1);
         const float c1 = warp_col_reduce32f(s1);
         const float c2 = warp_col_reduce32f(s2);
         atomicAdd(p.sum + n0 + c + lane_id(), c1);
@@ -251,13 +248,7 @@ conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           z[i] = x;
         }
         if (!p.pool) {
-          if (row_ok) {
-            uint4* o4 = reinterpret_cast<uint4*>(p.out + static_cast<long long>(row) * p.N + n0 + c);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o4[i] = make_uint4(pack_bf16x2(z[8 * i], z[8 * i + 1]), pack_bf16x2(z[8 * i + 2], z[8 * i + 3]),
-                                 pack_bf16x2(z[8 * i + 4], z[8 * i + 5]), pack_bf16x2(z[8 * i + 6], z[8 * i + 7]));
-          }
+          if (row_ok) store_row32(reinterpret_cast<T*>(p.out) + static_cast<long long>(row) * p.N + n0 + c, z);
         } else {
           // stage the 128 x 32 activated tile, then 128 threads emit 32 pooled pixels x 32 channels
 #pragma unroll
@@ -283,8 +274,7 @@ conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const int rem = src_pix - b * pix_per_img;
             const int oh = (rem / p.W) >> 1, ow = (rem % p.W) >> 1;
             const long long opix = (static_cast<long long>(b) * OH + oh) * OW + ow;
-            *reinterpret_cast<uint4*>(p.out + opix * p.N + n0 + c + cg) =
-                make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+            store_row8(reinterpret_cast<T*>(p.out) + opix * p.N + n0 + c + cg, r);
           }
           asm volatile("bar.sync 1, 128;");
         }
@@ -335,20 +325,25 @@ static PFN_encodeTiled2 get_encode2() {
   }
   return fn;
 }
-static int encode_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                       const cuuint32_t* box) {
+static int encode_typed(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                        const cuuint32_t* box, int dtype) {
   PFN_encodeTiled2 enc = get_encode2();
   if (!enc) return -1;
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, es,
+  CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  if (dtype == 1) {                      // fp32 in memory, rounded to tf32 by the copy engine (see umma_gemm.cu)
+    const char* e = getenv("SLB200_TMAP_F32");
+    dt = (e && e[0] == '1') ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  }
+  CUresult r = enc(m, dt, rank, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
 }
 
-template <int BN>
+template <int BN, typename T>
 static int launch_fused(const CUtensorMap& a, const CUtensorMap& b, const FusedCutParams& p, int grid, cudaStream_t st) {
-  auto k = conv_bn_act_p2p_kernel<BN>;
+  auto k = conv_bn_act_p2p_kernel<BN, T>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem<BN>::TOTAL);
@@ -372,20 +367,25 @@ extern "C" {
 int slb_preload_fused() {
   cudaFuncAttributes a;
   int bad = 0;
-  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<64>) != cudaSuccess;
-  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<128>) != cudaSuccess;
-  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<256>) != cudaSuccess;
+  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<64, __nv_bfloat16>) != cudaSuccess;
+  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<128, __nv_bfloat16>) != cudaSuccess;
+  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<256, __nv_bfloat16>) != cudaSuccess;
+  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<64, float>) != cudaSuccess;
+  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<128, float>) != cudaSuccess;
+  bad += cudaFuncGetAttributes(&a, conv_bn_act_p2p_kernel<256, float>) != cudaSuccess;
   return bad;
 }
 
-// Fused cut-tail forward.  x [B,H,W,Cin] bf16, w [Cout][3][3][Cin] bf16.  `out` may be a peer pointer.
+// Fused cut-tail forward.  x [B,H,W,Cin], w [Cout][3][3][Cin], y_opt / out: bf16 (dtype 0) or fp32 (dtype 1, kind::tf32).
+// `out` may be a peer pointer.
 // `grid_bar`: 4 zero-initialised uint32 owned by this call site.  sum/sumsq: zeroed by the caller.
 int slb_conv_bn_act_p2p(const void* x, const void* w, const float* bias, const float* gamma, const float* beta,
                         float* running_mean, float* running_var, long long* nbt, float* save_mean, float* save_invstd,
                         float* sum, float* sumsq, void* y_opt, void* out, int B, int H, int W, int Cin, int Cout, int relu,
                         int pool, float momentum, float eps, int update_running, uint32_t* grid_bar, uint32_t* flag,
-                        uint32_t* seq, uint32_t* hint, int num_sms, cudaStream_t st) {
-  if (Cin % 64 || Cout % 64 || (128 % W)) return -10;
+                        uint32_t* seq, uint32_t* hint, int num_sms, int dtype, cudaStream_t st) {
+  const int esz = dtype == 1 ? 4 : 2, KE = 128 / esz;
+  if (Cin % KE || Cout % 64 || (128 % W)) return -10;
   const int M = B * H * W;
   int tw = W, rows = 128 / W, th, tb;
   if (rows <= H) { th = rows; tb = 1; } else { th = H; tb = rows / H; }
@@ -404,27 +404,35 @@ int slb_conv_bn_act_p2p(const void* x, const void* w, const float* bias, const f
   CUtensorMap ta, tbm;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
-    int r = encode_bf16(&ta, x, 4, dims, str, box);
+    cuuint64_t str[3] = {(cuuint64_t)Cin * esz, (cuuint64_t)W * Cin * esz, (cuuint64_t)H * W * Cin * esz};
+    cuuint32_t box[4] = {(cuuint32_t)KE, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+    int r = encode_typed(&ta, x, 4, dims, str, box, dtype);
     if (r) return r;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
-    cuuint64_t str[1] = {(cuuint64_t)9 * Cin * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)bn};
-    int r = encode_bf16(&tbm, w, 2, dims, str, box);
+    cuuint64_t str[1] = {(cuuint64_t)9 * Cin * esz};
+    cuuint32_t box[2] = {(cuuint32_t)KE, (cuuint32_t)bn};
+    int r = encode_typed(&tbm, w, 2, dims, str, box, dtype);
     if (r) return r;
   }
   p.bias = bias; p.gamma = gamma; p.beta = beta; p.running_mean = running_mean; p.running_var = running_var; p.nbt = nbt;
   p.save_mean = save_mean; p.save_invstd = save_invstd; p.sum = sum; p.sumsq = sumsq;
-  p.y = reinterpret_cast<__nv_bfloat16*>(y_opt); p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.y = y_opt; p.out = out;
   p.relu = relu; p.pool = pool; p.momentum = momentum; p.eps = eps; p.update_running = update_running;
   p.grid_bar = grid_bar; p.flag = flag; p.seq = seq; p.hint = hint;
+  if (dtype == 1) {
+    switch (bn) {
+      case 64: return launch_fused<64, float>(ta, tbm, p, grid, st);
+      case 128: return launch_fused<128, float>(ta, tbm, p, grid, st);
+      case 256: return launch_fused<256, float>(ta, tbm, p, grid, st);
+      default: return -3;
+    }
+  }
   switch (bn) {
-    case 64: return launch_fused<64>(ta, tbm, p, grid, st);
-    case 128: return launch_fused<128>(ta, tbm, p, grid, st);
-    case 256: return launch_fused<256>(ta, tbm, p, grid, st);
+    case 64: return launch_fused<64, __nv_bfloat16>(ta, tbm, p, grid, st);
+    case 128: return launch_fused<128, __nv_bfloat16>(ta, tbm, p, grid, st);
+    case 256: return launch_fused<256, __nv_bfloat16>(ta, tbm, p, grid, st);
     default: return -3;
   }
 }

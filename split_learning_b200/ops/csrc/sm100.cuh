@@ -132,12 +132,28 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// Instruction descriptor for kind::f16 with BF16 A/B and FP32 accumulate.
-//   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt  [15] A major (1 = MN)  [16] B major
+// MN-major operands of 32-bit types (tf32) exist in ONE shared-memory layout only: 128-byte rows swizzled in 32-byte
+// chunks, chunk ^= (row & 3) (CuTe Swizzle<2,5,2>; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), descriptor layout type 1.
+// Atom = 128 bytes of M/N x 4 k-rows (512 B): SBO = distance between 4-row groups, LBO = distance between 32-element
+// M/N groups.  (With the ordinary 16-byte-chunk SW128 layout the transposing read path returns garbage for tf32.)
+__device__ __forceinline__ uint64_t umma_desc_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;
+  return d;
+}
+// Instruction descriptor (kind::f16 / kind::tf32), FP32 accumulate.
+//   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16, 2 = tf32)  [10,13) B fmt  [15] A major (1 = MN)  [16] B major
 //   [17,23) N >> 3         [24,29) M >> 4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
          ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major) {
+  return umma_idesc(M, N, a_mn_major, b_mn_major, 1u);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -147,6 +163,42 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// kind::tf32: operands are 32-bit containers in shared memory (fp32 bit patterns; the tensor core uses sign, 8-bit
+// exponent and the 10 high mantissa bits), K = 8 per instruction (32 bytes, same byte geometry as K = 16 bf16).
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Operand-type traits of the GEMM pipelines: one K block is always one 128-byte swizzle row.
+//   KE       elements per 128 bytes (= K elements per pipeline stage, = M/N elements per MN-major group)
+//   MN_STEP  byte advance of an MN-major descriptor per MMA (UMMA_K rows of 128 bytes)
+template <typename T> struct OperandTraits;
+template <> struct OperandTraits<__nv_bfloat16> {
+  static constexpr int KE = 64;
+  static constexpr uint32_t MN_STEP = 2048, FMT = 1;
+  static constexpr bool TF32 = false;
+};
+template <> struct OperandTraits<float> {
+  static constexpr int KE = 32;
+  static constexpr uint32_t MN_STEP = 1024, FMT = 2;
+  static constexpr bool TF32 = true;
+};
+// MN-major operand descriptor for MMA number k of a stage (group = one 128-byte-wide M/N slab of KE k-rows)
+template <typename T>
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t base, int k, uint32_t group_bytes) {
+  if constexpr (OperandTraits<T>::TF32) return umma_desc_sw128_base32(base + k * OperandTraits<T>::MN_STEP, group_bytes, 512);
+  else return umma_desc_sw128(base + k * OperandTraits<T>::MN_STEP, group_bytes, 1024);
+}
+template <typename T>
+__device__ __forceinline__ void umma_issue(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  if constexpr (OperandTraits<T>::TF32) umma_tf32(d_tmem, a_desc, b_desc, idesc, acc);
+  else umma_bf16(d_tmem, a_desc, b_desc, idesc, acc);
 }
 // Arrive on an mbarrier once every previously issued tcgen05.mma has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -183,6 +235,30 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+
+// 32 consecutive output columns of one row (fp32 accumulator values) -> bf16 (64 B) or fp32 (128 B), 16-byte stores
+__device__ __forceinline__ void store_row32(__nv_bfloat16* o, const float (&f)[32]) {
+  uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                       pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+}
+__device__ __forceinline__ void store_row32(float* o, const float (&f)[32]) {
+  float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+}
+__device__ __forceinline__ void store_row8(__nv_bfloat16* o, const float (&r)[8]) {
+  *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+}
+__device__ __forceinline__ void store_row8(float* o, const float (&r)[8]) {
+  reinterpret_cast<float4*>(o)[0] = make_float4(r[0], r[1], r[2], r[3]);
+  reinterpret_cast<float4*>(o)[1] = make_float4(r[4], r[5], r[6], r[7]);
+}
+// the value a consumer will read back after the store (bf16 rounding is part of the stored activation)
+__device__ __forceinline__ float stored_value(float x, const __nv_bfloat16*) { return __bfloat162float(__float2bfloat16(x)); }
+__device__ __forceinline__ float stored_value(float x, const float*) { return x; }
 
 // host: launch with the PDL attribute (SLB200_PDL=0 disables it; the device-side waits then are no-ops)
 inline int pdl_enabled() {

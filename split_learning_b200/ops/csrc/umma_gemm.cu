@@ -12,13 +12,18 @@
 //
 // Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread MMA issue,
 // warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).  BLOCK_M = 128 (UMMA M),
-// BLOCK_K = 64 bf16 = one 128-byte swizzle row, fp32 accumulators in TMEM.
+// BLOCK_K = one 128-byte swizzle row, fp32 accumulators in TMEM.
+//
+// Two operand precisions share the pipeline (template parameter T, sm100.cuh OperandTraits):
+//   float          fp32 tensors in HBM and shared memory, tcgen05.mma kind::tf32 (the reference's precision: PyTorch
+//                  runs cuDNN convolutions on TF32 tensor cores by default, SURVEY §2.7 note), BLOCK_K = 32, fp32 outputs
+//   __nv_bfloat16  bf16 operands / outputs, kind::f16, BLOCK_K = 64 (opt-in fast mode)
 #include "sm100.cuh"
 
 namespace slb {
 
 enum { MODE_CONV = 0, MODE_WGRAD = 1, MODE_GEMM = 2 };
-enum { EPI_BF16 = 0, EPI_F32_ATOMIC = 1, EPI_F32_ATOMIC_T = 2, EPI_F32_STORE = 3 };
+enum { EPI_BF16 = 0 /* activation-typed store (bf16 or fp32) */, EPI_F32_ATOMIC = 1, EPI_F32_ATOMIC_T = 2, EPI_F32_STORE = 3 };
 
 struct GemmParams {
   // generic
@@ -46,7 +51,7 @@ struct GemmParams {
   // split-K with in-kernel finalisation: the last K-slice of a tile to finish converts the fp32 partial sums
   // (accumulated with red.add in `out`) into the bf16 result + BN statistics — no separate finalize launch.
   uint32_t* tile_counters;   // [m_tiles * n_tiles], zero at rest (self-resetting)
-  __nv_bfloat16* fin_out;    // bf16 destination [M][fin_ld]
+  void* fin_out;             // activation-typed destination [M][fin_ld]
   long long fin_ld;
   // dgrad epilogue doubling as the BatchNorm-backward reduction of the *upstream* block (whose ReLU output this dX is
   // the gradient of): col_sum += sum_p m*dX (dbeta), col_sumsq += sum_p m*dX*xhat (dgamma), m = ReLU mask recomputed
@@ -101,13 +106,13 @@ __device__ __forceinline__ float warp_col_reduce32(float (&v)[32]) {
 
 // Per-element terms of the two column reductions of an epilogue chunk (row = pixel, 32 consecutive channels):
 // BatchNorm forward statistics (x, x^2) or, with bnb_y, the BatchNorm backward sums of the upstream block.
-template <bool BNB>
+template <bool BNB, typename T>
 __device__ __forceinline__ void stat_terms(const GemmParams& p, int row, bool row_ok, int col0, const float (&f)[32],
                                            float (&s1)[32], float (&s2)[32]) {
   if (!BNB || p.bnb_y == nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float r = row_ok ? __bfloat162float(__float2bfloat16(f[j])) : 0.f;   // statistics of the stored values
+      const float r = row_ok ? stored_value(f[j], static_cast<const T*>(nullptr)) : 0.f;   // statistics of the stored values
       s1[j] = r;
       s2[j] = r * r;
     }
@@ -185,11 +190,15 @@ __device__ __forceinline__ void stat_terms(const GemmParams& p, int row, bool ro
 
 // BNB: instantiate the upstream-BatchNorm-backward epilogue (dgrad only).  A separate instantiation on purpose: with the
 // code in the common kernel every conv paid ~1.8 % (205 vs 154 registers; same-box A/B, profiles/README.md).
-template <int MODE, int BLOCK_N, bool BNB = false>
+template <int MODE, int BLOCK_N, typename T, bool BNB = false>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   using L = SmemLayout<BLOCK_N>;
+  using OT = OperandTraits<T>;
+  constexpr int KE = OT::KE;                       // K elements per stage == elements per MN-major group (128 bytes)
+  constexpr int GROUP_BYTES = KE * 128;            // one MN-major group: KE k-rows of 128 bytes
+  static_assert(!BNB || !OT::TF32, "the fused BatchNorm-backward epilogue is a bf16-only option");
   constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   pdl_trigger();                      // the next kernel may start its prologue now
   extern __shared__ uint8_t smem_raw[];
@@ -240,7 +249,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sb = sa + L::A_BYTES;
           mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           if constexpr (MODE == MODE_CONV) {
-            const int kc_per_tap = p.C >> 6;
+            const int kc_per_tap = p.C / KE;
             const int tap = it / kc_per_tap, kc = it - tap * kc_per_tap;
             int dh = tap / 3 - 1, dw = tap % 3 - 1;
             if (p.flip) { dh = -dh; dw = -dw; }
@@ -249,50 +258,51 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int b0 = m0 / pix_per_img;
             const int rem = m0 - b0 * pix_per_img;
             const int h0 = rem / p.W;
-            tma_load_4d(sa, &tmA, &full_bar[stage], kc * 64, dw, h0 + dh, b0);
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * KE, dw, h0 + dh, b0);
             if (!p.b_mn) {
-              tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.b_row_stride + kc * 64, n0);
+              tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.b_row_stride + kc * KE, n0);
             } else {
 #pragma unroll
-              for (int g = 0; g < BLOCK_N / 64; ++g)
-                tma_load_2d(sb + g * 8192, &tmB, &full_bar[stage], tap * p.b_row_stride + n0 + g * 64, kc * 64);
+              for (int g = 0; g < BLOCK_N / KE; ++g)
+                tma_load_2d(sb + g * GROUP_BYTES, &tmB, &full_bar[stage], tap * p.b_row_stride + n0 + g * KE, kc * KE);
             }
           } else if constexpr (MODE == MODE_WGRAD) {
-            // K iteration = 64 consecutive pixels starting at it*64
-            const int pix0 = it * 64;
+            // K iteration = KE consecutive pixels starting at it*KE
+            const int pix0 = it * KE;
             const int pix_per_img = p.H * p.W;
             const int b0 = pix0 / pix_per_img;
             const int rem = pix0 - b0 * pix_per_img;
             const int h0 = rem / p.W;
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const int r = m0 + g * 64;
+            for (int g = 0; g < 128 / KE; ++g) {
+              const int r = m0 + g * KE;
               const int tap = r / p.Cout, c0 = r - tap * p.Cout;
               if (tap < 9) {
                 const int dh = tap / 3 - 1, dw = tap % 3 - 1;
                 // dW[co][tap][ci] = sum_q dY[q - tap][co] * X[q][ci]
-                tma_load_4d(sa + g * 8192, &tmA, &full_bar[stage], c0, -dw, h0 - dh, b0);
+                tma_load_4d(sa + g * GROUP_BYTES, &tmA, &full_bar[stage], c0, -dw, h0 - dh, b0);
               } else {
-                // padding half-tile (9 taps is odd when Cout == 64): re-load tap 8, result is discarded
-                tma_load_4d(sa + g * 8192, &tmA, &full_bar[stage], c0, 0, h0, b0);
+                // padding group (9 * Cout is not a multiple of 128 when Cout == 64): re-load tap 8, result is discarded
+                tma_load_4d(sa + g * GROUP_BYTES, &tmA, &full_bar[stage], c0, 0, h0, b0);
               }
             }
 #pragma unroll
-            for (int g = 0; g < BLOCK_N / 64; ++g)
-              tma_load_4d(sb + g * 8192, &tmB, &full_bar[stage], n0 + g * 64, 0, h0, b0);
+            for (int g = 0; g < BLOCK_N / KE; ++g)
+              tma_load_4d(sb + g * GROUP_BYTES, &tmB, &full_bar[stage], n0 + g * KE, 0, h0, b0);
           } else {
             if (!p.a_mn) {
-              tma_load_2d(sa, &tmA, &full_bar[stage], it * 64, m0);
+              tma_load_2d(sa, &tmA, &full_bar[stage], it * KE, m0);
             } else {
 #pragma unroll
-              for (int g = 0; g < 2; ++g) tma_load_2d(sa + g * 8192, &tmA, &full_bar[stage], m0 + g * 64, it * 64);
+              for (int g = 0; g < 128 / KE; ++g)
+                tma_load_2d(sa + g * GROUP_BYTES, &tmA, &full_bar[stage], m0 + g * KE, it * KE);
             }
             if (!p.b_mn) {
-              tma_load_2d(sb, &tmB, &full_bar[stage], it * 64, n0);
+              tma_load_2d(sb, &tmB, &full_bar[stage], it * KE, n0);
             } else {
 #pragma unroll
-              for (int g = 0; g < (BLOCK_N + 63) / 64; ++g)
-                tma_load_2d(sb + g * 8192, &tmB, &full_bar[stage], n0 + g * 64, it * 64);
+              for (int g = 0; g < (BLOCK_N + KE - 1) / KE; ++g)
+                tma_load_2d(sb + g * GROUP_BYTES, &tmB, &full_bar[stage], n0 + g * KE, it * KE);
             }
           }
           if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
@@ -300,7 +310,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     } else if (warp == 1) {
       // ============================== MMA issuer ==============================
-      const uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, p.a_mn != 0, p.b_mn != 0);
+      const uint32_t idesc = umma_idesc(128, BLOCK_N, p.a_mn != 0, p.b_mn != 0, OT::FMT);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < my_iters; ++it) {
@@ -311,11 +321,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t b_base = a_base + L::A_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = p.a_mn ? umma_desc_sw128(a_base + k * 2048, 8192, 1024)
-                                       : umma_desc_sw128(a_base + k * 32, 16, 1024);
-            const uint64_t db = p.b_mn ? umma_desc_sw128(b_base + k * 2048, 8192, 1024)
-                                       : umma_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            const uint64_t da = p.a_mn ? umma_desc_mn<T>(a_base, k, GROUP_BYTES) : umma_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t db = p.b_mn ? umma_desc_mn<T>(b_base, k, GROUP_BYTES) : umma_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_issue<T>(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                  // frees this smem stage once the MMAs retire
           if (it == my_iters - 1) umma_commit(accum_bar);  // accumulator complete
@@ -359,7 +367,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.bias != nullptr && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
             f[j] = x;
           }
-          if constexpr (MODE == MODE_GEMM) {
+          if constexpr (MODE == MODE_GEMM && !OT::TF32) {
             if (p.residual != nullptr && row_store) {
               const __nv_bfloat16* rs = p.residual + row_off + col0;
               if (col0 + 32 <= p.N) {
@@ -396,21 +404,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (row_store) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
+            T* o = reinterpret_cast<T*>(p.out) + row_off + col0;
             if (col0 + 32 <= p.N) {
-              uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              store_row32(o, f);
             } else {
-              for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = __float2bfloat16(f[j]);
+              for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = static_cast<T>(f[j]);
             }
           }
           if (want_stats) {
-            // statistics of the bf16-rounded values that were stored (what the consumer normalises)
+            // statistics of the values that were stored (what the consumer normalises; bf16-rounded in bf16 mode)
             float s1[32], s2[32];
-            stat_terms<BNB>(p, row, row_ok, col0, f, s1, s2);
+            stat_terms<BNB, T>(p, row, row_ok, col0, f, s1, s2);
             const float c1 = warp_col_reduce32(s1);
             const float c2 = warp_col_reduce32(s2);
             atomicAdd(&s_stats[c + lane_id()], c1);
@@ -486,16 +490,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
             }
-            if (row_ok) {
-              uint4* o4 = reinterpret_cast<uint4*>(p.fin_out + static_cast<long long>(row) * p.fin_ld + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-            }
+            if (row_ok) store_row32(reinterpret_cast<T*>(p.fin_out) + static_cast<long long>(row) * p.fin_ld + col0, f);
             if (want_stats) {
               float s1[32], s2[32];
-              stat_terms<BNB>(p, row, row_ok, col0, f, s1, s2);
+              stat_terms<BNB, T>(p, row, row_ok, col0, f, s1, s2);
               const float c1 = warp_col_reduce32(s1);
               const float c2 = warp_col_reduce32(s2);
               atomicAdd(&s_stats[c + lane_id()], c1);
@@ -543,9 +541,18 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// bf16 tensor map, SWIZZLE_128B, inner box = 64 elements (128 B).  dims/strides innermost first.
+// Tensor map, SWIZZLE_128B, inner box = 128 bytes.  dims/strides innermost first.  fp32 operands are encoded as
+// TFLOAT32 (same 4-byte memory format; the copy engine rounds to tf32 on the way into shared memory, which is what
+// cuDNN's TF32 convolutions do to their inputs).  SLB200_TMAP_F32=1 selects plain FLOAT32 (the MMA then truncates).
+static int esize(int dtype) { return dtype == 1 ? 4 : 2; }
+static CUtensorMapDataType tmap_dtype(int dtype) {
+  if (dtype != 1) return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  static int plain = -1;
+  if (plain < 0) { const char* e = getenv("SLB200_TMAP_F32"); plain = (e && e[0] == '1') ? 1 : 0; }
+  return plain ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+}
 static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box) {
+                     const uint32_t* box, int dtype, int mn_major = 0) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return -1;
   cuuint64_t gdim[5], gstr[4];
@@ -556,29 +563,34 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
     es[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i];
   }
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  // MN-major fp32 (tf32) operands must sit in the 32-byte-chunk swizzle (sm100.cuh umma_desc_sw128_base32)
+  const CUtensorMapSwizzle sw = (dtype == 1 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(m, tmap_dtype(dtype), rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
 }
 
 static int tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
-                   uint32_t box_rows) {
+                   uint32_t box_rows, int dtype = 0, int mn_major = 0) {
+  const uint64_t e = esize(dtype);
   uint64_t dims[2] = {cols, rows};
-  uint64_t str[2] = {2, ld_elems * 2};
+  uint64_t str[2] = {e, ld_elems * e};
   uint32_t box[2] = {box_cols, box_rows};
-  return make_tmap(m, base, 2, dims, str, box);
+  return make_tmap(m, base, 2, dims, str, box, dtype, mn_major);
 }
-static int tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int tb, int th, int tw) {
+static int tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int tb, int th, int tw, int dtype = 0,
+                     int mn_major = 0) {
+  const uint64_t e = esize(dtype);
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-  uint64_t str[4] = {2, (uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-  uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
-  return make_tmap(m, base, 4, dims, str, box);
+  uint64_t str[4] = {e, (uint64_t)C * e, (uint64_t)W * C * e, (uint64_t)H * W * C * e};
+  uint32_t box[4] = {(uint32_t)(128 / e), (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
+  return make_tmap(m, base, 4, dims, str, box, dtype, mn_major);
 }
 
-template <int MODE, int BN, bool BNB = false>
+template <int MODE, int BN, typename T, bool BNB = false>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid, cudaStream_t st) {
-  auto k = umma_gemm_kernel<MODE, BN, BNB>;
+  auto k = umma_gemm_kernel<MODE, BN, T, BNB>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::TOTAL);
@@ -592,31 +604,45 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& 
 }
 
 template <int MODE>
-static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid,
+static int dispatch_bn(int bn, int dtype, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid,
                        cudaStream_t st) {
+  using bf = __nv_bfloat16;
+  if (dtype == 1) {                               // fp32 tensors, kind::tf32 (conv fwd / dgrad / wgrad only)
+    if constexpr (MODE == MODE_GEMM) return -5;
+    else {
+      if (p.bnb_y != nullptr) return -6;
+      switch (bn) {
+        case 32: return launch<MODE, 32, float>(a, b, p, grid, st);
+        case 64: return launch<MODE, 64, float>(a, b, p, grid, st);
+        case 128: return launch<MODE, 128, float>(a, b, p, grid, st);
+        case 256: return launch<MODE, 256, float>(a, b, p, grid, st);
+        default: return -3;
+      }
+    }
+  }
   if constexpr (MODE == MODE_CONV) {
     if (p.bnb_y != nullptr) {
       switch (bn) {
-        case 64: return launch<MODE, 64, true>(a, b, p, grid, st);
-        case 128: return launch<MODE, 128, true>(a, b, p, grid, st);
-        case 256: return launch<MODE, 256, true>(a, b, p, grid, st);
+        case 64: return launch<MODE, 64, bf, true>(a, b, p, grid, st);
+        case 128: return launch<MODE, 128, bf, true>(a, b, p, grid, st);
+        case 256: return launch<MODE, 256, bf, true>(a, b, p, grid, st);
         default: return -3;
       }
     }
   }
   switch (bn) {
-    case 32: return launch<MODE, 32>(a, b, p, grid, st);
-    case 64: return launch<MODE, 64>(a, b, p, grid, st);
-    case 128: return launch<MODE, 128>(a, b, p, grid, st);
-    case 256: return launch<MODE, 256>(a, b, p, grid, st);
+    case 32: return launch<MODE, 32, bf>(a, b, p, grid, st);
+    case 64: return launch<MODE, 64, bf>(a, b, p, grid, st);
+    case 128: return launch<MODE, 128, bf>(a, b, p, grid, st);
+    case 256: return launch<MODE, 256, bf>(a, b, p, grid, st);
     default: return -3;
   }
 }
 
-template <int MODE, int BN, bool BNB = false>
+template <int MODE, int BN, typename T, bool BNB = false>
 static int preload_one() {
   cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, umma_gemm_kernel<MODE, BN, BNB>) == cudaSuccess ? 0 : 1;
+  return cudaFuncGetAttributes(&a, umma_gemm_kernel<MODE, BN, T, BNB>) == cudaSuccess ? 0 : 1;
 }
 
 static void pixel_box(int H, int W, int pixels, int* tb, int* th, int* tw) {
@@ -635,34 +661,39 @@ extern "C" {
 // Force-load every instantiation (CUDA lazy loading would otherwise load a kernel at its first launch, which can
 // block behind a running flag-spinning kernel of a sibling stage sharing the GPU).
 int slb_preload_gemm() {
+  using bf = __nv_bfloat16;
   int bad = 0;
-  bad += preload_one<MODE_CONV, 64>() + preload_one<MODE_CONV, 128>() + preload_one<MODE_CONV, 256>() + preload_one<MODE_CONV, 32>();
-  bad += preload_one<MODE_WGRAD, 64>() + preload_one<MODE_WGRAD, 128>() + preload_one<MODE_WGRAD, 256>() + preload_one<MODE_WGRAD, 32>();
-  bad += preload_one<MODE_GEMM, 32>() + preload_one<MODE_GEMM, 64>() + preload_one<MODE_GEMM, 128>() + preload_one<MODE_GEMM, 256>();
-  bad += preload_one<MODE_CONV, 64, true>() + preload_one<MODE_CONV, 128, true>() + preload_one<MODE_CONV, 256, true>();
+  bad += preload_one<MODE_CONV, 64, bf>() + preload_one<MODE_CONV, 128, bf>() + preload_one<MODE_CONV, 256, bf>() + preload_one<MODE_CONV, 32, bf>();
+  bad += preload_one<MODE_WGRAD, 64, bf>() + preload_one<MODE_WGRAD, 128, bf>() + preload_one<MODE_WGRAD, 256, bf>() + preload_one<MODE_WGRAD, 32, bf>();
+  bad += preload_one<MODE_GEMM, 32, bf>() + preload_one<MODE_GEMM, 64, bf>() + preload_one<MODE_GEMM, 128, bf>() + preload_one<MODE_GEMM, 256, bf>();
+  bad += preload_one<MODE_CONV, 64, bf, true>() + preload_one<MODE_CONV, 128, bf, true>() + preload_one<MODE_CONV, 256, bf, true>();
+  bad += preload_one<MODE_CONV, 64, float>() + preload_one<MODE_CONV, 128, float>() + preload_one<MODE_CONV, 256, float>() + preload_one<MODE_CONV, 32, float>();
+  bad += preload_one<MODE_WGRAD, 64, float>() + preload_one<MODE_WGRAD, 128, float>() + preload_one<MODE_WGRAD, 256, float>() + preload_one<MODE_WGRAD, 32, float>();
   return bad;
 }
 
-// y[B,H,W,Cout] (bf16, pre-BN) = conv3x3(x[B,H,W,Cin], w[Cout][3][3][Cin]) + bias ; optional per-channel
+// y[B,H,W,Cout] (pre-BN) = conv3x3(x[B,H,W,Cin], w[Cout][3][3][Cin]) + bias ; optional per-channel
 // sum / sum-of-squares accumulation (caller zeroes them).  flip=1 computes the input gradient:
 // x := dY [B,H,W,Cout_w], w as stored, out = dX[B,H,W,Cin_w]  (then Cin here means channels of A = Cout_w).
+// dtype: 0 = bf16 tensors (kind::f16), 1 = fp32 tensors (kind::tf32); x, w and y share it.
 // block_n in {64,128,256} (0 = auto); k_split > 1 accumulates fp32 partial sums into `acc` ([M][Nout], zeroed by the
-// caller) with vector red.add instead of writing y — the caller then runs slb_conv_finalize.
+// caller) with vector red.add instead of writing y — the last K slice of a tile (tile_counters) or slb_conv_finalize
+// then produces y.
 struct BnbArgs { const void* y; const float *mean, *istd, *gamma, *beta; int relu, pool; };
 static int conv_igemm_impl(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
                            int B, int H, int W, int Ca, int Nout, int flip, int w_cin, int w_cout, int block_n, int k_split,
-                           float* acc, uint32_t* tile_counters, const BnbArgs* bnb, cudaStream_t st);
+                           float* acc, uint32_t* tile_counters, const BnbArgs* bnb, int dtype, cudaStream_t st);
 
 int slb_conv3x3_igemm(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
                       int B, int H, int W, int Ca /*channels of A*/, int Nout /*output channels*/, int flip,
                       int w_cin /*Cin of the weight tensor*/, int w_cout, int block_n, int k_split, float* acc,
-                      uint32_t* tile_counters, cudaStream_t st) {
+                      uint32_t* tile_counters, int dtype, cudaStream_t st) {
   return conv_igemm_impl(x, w, y, bias, col_sum, col_sumsq, B, H, W, Ca, Nout, flip, w_cin, w_cout, block_n, k_split, acc,
-                         tile_counters, nullptr, st);
+                         tile_counters, nullptr, dtype, st);
 }
 
 // dgrad whose epilogue also reduces the BatchNorm backward sums of the upstream block: dbeta / dgamma (zeroed by the
-// caller) receive sum m*dX and sum m*dX*xhat; needs k_split == 1 or in-kernel finalisation (tile_counters).
+// caller) receive sum m*dX and sum m*dX*xhat; needs k_split == 1 or in-kernel finalisation (tile_counters).  bf16 only.
 int slb_conv3x3_dgrad_bnstats(const void* dy, const void* w, void* dx, int B, int H, int W, int Ca, int Nout, int w_cin,
                               int w_cout, int block_n, int k_split, float* acc, uint32_t* tile_counters,
                               const void* up_y, const float* up_mean, const float* up_istd, const float* up_gamma,
@@ -670,31 +701,33 @@ int slb_conv3x3_dgrad_bnstats(const void* dy, const void* w, void* dx, int B, in
   if (k_split > 1 && tile_counters == nullptr) return -18;
   BnbArgs b = {up_y, up_mean, up_istd, up_gamma, up_beta, up_relu, up_pool};
   return conv_igemm_impl(dy, w, dx, nullptr, dbeta, dgamma, B, H, W, Ca, Nout, 1, w_cin, w_cout, block_n, k_split, acc,
-                         tile_counters, &b, st);
+                         tile_counters, &b, 0, st);
 }
 
 }  // extern "C"
 
 static int conv_igemm_impl(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
                            int B, int H, int W, int Ca, int Nout, int flip, int w_cin, int w_cout, int block_n, int k_split,
-                           float* acc, uint32_t* tile_counters, const BnbArgs* bnb, cudaStream_t st) {
-  if (Ca % 64 != 0 || Nout % 64 != 0) return -10;
+                           float* acc, uint32_t* tile_counters, const BnbArgs* bnb, int dtype, cudaStream_t st) {
+  const int KE = 128 / esize(dtype);
+  if (Ca % KE != 0 || Nout % 32 != 0) return -10;
   const int M = B * H * W;
   if (128 % W != 0 && W % 128 != 0) return -11;
   int tb, th, tw;
   pixel_box(H, W, 128, &tb, &th, &tw);
   if (tw * th * tb != 128) return -12;
-  int bn = block_n > 0 ? block_n : (Nout >= 256 ? 256 : Nout);   // 64, 128, 256
+  int bn = block_n > 0 ? block_n : (Nout >= 256 ? 256 : Nout);   // 32, 64, 128, 256
   if (bn > Nout) bn = Nout;
   if (Nout % bn) return -16;
+  if (flip && bn < KE) return -4;                                  // MN-major B needs whole 128-byte groups
   CUtensorMap ta, tbm;
-  int r = tmap_nhwc(&ta, x, B, H, W, Ca, tb, th, tw);
+  int r = tmap_nhwc(&ta, x, B, H, W, Ca, tb, th, tw, dtype);
   if (r) return r;
-  if (!flip) r = tmap_2d(&tbm, w, (uint64_t)9 * w_cin, w_cout, (uint64_t)9 * w_cin, 64, bn);
-  else       r = tmap_2d(&tbm, w, (uint64_t)9 * w_cin, w_cout, (uint64_t)9 * w_cin, 64, 64);
+  if (!flip) r = tmap_2d(&tbm, w, (uint64_t)9 * w_cin, w_cout, (uint64_t)9 * w_cin, KE, bn, dtype);
+  else       r = tmap_2d(&tbm, w, (uint64_t)9 * w_cin, w_cout, (uint64_t)9 * w_cin, KE, KE, dtype, 1);
   if (r) return r;
   GemmParams p = {};
-  p.M = M; p.N = Nout; p.k_iters = 9 * (Ca / 64);
+  p.M = M; p.N = Nout; p.k_iters = 9 * (Ca / KE);
   if (k_split < 1) k_split = 1;
   if (k_split > p.k_iters) k_split = p.k_iters;
   {  // no empty K slices (the tile semaphore counts exactly k_split arrivals)
@@ -707,7 +740,7 @@ static int conv_igemm_impl(const void* x, const void* w, void* y, const float* b
     if (acc == nullptr) return -17;
     p.epi = EPI_F32_ATOMIC; p.out = acc;
     if (tile_counters != nullptr) {       // in-kernel finalisation by the last K-slice of every tile
-      p.tile_counters = tile_counters; p.fin_out = reinterpret_cast<__nv_bfloat16*>(y); p.fin_ld = Nout;
+      p.tile_counters = tile_counters; p.fin_out = y; p.fin_ld = Nout;
       p.bias = bias; p.col_sum = col_sum; p.col_sumsq = col_sumsq;
     }
   } else {
@@ -720,30 +753,32 @@ static int conv_igemm_impl(const void* x, const void* w, void* y, const float* b
     p.bnb_mean = bnb->mean; p.bnb_istd = bnb->istd; p.bnb_gamma = bnb->gamma; p.bnb_beta = bnb->beta; p.bnb_relu = bnb->relu; p.bnb_pool = bnb->pool;
   }
   dim3 grid((M + 127) / 128, Nout / bn, k_split);
-  return dispatch_bn<MODE_CONV>(bn, ta, tbm, p, grid, st);
+  return dispatch_bn<MODE_CONV>(bn, dtype, ta, tbm, p, grid, st);
 }
 
 extern "C" {
 
-// dw[Cout][3][3][Cin] (fp32, accumulated with red.add; caller zeroes) += sum_pixels dy (x) x
+// dw[Cout][3][3][Cin] (fp32, accumulated with red.add; caller zeroes) += sum_pixels dy (x) x ; x / dy typed by dtype
 int slb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int k_split,
-                      int block_n, cudaStream_t st) {
-  if (Cin % 64 != 0 || Cout % 64 != 0) return -10;
+                      int block_n, int dtype, cudaStream_t st) {
+  const int KE = 128 / esize(dtype);
+  if (Cin % KE != 0 || Cout % KE != 0) return -10;
   const int pixels = B * H * W;
+  if (KE % W != 0) return -11;
   int tb, th, tw;
-  pixel_box(H, W, 64, &tb, &th, &tw);
-  if (tw * th * tb != 64) return -12;
+  pixel_box(H, W, KE, &tb, &th, &tw);
+  if (tw * th * tb != KE) return -12;
   int bn = block_n > 0 ? block_n : (Cin >= 128 ? 128 : Cin);
   if (bn > Cin) bn = Cin;
-  if (Cin % bn) return -16;
+  if (Cin % bn || bn % KE) return -16;
   CUtensorMap ta, tbm;
-  int r = tmap_nhwc(&ta, dy, B, H, W, Cout, tb, th, tw);
+  int r = tmap_nhwc(&ta, dy, B, H, W, Cout, tb, th, tw, dtype, 1);
   if (r) return r;
-  r = tmap_nhwc(&tbm, x, B, H, W, Cin, tb, th, tw);
+  r = tmap_nhwc(&tbm, x, B, H, W, Cin, tb, th, tw, dtype, 1);
   if (r) return r;
   GemmParams p = {};
   const int rows = 9 * Cout;
-  p.M = ((rows + 127) / 128) * 128; p.N = Cin; p.k_iters = (pixels + 63) / 64;   // tail pixels are TMA zero-fill
+  p.M = ((rows + 127) / 128) * 128; p.N = Cin; p.k_iters = (pixels + KE - 1) / KE;   // tail pixels are TMA zero-fill
   const int m_tiles = p.M / 128, n_tiles = Cin / bn;
   if (k_split <= 0) {
     k_split = (148 + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
@@ -762,7 +797,7 @@ int slb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int H, in
   p.rmod = Cout; p.rmul1 = (long long)9 * Cin; p.rmul2 = Cin; p.m_valid_mod = 9;
   p.C = Cout; p.tw = tw; p.th = th; p.tb = tb; p.H = H; p.W = W; p.Cout = Cout;
   dim3 grid(m_tiles, n_tiles, k_split);
-  return dispatch_bn<MODE_WGRAD>(bn, ta, tbm, p, grid, st);
+  return dispatch_bn<MODE_WGRAD>(bn, dtype, ta, tbm, p, grid, st);
 }
 
 // Generic bf16 GEMM:  D[M,N] = A x B  with fp32 result.
@@ -788,7 +823,7 @@ int slb_gemm_bf16(const void* A, const void* Bm, float* out, int M, int N, int K
   if (epi == EPI_F32_STORE) k_split = 1;
   p.k_split = k_split; p.a_mn = a_mn; p.b_mn = b_mn; p.epi = epi; p.out = out; p.ldo = ldo;
   dim3 grid((M + 127) / 128, (N + block_n - 1) / block_n, k_split);
-  return dispatch_bn<MODE_GEMM>(block_n, ta, tbm, p, grid, st);
+  return dispatch_bn<MODE_GEMM>(block_n, 0, ta, tbm, p, grid, st);
 }
 
 // Transformer GEMM: out_bf16[M][ldo] = act(A * B + bias + residual), optional pre-activation copy in `aux`.
@@ -812,7 +847,7 @@ int slb_gemm_bf16_act(const void* A, const void* Bm, void* out, int M, int N, in
   p.bias = bias; p.act = act; p.aux_out = reinterpret_cast<__nv_bfloat16*>(aux);
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   dim3 grid((M + 127) / 128, (N + block_n - 1) / block_n, 1);
-  return dispatch_bn<MODE_GEMM>(block_n, ta, tbm, p, grid, st);
+  return dispatch_bn<MODE_GEMM>(block_n, 0, ta, tbm, p, grid, st);
 }
 
 }  // extern "C"

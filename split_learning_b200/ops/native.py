@@ -68,6 +68,13 @@ def _p(t) -> c_void_p:
     return c_void_p(t.data_ptr())
 
 
+def _dt(t) -> c_int:
+    """Activation dtype code of the C API: 0 = bf16, 1 = fp32 (tensors or raw ``DevPtr`` views of peer memory)."""
+    if isinstance(t, torch.Tensor):
+        return c_int(1 if t.dtype == torch.float32 else 0)
+    return c_int(1 if getattr(t, "itemsize", 2) == 4 else 0)
+
+
 def _stream() -> c_void_p:
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -104,11 +111,11 @@ def _tuning():
     return _TUNING
 
 
-def conv_tiling(M: int, N: int, Ca: int, target_ctas: int = 96, flip: int = 0):
+def conv_tiling(M: int, N: int, Ca: int, target_ctas: int = 96, flip: int = 0, ke: int = 64):
     """(block_n, k_split) for the implicit-GEMM conv: these problems are latency- not FLOP-bound at microbatch 32,
     so spread every layer over ~all SMs — narrow N tiles first, then split K (fp32 vector red.add + finalize).
     A measured entry of ``conv_tuning.json`` for exactly this shape wins over the heuristic."""
-    hit = _tuning()["conv"].get(f"{M},{N},{Ca},{flip}")
+    hit = _tuning()["conv" if ke == 64 else "conv_f32"].get(f"{M},{N},{Ca},{flip}") if ("conv_f32" in _tuning() or ke == 64) else None
     if hit:
         return int(hit["bn"]), int(hit["ks"])
     m_tiles = (M + 127) // 128
@@ -119,24 +126,29 @@ def conv_tiling(M: int, N: int, Ca: int, target_ctas: int = 96, flip: int = 0):
             break
     bn = min(bn, N)
     tiles = m_tiles * (N // bn)
-    k_iters = 9 * (Ca // 64)
+    k_iters = 9 * (Ca // ke)
     k_split = 1
     if tiles < target_ctas:
         k_split = max(1, min((128 + tiles - 1) // tiles, k_iters // 4))
     return bn, k_split
 
 
+def _ke(t) -> int:
+    return 32 if _dt(t).value == 1 else 64
+
+
 def conv3x3_fwd(x, w_bf16, y, bias=None, col_sum=None, col_sumsq=None, acc=None, tiling=None, counters=None):
-    """x [B,H,W,Cin] bf16, w [Cout,3,3,Cin] bf16 -> y [B,H,W,Cout] bf16 (pre-BN) + optional BN sums.
-    ``acc``: zeroed fp32 [M, Cout] scratch enabling split-K (then a finalize kernel produces y and the sums)."""
+    """x [B,H,W,Cin], w [Cout,3,3,Cin] -> y [B,H,W,Cout] (pre-BN) + optional BN sums; x / w / y all bf16 (kind::f16)
+    or all fp32 (kind::tf32).  ``acc``: zeroed fp32 [M, Cout] scratch enabling split-K (the last K slice of a tile —
+    or a finalize kernel — then produces y and the sums)."""
     B, H, W, Cin = x.shape
     Cout = w_bf16.shape[0]
-    bn, ks = tiling or conv_tiling(B * H * W, Cout, Cin)
+    bn, ks = tiling or conv_tiling(B * H * W, Cout, Cin, ke=_ke(x))
     if acc is None:
         ks = 1
     _check(lib().slb_conv3x3_igemm(_p(x), _p(w_bf16), _p(y), _p(bias), _p(col_sum), _p(col_sumsq), c_int(B), c_int(H),
                                    c_int(W), c_int(Cin), c_int(Cout), c_int(0), c_int(Cin), c_int(Cout), c_int(bn), c_int(ks),
-                                   _p(acc), _p(counters), _stream()), "conv3x3_fwd")
+                                   _p(acc), _p(counters), _dt(x), _stream()), "conv3x3_fwd")
     if ks > 1 and counters is None:
         conv_finalize(acc, bias, y, col_sum, col_sumsq)
 
@@ -147,7 +159,9 @@ def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None, bn_stats
     [+ MaxPool2]) whose output gradient is dx: the epilogue then also reduces that block's BatchNorm-backward sums."""
     B, H, W, Cout = dy.shape
     Cin = w_bf16.shape[3]
-    bn, ks = tiling or conv_tiling(B * H * W, Cin, Cout, flip=1)
+    bn, ks = tiling or conv_tiling(B * H * W, Cin, Cout, flip=1, ke=_ke(dy))
+    if _dt(dy).value == 1:
+        bn = max(bn, 32)
     if acc is None:
         ks = 1
     if bn_stats is not None:
@@ -161,7 +175,7 @@ def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None, bn_stats
         return
     _check(lib().slb_conv3x3_igemm(_p(dy), _p(w_bf16), _p(dx), _p(None), _p(None), _p(None), c_int(B), c_int(H), c_int(W),
                                    c_int(Cout), c_int(Cin), c_int(1), c_int(Cin), c_int(Cout), c_int(bn), c_int(ks), _p(acc),
-                                   _p(counters), _stream()), "conv3x3_dgrad")
+                                   _p(counters), _dt(dy), _stream()), "conv3x3_dgrad")
     if ks > 1 and counters is None:
         conv_finalize(acc, None, dx, None, None)
 
@@ -169,8 +183,8 @@ def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None, bn_stats
 def conv_finalize(acc, bias, y, col_sum, col_sumsq):
     C = y.shape[-1]
     P = y.numel() // C
-    _check(lib().slb_conv_finalize(_p(acc), _p(bias), _p(y), _p(col_sum), _p(col_sumsq), c_longlong(P), c_int(C), _stream()),
-           "conv_finalize")
+    _check(lib().slb_conv_finalize(_p(acc), _p(bias), _p(y), _p(col_sum), _p(col_sumsq), c_longlong(P), c_int(C), _dt(y),
+                                   _stream()), "conv_finalize")
 
 
 def conv3x3_wgrad(x, dy, dw_f32, k_split: int = 0, block_n: int = 0):
@@ -178,12 +192,12 @@ def conv3x3_wgrad(x, dy, dw_f32, k_split: int = 0, block_n: int = 0):
     whose K fits one slice is written with plain stores."""
     B, H, W, Cin = x.shape
     Cout = dy.shape[3]
-    if k_split == 0 and block_n == 0:
+    if k_split == 0 and block_n == 0 and _ke(x) == 64:
         hit = _tuning()["wgrad"].get(f"{B * H * W},{Cin},{Cout}")
         if hit:
             block_n, k_split = int(hit["bn"]), int(hit["ks"])
     _check(lib().slb_conv3x3_wgrad(_p(x), _p(dy), _p(dw_f32), c_int(B), c_int(H), c_int(W), c_int(Cin), c_int(Cout),
-                                   c_int(k_split), c_int(block_n), _stream()), "conv3x3_wgrad")
+                                   c_int(k_split), c_int(block_n), _dt(x), _stream()), "conv3x3_wgrad")
 
 
 EPI_ATOMIC, EPI_ATOMIC_T, EPI_STORE = 1, 2, 3
@@ -239,11 +253,11 @@ def conv_bn_act_p2p(x, w_bf16, bias, gamma, beta, running_mean, running_var, nbt
                                      _p(nbt), _p(save_mean), _p(save_invstd), _p(col_sum), _p(col_sumsq), _p(y_opt), _p(out),
                                      c_int(B), c_int(H), c_int(W), c_int(Cin), c_int(Cout), c_int(int(relu)), c_int(int(pool)),
                                      c_float(momentum), c_float(eps), c_int(int(update_running)), _p(grid_bar), _p(flag),
-                                     _p(seq), _p(hint), c_int(num_sms(x.device)), _stream()), "conv_bn_act_p2p")
+                                     _p(seq), _p(hint), c_int(num_sms(x.device)), _dt(x), _stream()), "conv_bn_act_p2p")
 
 
-def fused_cut_supported(B, H, W, Cin, Cout, pool) -> bool:
-    if Cin % 64 or Cout % 64 or 128 % W:
+def fused_cut_supported(B, H, W, Cin, Cout, pool, ke: int = 64) -> bool:
+    if Cin % ke or Cout % 64 or 128 % W:
         return False
     rows = 128 // W
     th = rows if rows <= H else H
@@ -268,7 +282,7 @@ def bn_relu_pool_fwd(y, col_sum, col_sumsq, gamma, beta, running_mean, running_v
                                       _p(running_var), _p(nbt), _p(save_mean), _p(save_invstd), _p(out), c_int(P), c_int(C),
                                       c_int(H), c_int(W), c_int(int(relu)), c_int(int(pool)), c_float(momentum), c_float(eps),
                                       c_int(int(update_running)), c_int(int(identity)), _p(ticket), _p(flag), _p(seq), _p(hint),
-                                      _stream()), "bn_relu_pool_fwd")
+                                      _dt(y), _stream()), "bn_relu_pool_fwd")
 
 
 def bn_relu_pool_bwd(dout, y, gamma, beta, save_mean, save_invstd, dgamma, dbeta, dy, H, W, relu, pool, identity=False,
@@ -280,51 +294,96 @@ def bn_relu_pool_bwd(dout, y, gamma, beta, save_mean, save_invstd, dgamma, dbeta
         identity, grid_bar = 2, None
     _check(lib().slb_bn_relu_pool_bwd(_p(dout), _p(y), _p(gamma), _p(beta), _p(save_mean), _p(save_invstd), _p(dgamma),
                                       _p(dbeta), _p(dy), c_int(P), c_int(C), c_int(H), c_int(W), c_int(int(relu)),
-                                      c_int(int(pool)), c_int(int(identity)), _p(grid_bar), _stream()), "bn_relu_pool_bwd",
+                                      c_int(int(pool)), c_int(int(identity)), _p(grid_bar), _dt(y), _stream()), "bn_relu_pool_bwd",
            1 if (identity or grid_bar is not None) else 2)
 
 
 def col_stats(y2d, col_sum, col_sumsq=None):
     P, C = y2d.shape
-    _check(lib().slb_col_stats(_p(y2d), _p(col_sum), _p(col_sumsq), c_longlong(P), c_int(C), _stream()), "col_stats")
+    _check(lib().slb_col_stats(_p(y2d), _p(col_sum), _p(col_sumsq), c_longlong(P), c_int(C), _dt(y2d), _stream()), "col_stats")
 
 
 def conv3x3_small_fwd(x_nchw_f32, w_f32, bias, y, col_sum=None, col_sumsq=None):
     B, Cin, H, W = x_nchw_f32.shape
     Cout = w_f32.shape[0]
     _check(lib().slb_conv3x3_small_fwd(_p(x_nchw_f32), _p(w_f32), _p(bias), _p(y), _p(col_sum), _p(col_sumsq), c_int(B),
-                                       c_int(Cin), c_int(H), c_int(W), c_int(Cout), _stream()), "conv3x3_small_fwd")
+                                       c_int(Cin), c_int(H), c_int(W), c_int(Cout), _dt(y), _stream()), "conv3x3_small_fwd")
 
 
 def conv3x3_small_wgrad(x_nchw_f32, dy, dw_f32):
     B, Cin, H, W = x_nchw_f32.shape
     Cout = dy.shape[3]
     _check(lib().slb_conv3x3_small_wgrad(_p(x_nchw_f32), _p(dy), _p(dw_f32), c_int(B), c_int(Cin), c_int(H), c_int(W),
-                                         c_int(Cout), _stream()), "conv3x3_small_wgrad")
+                                         c_int(Cout), _dt(dy), _stream()), "conv3x3_small_wgrad")
 
 
 def linear_finalize(acc, bias, out_bf16, out_f32, mask, relu, drop_p=0.0, seed=0, step_ptr=None):
     B, N = acc.shape
     ldo = out_bf16.stride(0) if out_bf16 is not None else N
     _check(lib().slb_linear_finalize(_p(acc), _p(bias), _p(out_bf16), _p(out_f32), _p(mask), c_int(B), c_int(N), c_int(ldo),
-                                     c_int(int(relu)), c_float(drop_p), c_uint32(seed), _p(step_ptr), _stream()),
-           "linear_finalize")
+                                     c_int(int(relu)), c_float(drop_p), c_uint32(seed), _p(step_ptr),
+                                     _dt(out_bf16) if out_bf16 is not None else c_int(0), _stream()), "linear_finalize")
 
 
 def linear_bwd_prep(dacc, yout, mask, dz, dbias, relu, drop_p=0.0):
     B, N = dacc.shape
     _check(lib().slb_linear_bwd_prep(_p(dacc), _p(yout), _p(mask), _p(dz), _p(dbias), c_int(B), c_int(N),
                                      c_int(yout.stride(0) if yout is not None else N), c_int(dz.stride(0)),
-                                     c_int(int(relu)), c_float(drop_p), _stream()), "linear_bwd_prep")
+                                     c_int(int(relu)), c_float(drop_p), _dt(dz), _stream()), "linear_bwd_prep")
 
 
 def dropout_fwd(x, y, mask, p, seed, step_ptr=None):
     _check(lib().slb_dropout_fwd(_p(x), _p(y), _p(mask), c_longlong(x.numel()), c_float(p), c_uint32(seed), _p(step_ptr),
-                                 _stream()), "dropout_fwd")
+                                 _dt(x), _stream()), "dropout_fwd")
 
 
 def dropout_bwd(dacc, mask, dx, p):
-    _check(lib().slb_dropout_bwd(_p(dacc), _p(mask), _p(dx), c_longlong(dacc.numel()), c_float(p), _stream()), "dropout_bwd")
+    _check(lib().slb_dropout_bwd(_p(dacc), _p(mask), _p(dx), c_longlong(dacc.numel()), c_float(p), _dt(dx), _stream()),
+           "dropout_bwd")
+
+
+# ---- fp32 Linear on the CUDA cores (parity mode: the reference's nn.Linear is a plain fp32 GEMM)
+def linear_fwd_f32(x, w, acc):
+    """acc[b][out] (fp32, zeroed) += x[b][in] @ w[out][in]^T, IEEE fp32 FMAs."""
+    Bn, K = x.shape
+    _check(lib().slb_linear_fwd_f32(_p(x), _p(w), _p(acc), c_int(Bn), c_int(w.shape[0]), c_int(K), c_int(x.stride(0)),
+                                    c_int(w.stride(0)), c_int(acc.stride(0)), _stream()), "linear_fwd_f32")
+
+
+def linear_dgrad_f32(dz, w, dacc):
+    """dacc[b][in] (fp32, zeroed) += dz[b][out] @ w[out][in]."""
+    Bn = dz.shape[0]
+    out_f, in_f = w.shape
+    _check(lib().slb_linear_dgrad_f32(_p(dz), _p(w), _p(dacc), c_int(Bn), c_int(out_f), c_int(in_f), c_int(dz.stride(0)),
+                                      c_int(w.stride(0)), c_int(dacc.stride(0)), _stream()), "linear_dgrad_f32")
+
+
+def linear_wgrad_f32(dz, x, g=None, sgd=None, accumulate=False):
+    """Weight gradient dz^T @ x.  ``sgd=(P, M, bias_P, bias_M, bias_G, lr, mu)``: the SGD-momentum update is applied in
+    the same pass (weights and bias rows; no gradient buffer is written); otherwise ``g`` receives (or accumulates) it."""
+    Bn, in_f = x.shape
+    out_f = dz.shape[1]
+    if sgd is not None:
+        P, M, bp, bm, bg, lr, mu = sgd
+        n = (Bn + 31) // 32
+        _check(lib().slb_linear_wgrad_f32(_p(dz), _p(x), _p(None), _p(P), _p(M), _p(bp), _p(bm), _p(bg), c_int(Bn), c_int(out_f),
+                                          c_int(in_f), c_int(dz.stride(0)), c_int(x.stride(0)), c_int(P.stride(0)), c_int(2),
+                                          c_float(lr), c_float(mu), _stream()), "linear_wgrad_f32", n)
+        return
+    _check(lib().slb_linear_wgrad_f32(_p(dz), _p(x), _p(g), _p(None), _p(None), _p(None), _p(None), _p(None), c_int(Bn),
+                                      c_int(out_f), c_int(in_f), c_int(dz.stride(0)), c_int(x.stride(0)), c_int(g.stride(0)),
+                                      c_int(1 if accumulate else 0), c_float(0.0), c_float(0.0), _stream()), "linear_wgrad_f32",
+           (Bn + 31) // 32)
+
+
+def sumsq(g, out):
+    """out[0] (zeroed by the caller) += sum(g^2) over a flat fp32 buffer."""
+    _check(lib().slb_sumsq(_p(g), c_longlong(g.numel()), _p(out), _stream()), "sumsq")
+
+
+def clip_scale(g, sumsq_t, max_norm: float):
+    """g *= min(1, max_norm / (sqrt(sumsq) + 1e-6)) — torch.nn.utils.clip_grad_norm_ on the flat gradient."""
+    _check(lib().slb_clip_scale(_p(g), c_longlong(g.numel()), _p(sumsq_t), c_float(max_norm), _stream()), "clip_scale")
 
 
 def ce_fwd_bwd(logits_f32, labels_i64, dlogits_f32, loss_sum, nan_flag):

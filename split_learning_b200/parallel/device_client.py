@@ -79,6 +79,7 @@ class DeviceRpcClient(RpcClient):
         depth = int(self.learning.get("control-count", 3))
         lanes = self._lanes(msg)
         dev = ex.device
+        isz = 4 if ex.fp32 else 2                                  # payload element size (all stages share b200.precision)
         my_q = f"ipc_{self.client_id}"
         self.channel.queue_declare(my_q)
         fwd_in: Dict[int, Mailbox] = {}
@@ -86,13 +87,13 @@ class DeviceRpcClient(RpcClient):
         for lane, up, down in lanes:
             if up is not None:                                     # I consume this lane's activations
                 c, h, w = ex.in_shape
-                spec_in = MailboxSpec(depth, B, (B, h, w, c))
+                spec_in = MailboxSpec(depth, B, (B, h, w, c), itemsize=isz)
                 fwd_in[lane], hdl = Mailbox.allocate_exportable(spec_in, dev)
                 self.channel.publish_obj(f"ipc_{up}", {"kind": "act", "lane": lane, "handle": hdl,
                                                        "shape": spec_in.payload_shape})
             if down is not None:                                   # I consume the gradients of this lane's output
                 c, h, w = ex.out_shape
-                spec_out = MailboxSpec(depth, B, (B, h, w, c))
+                spec_out = MailboxSpec(depth, B, (B, h, w, c), itemsize=isz)
                 grad_in[lane], hdl = Mailbox.allocate_exportable(spec_out, dev)
                 self.channel.publish_obj(f"ipc_{down}", {"kind": "grad", "lane": lane, "handle": hdl,
                                                          "shape": spec_out.payload_shape})
@@ -106,7 +107,7 @@ class DeviceRpcClient(RpcClient):
                 if time.monotonic() - t0 > self.watchdog:
                     raise TimeoutError("peer never posted its IPC handle")
                 continue
-            spec = MailboxSpec(depth, B, tuple(m["shape"]))
+            spec = MailboxSpec(depth, B, tuple(m["shape"]), itemsize=isz)
             mb = Mailbox.open_peer(spec, m["handle"], dev)
             if m["kind"] == "act":                                 # downstream's activation ring: I produce into it
                 fwd_out[m["lane"]] = mb

@@ -75,12 +75,17 @@ class DevPtr:
 class MailboxSpec:
     depth: int
     batch: int
-    payload_shape: Tuple[int, ...]      # per-microbatch tensor shape, bf16
+    payload_shape: Tuple[int, ...]      # per-microbatch tensor shape
     with_labels: bool = True
+    itemsize: int = 4                   # 4 = fp32 payload (tf32 parity mode, the reference's wire format), 2 = bf16
+
+    @property
+    def dtype(self):
+        return torch.float32 if self.itemsize == 4 else torch.bfloat16
 
     @property
     def payload_bytes(self) -> int:
-        n = 2
+        n = self.itemsize
         for d in self.payload_shape:
             n *= d
         return _align(n)
@@ -137,17 +142,17 @@ class Mailbox:
         self.raw_ptr = raw_ptr if raw_ptr is not None else base.data_ptr()
         d = spec.depth
         if base is None:                     # peer-mapped: raw pointer views only
-            self.payload = [DevPtr(self.raw_ptr + s * spec.payload_bytes, spec.payload_shape, 2) for s in range(d)]
+            self.payload = [DevPtr(self.raw_ptr + s * spec.payload_bytes, spec.payload_shape, spec.itemsize) for s in range(d)]
             self.labels = [DevPtr(self.raw_ptr + spec.labels_off + s * spec.batch * 8, (spec.batch,), 8) for s in range(d)]
             self.flags = None
             self.header = None
             return
         self.payload: List[torch.Tensor] = []
         for s in range(d):
-            nb = 2
+            nb = spec.itemsize
             for x in spec.payload_shape:
                 nb *= x
-            t = base[s * spec.payload_bytes: s * spec.payload_bytes + nb].view(torch.bfloat16).view(spec.payload_shape)
+            t = base[s * spec.payload_bytes: s * spec.payload_bytes + nb].view(spec.dtype).view(spec.payload_shape)
             self.payload.append(t)
         lab = base[spec.labels_off: spec.labels_off + d * spec.batch * 8].view(torch.int64).view(d, spec.batch)
         self.labels = [lab[s] for s in range(d)]

@@ -35,7 +35,7 @@ def act_spec(ex: B200Executor, batch: int, depth: int) -> MailboxSpec:
     if ex.out_kind != "image":
         raise NotImplementedError("device data plane supports cuts inside the convolutional trunk")
     c, h, w = ex.out_shape
-    return MailboxSpec(depth, batch, (batch, h, w, c), with_labels=True)
+    return MailboxSpec(depth, batch, (batch, h, w, c), with_labels=True, itemsize=4 if ex.fp32 else 2)
 
 
 class DeviceStage:

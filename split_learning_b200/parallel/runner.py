@@ -51,7 +51,7 @@ def build_chain_stage(rank: int, world: int, cut: int, batch: int, depth: int, l
         spec = act_spec(ex, batch, depth)
     else:
         c, h, w = ex.in_shape
-        spec = MailboxSpec(depth, batch, (batch, h, w, c))
+        spec = MailboxSpec(depth, batch, (batch, h, w, c), itemsize=4 if ex.fp32 else 2)
     own, handle = Mailbox.allocate_exportable(spec, device)          # grads (stage 1) / activations (stage 2)
     handles = exchange_handles({"mb": handle})
     remote = Mailbox.open_peer(spec, handles[peer]["mb"], device)
@@ -141,7 +141,7 @@ def fedavg_round(st: DeviceStage, rank: int, world: int, dev) -> Optional[dict]:
 
 
 def bench_multi_gpu(args) -> dict:
-    from bench import ClockSampler, synthetic_batches     # bench.py is the entry script (repo root on sys.path)
+    from bench import DTYPE_LABEL, ClockSampler, synthetic_batches     # bench.py is the entry script (repo root on sys.path)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -151,7 +151,8 @@ def bench_multi_gpu(args) -> dict:
     torch.cuda.set_device(dev)
     init_dist(dev)
     W, K, B, depth = args.warmup, args.steps, args.batch, args.depth
-    learning = {"learning-rate": 0.0005, "momentum": 0.5, "batch-size": B, "control-count": depth}
+    learning = {"learning-rate": 0.0005, "momentum": 0.5, "batch-size": B, "control-count": depth,
+                "precision": getattr(args, "precision", "tf32")}
     st = build_chain_stage(rank, world, args.cut, B, depth, learning, dev, use_graphs=not args.no_graphs)
     n = world // 2
     pool = synthetic_batches(16, B, seed=1 + rank) if st.ex.is_first else None
@@ -211,7 +212,7 @@ def bench_multi_gpu(args) -> dict:
     return {
         "metric": "VGG16/CIFAR10 split images/sec", "value": images / (results["device"] / 1e3), "unit": "images/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": results["device"] / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_LABEL[getattr(args, "precision", "tf32")], "data": "synthetic",
         "config": {"model": "VGG16_CIFAR10", "global_batch": B * n, "microbatch": B, "seq_len": None, "cut_layers": [args.cut],
                    "clients": [n, n], "control_count": depth, "parallelism": f"pp2 x dp{n} (one GPU per stage replica)",
                    "optimizer": "SGD lr=5e-4 momentum=0.5, step per microbatch", "recompute": True,

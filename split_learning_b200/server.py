@@ -73,6 +73,12 @@ class Server:
         self.history: List[dict] = []         # per-round metrics (loss/acc/seconds)
         self._round_t0 = time.monotonic()
         self.watchdog = float(config.b200.get("watchdog-seconds", 120.0))
+        # liveness: clients beacon every ``heartbeat-seconds``; one that has beaconed before and stays silent for
+        # ``watchdog-seconds`` is declared dead (the round is aborted with STOP instead of dead-locking); the server relays
+        # a beacon to every client so that *their* waits (PAUSE, sequential turns, long rounds) never expire on a live run
+        self.heartbeat = float(config.b200.get("heartbeat-seconds", min(10.0, self.watchdog / 4)))
+        self.last_seen: Dict[str, float] = {}
+        self._last_beacon = time.monotonic()
         self.logger = logger or Logger(os.path.join(config.log_path, "app.log"), config.debug_mode)
         self.logger.log_info(f"Application start. Server is waiting for {self.total_clients} clients.")
         for w in config.warnings:
@@ -85,16 +91,33 @@ class Server:
         limit = idle_timeout if idle_timeout is not None else max(self.watchdog * 4, 600.0)
         while not self.done:
             m = self.ch.get_obj(M.RPC_QUEUE, 0.1)
+            now = time.monotonic()
+            if now - self._last_beacon >= self.heartbeat:
+                self._beacon(now)
             if m is None:
-                if time.monotonic() - last > limit:
+                if now - last > limit:
                     raise TimeoutError(f"server: no client message for {limit}s (registered "
                                        f"{self.register_clients} of {self.total_clients})")
                 continue
-            last = time.monotonic()
+            last = now
             self.on_request(m)
+
+    def _beacon(self, now: float) -> None:
+        """Relay liveness to every client and check that every beaconing client is still there."""
+        self._last_beacon = now
+        for c in self.clients:
+            self.send_to_response(c.client_id, M.heartbeat())
+        dead = [cid for cid, t in self.last_seen.items() if now - t > max(self.watchdog, 3 * self.heartbeat)]
+        if dead and not self.done:
+            self.logger.log_error(f"clients silent for {self.watchdog}s: {dead}; stopping the run")
+            self.notify_clients(start=False)
+            raise TimeoutError(f"server: client(s) {dead} stopped sending heartbeats")
 
     def on_request(self, message: dict) -> None:
         action = message["action"]
+        if action == M.HEARTBEAT:
+            self.last_seen[str(message.get("client_id"))] = time.monotonic()
+            return
         handler = {M.REGISTER: self.on_register, M.NOTIFY: self.on_notify, M.UPDATE: self.on_update,
                    M.READY: self.on_ready}.get(action)
         if handler is None:

@@ -9,9 +9,20 @@ A stage's ``LayerSpec`` slice is compiled into a static plan of fused blocks
     Dropout     = standalone dropout on a dense activation (VGG layer 46)
     LinearBlock = Linear [ReLU] [Dropout]   (swap-AB tcgen05 GEMM, split-K, fused finalisation)
 
-over flat fp32 master / gradient / momentum buffers with a bf16 shadow copy refreshed by the
-fused SGD kernel.  Forward, backward(+recompute) and the optimizer step of one microbatch are
-captured once per batch size into CUDA graphs; the host only copies the input in and replays.
+over flat fp32 master / gradient / momentum buffers.  Forward, backward(+recompute) and the
+optimizer step of one microbatch are captured once per batch size into CUDA graphs; the host
+only copies the input in and replays.
+
+Two compute precisions (``precision=`` / ``b200.precision`` / ``SLB200_PRECISION``):
+
+* ``tf32`` (default, the reference's precision): fp32 activations and weights end to end,
+  convolutions on ``tcgen05.mma kind::tf32`` with fp32 accumulation (what PyTorch/cuDNN does by
+  default for the reference's ``nn.Conv2d``), Linear layers in IEEE fp32 on the CUDA cores (the
+  reference's ``nn.Linear`` is an fp32 cuBLAS GEMM) with the SGD-momentum step fused into the
+  weight-gradient pass; BN / ReLU / pool / CE / SGD in fp32.  No reduced-precision copy of
+  anything exists in this mode.
+* ``bf16`` (opt-in fast mode): bf16 activations and a bf16 weight shadow refreshed by the fused
+  SGD kernel, ``kind::f16`` tensor-core GEMMs for convolutions and Linear layers.
 
 Semantics follow the reference trainer (src/train/VGG16.py:61-190): SGD(lr, momentum) step per
 microbatch, recompute-forward with *current* weights on non-last stages (BN running stats
@@ -165,8 +176,20 @@ def _align(n: int, a: int = 128) -> int:
 # ----------------------------------------------------------------------------- executor
 class B200Executor(StageExecutor):
     def __init__(self, model: SplitModel, model_name: str, learning: dict, device, is_first=False, is_last=False,
-                 recompute: bool = True, use_graphs: bool = True, seed: int = 1234, fused_cut: bool = True):
+                 recompute: bool = True, use_graphs: bool = True, seed: int = 1234, fused_cut: bool = True,
+                 precision: Optional[str] = None):
         N.require()
+        import os
+        precision = (precision or learning.get("precision") or os.environ.get("SLB200_PRECISION") or "tf32").lower()
+        if precision in ("fp32", "float32"):
+            precision = "tf32"
+        if precision not in ("tf32", "bf16"):
+            raise ValueError(f"precision must be tf32 or bf16, got {precision!r}")
+        self.precision = precision
+        self.fp32 = precision == "tf32"
+        self.act_dtype = torch.float32 if self.fp32 else torch.bfloat16
+        self.ke = 32 if self.fp32 else 64                 # K elements per 128-byte MMA pipeline stage
+        self.clip = float(learning.get("clip-grad-norm") or 0.0)
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         N.preload(self.device)
@@ -176,7 +199,6 @@ class B200Executor(StageExecutor):
         self.is_first, self.is_last = is_first, is_last
         self.recompute = recompute
         self.use_graphs = use_graphs
-        import os
         self.fused_cut = fused_cut and os.environ.get("SLB200_FUSED_CUT", "1") != "0"
         # single-launch BN backward (reduce -> grid barrier -> apply): measured SLOWER than two PDL-chained launches
         # (L pass 825 us vs 776 us) — a software grid barrier costs more than a kernel boundary here.  Off by default.
@@ -252,7 +274,7 @@ class B200Executor(StageExecutor):
         self.P = torch.zeros(self.n_params, device=dev)
         self.G = torch.zeros(self.n_params, device=dev)
         self.M = torch.zeros(self.n_params, device=dev)
-        self.PB = torch.zeros(self.n_params, device=dev, dtype=torch.bfloat16)
+        self.PB = None if self.fp32 else torch.zeros(self.n_params, device=dev, dtype=torch.bfloat16)
         self.bn_state: Dict[int, Dict[str, torch.Tensor]] = {}
         for b in self.blocks:
             if isinstance(b, ConvBlock) and b.bn is not None:
@@ -263,6 +285,10 @@ class B200Executor(StageExecutor):
     def view(self, buf: torch.Tensor, key: str) -> torch.Tensor:
         off, shape = self.entries[key]
         return buf[off:off + math.prod(shape)].view(shape)
+
+    def W(self, key: str) -> torch.Tensor:
+        """The tensor the GEMMs read: the fp32 master itself (tf32 mode) or its bf16 shadow."""
+        return self.view(self.P if self.fp32 else self.PB, key)
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         with torch.no_grad():
@@ -275,7 +301,8 @@ class B200Executor(StageExecutor):
                 for k in st:
                     if f"layer{bn}.{k}" in sd:
                         st[k].copy_(sd[f"layer{bn}.{k}"].to(self.device))
-            self.PB.copy_(self.P)
+            if self.PB is not None:
+                self.PB.copy_(self.P)
         torch.cuda.synchronize(self.device)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
@@ -308,8 +335,8 @@ class B200Executor(StageExecutor):
         if self.in_kind == "image":
             if x.dim() == 4 and x.shape[1] == self.in_shape[0] and x.shape[-1] != self.in_shape[0]:
                 x = x.permute(0, 2, 3, 1)                # NCHW wire -> NHWC
-            return x.to(torch.bfloat16).contiguous()
-        return x.to(torch.bfloat16).contiguous()
+            return x.to(self.act_dtype).contiguous()
+        return x.to(self.act_dtype).contiguous()
 
     def _from_internal_out(self, t: torch.Tensor) -> torch.Tensor:
         if self.out_kind == "image":
@@ -346,7 +373,7 @@ class B200Executor(StageExecutor):
         g = grad.to(self.device)
         if self.out_kind == "image" and g.dim() == 4 and g.shape[1] == self.out_shape[0] and g.shape[-1] != self.out_shape[0]:
             g = g.permute(0, 2, 3, 1)
-        g = g.to(torch.bfloat16)
+        g = g.to(self.act_dtype)
         self._enter()
         with torch.cuda.stream(self.stream):
             pl.dout_in.copy_(g, non_blocking=True)
@@ -397,7 +424,7 @@ class _Plan:
     def __init__(self, ex: B200Executor, B: int):
         self.ex, self.B = ex, B
         dev = ex.device
-        bf = torch.bfloat16
+        bf = ex.act_dtype                                  # activation dtype of this plan (fp32 in tf32 mode)
         self.n_slots = ex.slots if (ex.recompute or ex.is_last) else ex.slots
         self.free = list(range(self.n_slots))
         # ---- stage input slots
@@ -425,9 +452,9 @@ class _Plan:
                     reserve((bi, "sumsq"), b.cout)
                 if b.conv is not None and b.cin > 4:
                     M = B * b.H * b.W
-                    if N.conv_tiling(M, b.cout, b.cin)[1] > 1:
+                    if N.conv_tiling(M, b.cout, b.cin, ke=ex.ke)[1] > 1:
                         reserve((bi, "facc"), M * b.cout)           # split-K partial sums, forward
-                    if N.conv_tiling(M, b.cin, b.cout, flip=1)[1] > 1 and not (bi == 0 and ex.is_first):
+                    if N.conv_tiling(M, b.cin, b.cout, flip=1, ke=ex.ke)[1] > 1 and not (bi == 0 and ex.is_first):
                         reserve((bi, "dacc"), M * b.cin)            # split-K partial sums, dgrad
             elif isinstance(b, LinearBlock):
                 reserve((bi, "acc"), B * b.fout)
@@ -468,6 +495,7 @@ class _Plan:
         self.dlogits = torch.zeros(B, ex.num_classes, device=dev) if ex.is_last else None
         self.ticket = torch.zeros(4, device=dev, dtype=torch.int32)
         self.tile_counters = torch.zeros(4096, device=dev, dtype=torch.int32)   # split-K tile semaphores (self-resetting)
+        self.gnorm = torch.zeros(4, device=dev)                                 # clip-grad-norm: sum of squared gradients
         # weight-gradient kernels run on a forked stream: they only feed the optimizer, so they overlap with the
         # dY -> dX critical path of the layers below (captured as parallel branches of the CUDA graph)
         self.side = torch.cuda.Stream(device=dev, priority=ex.stream_priority)
@@ -515,7 +543,7 @@ class _Plan:
                 if plain:
                     tgt = a["y"] if not (is_final and out_ptr_override is not None) else out_ptr_override
                     facc = self.s(bi, "facc") if (bi, "facc") in self.soff else None
-                    N.conv3x3_fwd(x, ex.view(ex.PB, f"layer{b.conv}.weight"), tgt, ex.view(ex.P, f"layer{b.conv}.bias"),
+                    N.conv3x3_fwd(x, ex.W(f"layer{b.conv}.weight"), tgt, ex.view(ex.P, f"layer{b.conv}.bias"),
                                   acc=facc, counters=self.tile_counters)
                     if is_final and publish is not None:
                         N.set_flag(publish["flag"].data_ptr() if hasattr(publish["flag"], "data_ptr") else publish["flag"],
@@ -525,7 +553,7 @@ class _Plan:
                     x = tgt
                     continue
                 fuse = (ex.fused_cut and is_final and out_ptr_override is not None and b.conv is not None and b.bn is not None
-                        and b.cin > 4 and N.fused_cut_supported(self.B, b.H, b.W, b.cin, b.cout, b.pool))
+                        and b.cin > 4 and N.fused_cut_supported(self.B, b.H, b.W, b.cin, b.cout, b.pool, ke=ex.ke))
                 if fuse:
                     # cut-tail kernel: GEMM + BN statistics + BN/ReLU/pool + store into the (peer) mailbox + flag
                     st = ex.bn_state[b.bn]
@@ -536,7 +564,7 @@ class _Plan:
                     kw = {}
                     if publish is not None:
                         kw = dict(flag=publish["flag"], seq=publish["seq"], hint=publish.get("hint"))
-                    N.conv_bn_act_p2p(x, ex.view(ex.PB, f"layer{b.conv}.weight"), ex.view(ex.P, f"layer{b.conv}.bias"),
+                    N.conv_bn_act_p2p(x, ex.W(f"layer{b.conv}.weight"), ex.view(ex.P, f"layer{b.conv}.bias"),
                                       ex.view(ex.P, f"layer{b.bn}.weight"), ex.view(ex.P, f"layer{b.bn}.bias"),
                                       st["running_mean"], st["running_var"], st["num_batches_tracked"], a["save_mean"],
                                       a["save_invstd"], self.s(bi, "sum"), self.s(bi, "sumsq"), keep_y, out_ptr_override,
@@ -551,7 +579,7 @@ class _Plan:
                         N.conv3x3_small_fwd(x, ex.view(ex.P, f"layer{b.conv}.weight"), bias, a["y"], s1, s2)
                     else:
                         facc = self.s(bi, "facc") if (bi, "facc") in self.soff else None
-                        N.conv3x3_fwd(x, ex.view(ex.PB, f"layer{b.conv}.weight"), a["y"], bias, s1, s2, acc=facc,
+                        N.conv3x3_fwd(x, ex.W(f"layer{b.conv}.weight"), a["y"], bias, s1, s2, acc=facc,
                                       counters=self.tile_counters)
                     y = a["y"]
                 else:
@@ -583,8 +611,11 @@ class _Plan:
                 xin = x.reshape(self.B, -1)
                 a["in"] = xin
                 acc = self.s(bi, "acc", (self.B, b.fout))
-                w = ex.view(ex.PB, f"layer{b.lin}.weight")
-                N.linear_fwd(xin, w, acc, k_split=max(1, min(8, (b.fin // 64) // 8)))
+                w = ex.W(f"layer{b.lin}.weight")
+                if ex.fp32:
+                    N.linear_fwd_f32(xin, w, acc)
+                else:
+                    N.linear_fwd(xin, w, acc, k_split=max(1, min(8, (b.fin // 64) // 8)))
                 N.linear_finalize(acc, ex.view(ex.P, f"layer{b.lin}.bias"), a["out"], a["logits"], a["mask"], b.relu,
                                   b.drop, ex.seed + b.lin, ex.step_ctr)
                 x = a["out"]
@@ -597,9 +628,13 @@ class _Plan:
         side = self.side
         forked = False
 
+        clip = ex.clip > 0.0                       # clip-grad-norm: the update needs the global norm -> one SGD at the end
+
         def sgd_block(bi):
+            if clip:
+                return
             lo, hi = ex.block_range[bi]
-            N.sgd_momentum(ex.P[lo:hi], ex.G[lo:hi], ex.M[lo:hi], ex.PB[lo:hi], ex.lr, ex.mu)
+            N.sgd_momentum(ex.P[lo:hi], ex.G[lo:hi], ex.M[lo:hi], None if ex.PB is None else ex.PB[lo:hi], ex.lr, ex.mu)
 
         def on_side(fn):
             """Run ``fn`` (weight-gradient launches) on the side stream after everything issued so far on ``main``."""
@@ -620,22 +655,35 @@ class _Plan:
                 if g.dtype != torch.float32:
                     g = g.float()                                   # compat path only (outside graphs)
                 N.linear_bwd_prep(g, a["out"], a["mask"], a["dz"], ex.view(ex.G, f"layer{b.lin}.bias"), b.relu, b.drop)
-                on_side(lambda a=a, b=b: N.linear_wgrad(a["dz"], a["in"], ex.view(ex.G, f"layer{b.lin}.weight")))
+                wkey, bkey = f"layer{b.lin}.weight", f"layer{b.lin}.bias"
+                fuse_sgd = ex.fp32 and not clip and self.B <= 32
+                if not ex.fp32:
+                    on_side(lambda a=a, b=b: N.linear_wgrad(a["dz"], a["in"], ex.view(ex.G, f"layer{b.lin}.weight")))
+                elif not fuse_sgd:
+                    on_side(lambda a=a, wkey=wkey: N.linear_wgrad_f32(a["dz"], a["in"], g=ex.view(ex.G, wkey)))
                 if need_dx:
                     dacc = self.s(bi, "dacc_in", (self.B, b.fin))
-                    N.linear_dgrad(a["dz"], ex.view(ex.PB, f"layer{b.lin}.weight"), dacc,
-                                   k_split=max(1, min(8, (b.fout // 64) // 8)))
+                    if ex.fp32:
+                        N.linear_dgrad_f32(a["dz"], ex.W(wkey), dacc)
+                    else:
+                        N.linear_dgrad(a["dz"], ex.W(wkey), dacc, k_split=max(1, min(8, (b.fout // 64) // 8)))
                     g = dacc
-                    if bi == 0:                                     # stage input gradient leaves as bf16
+                    if bi == 0:                                     # stage input gradient leaves in the activation dtype
                         N.dropout_bwd(dacc, None, a["dx_bf16"], 0.0)
                 # this block's optimizer step runs on the side stream as soon as its dgrad (the last reader of the
-                # bf16 weights) has been issued: the 134 MB classifier update hides behind the conv backward chain
-                on_side(lambda bi=bi: sgd_block(bi))
+                # weights) has been issued: the 134 MB classifier update hides behind the conv backward chain.  In
+                # tf32 mode the update rides on the weight-gradient pass itself (no gradient buffer traffic at all).
+                if fuse_sgd:
+                    on_side(lambda a=a, wkey=wkey, bkey=bkey: N.linear_wgrad_f32(
+                        a["dz"], a["in"], sgd=(ex.view(ex.P, wkey), ex.view(ex.M, wkey), ex.view(ex.P, bkey), ex.view(ex.M, bkey),
+                                               ex.view(ex.G, bkey), ex.lr, ex.mu)))
+                else:
+                    on_side(lambda bi=bi: sgd_block(bi))
             elif isinstance(b, DropoutOp):
                 N.dropout_bwd(g, a["mask"], a["dx"], b.p)
                 g = a["dx"]
             else:
-                if g.dtype == torch.float32:                        # from a Linear block straight into a conv block
+                if g.dtype != ex.act_dtype:                         # fp32 accumulator of a Linear block into a bf16 conv block
                     tmp = a["dout_bf16"]
                     N.dropout_bwd(g, None, tmp, 0.0)
                     g = tmp
@@ -671,14 +719,14 @@ class _Plan:
                             dacc = self.s(bi, "dacc") if (bi, "dacc") in self.soff else None
                             stats = None
                             up = ex.blocks[bi - 1] if bi > 0 else None
-                            if (ex.fused_bn_stats and isinstance(up, ConvBlock) and up.conv is not None and up.bn is not None
+                            if (ex.fused_bn_stats and not ex.fp32 and isinstance(up, ConvBlock) and up.conv is not None and up.bn is not None
                                     and (ex.fused_bn_stats >= 2 or not up.pool) and dx is a["dx"]):
                                 ua = self.act[bi - 1]
                                 stats = (ua["y_eff"], ua["save_mean"], ua["save_invstd"], ex.view(ex.P, f"layer{up.bn}.weight"),
                                          ex.view(ex.P, f"layer{up.bn}.bias"), up.relu, up.pool, ex.view(ex.G, f"layer{up.bn}.weight"),
                                          ex.view(ex.G, f"layer{up.bn}.bias"))
                                 bn_reduced.add(bi - 1)
-                            N.conv3x3_dgrad(dy, ex.view(ex.PB, f"layer{b.conv}.weight"), dx, acc=dacc, counters=self.tile_counters,
+                            N.conv3x3_dgrad(dy, ex.W(f"layer{b.conv}.weight"), dx, acc=dacc, counters=self.tile_counters,
                                             bn_stats=stats)
                             g = dx
                 else:
@@ -687,6 +735,12 @@ class _Plan:
                     on_side(lambda bi=bi: sgd_block(bi))
         if forked:
             main.wait_stream(side)                      # join: every weight gradient and parameter update is complete
+        if clip:
+            # torch.nn.utils.clip_grad_norm_ + optimizer.step() (other/Vanilla_SL/src/Scheduler.py:204-205) on the flat buffers
+            N.zero_(self.gnorm)
+            N.sumsq(ex.G, self.gnorm)
+            N.clip_scale(ex.G, self.gnorm, ex.clip)
+            N.sgd_momentum(ex.P, ex.G, ex.M, ex.PB, ex.lr, ex.mu)
         N.counter_inc(ex.step_ctr)
 
     def _last(self, slot: int = 0, labels: Optional[torch.Tensor] = None, grad_out_override=None) -> None:

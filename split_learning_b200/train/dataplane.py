@@ -23,7 +23,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from ..transport import Channel
+from ..transport import Channel, codec
 
 
 class QueueGrammar:
@@ -106,7 +106,7 @@ class HostDataPlane:
             torch.cuda.current_stream(torch.device(self.device)).wait_event(ev)
             return t.to(self.device, non_blocking=True)
         if isinstance(d, dict) and "__cuda_ipc__" in d:
-            src = pickle.loads(d["__cuda_ipc__"])          # maps the producer's block (peer memory if another GPU)
+            src = codec.loads_cuda_ipc(d["__cuda_ipc__"])  # maps the producer's block (peer memory if another GPU)
             out = src.to(self.device, non_blocking=False)
             if out.data_ptr() == src.data_ptr():           # same GPU: detach from the producer's allocation
                 out = src.clone()
@@ -119,16 +119,13 @@ class HostDataPlane:
         trace = list(trace) + [self.client_id] if trace else [self.client_id]
         q = self.grammar.forward_queue(self.layer_id, self.cluster, target)
         lab = labels.detach().cpu() if isinstance(labels, torch.Tensor) else labels
-        self.ch.basic_publish(q, pickle.dumps(
-            {"data_id": data_id, "data": self._pack(output), "label": lab, "trace": trace},
-            protocol=pickle.HIGHEST_PROTOCOL))
+        self.ch.basic_publish(q, codec.dumps({"data_id": data_id, "data": self._pack(output), "label": lab, "trace": trace}))
 
     def send_gradient(self, data_id, gradient: torch.Tensor, trace: List) -> None:
         trace = list(trace)
         to_client = trace.pop(-1)
         q = self.grammar.gradient_queue(self.layer_id - 1, to_client)
-        self.ch.basic_publish(q, pickle.dumps(
-            {"data_id": data_id, "data": self._pack(gradient), "trace": trace}, protocol=pickle.HIGHEST_PROTOCOL))
+        self.ch.basic_publish(q, codec.dumps({"data_id": data_id, "data": self._pack(gradient), "trace": trace}))
 
     # ---- consumer side -------------------------------------------------
     def recv_forward(self, timeout: float = 0.0, source=None):
@@ -136,7 +133,7 @@ class HostDataPlane:
         body = self.ch.basic_get(q, timeout)
         if body is None:
             return None
-        m = pickle.loads(body)
+        m = codec.loads(body)
         m["data"] = self._unpack(m["data"])
         if isinstance(m.get("label"), torch.Tensor):
             m["label"] = m["label"].to(self.device)
@@ -146,6 +143,6 @@ class HostDataPlane:
         body = self.ch.basic_get(self.my_grad_q, timeout)
         if body is None:
             return None
-        m = pickle.loads(body)
+        m = codec.loads(body)
         m["data"] = self._unpack(m["data"])
         return m

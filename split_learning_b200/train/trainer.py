@@ -46,14 +46,21 @@ class StageTrainer:
         self.verbose = verbose
         self.reply_q = M.reply_queue(client_id)
         self.pause_msg: Optional[dict] = None
+        self.alive_at = time.monotonic()          # last heartbeat relayed by the server: idle timers restart from here
 
     # ------------------------------------------------------------------
     def _send_to_server(self, msg) -> None:
         self.ch.publish_obj(M.RPC_QUEUE, msg)
 
     def _poll_pause(self, timeout: float = 0.0) -> bool:
+        if self.pause_msg is not None:
+            return True
         m = self.ch.get_obj(self.reply_q, timeout)
         if m is None:
+            return False
+        if m.get("action") == M.HEARTBEAT:       # aged by its send time: a backlog of old beacons proves nothing
+            age = max(0.0, time.time() - float(m.get("t", time.time())))
+            self.alive_at = max(self.alive_at, time.monotonic() - age)
             return False
         if m.get("action") == M.PAUSE:
             self.pause_msg = m
@@ -64,10 +71,26 @@ class StageTrainer:
         return False
 
     def _wait_pause(self) -> None:
+        # PAUSE arrives when the *slowest* first-stage peer of the cluster has finished (src/Server.py:137-153): that can
+        # take arbitrarily long on a healthy run, so the wait is bounded by server silence (heartbeats), not by wall time
         t0 = time.monotonic()
         while not self._poll_pause(0.05):
-            if time.monotonic() - t0 > self.watchdog:
-                raise TimeoutError(f"client {self.client_id}: no PAUSE within {self.watchdog}s")
+            if time.monotonic() - max(t0, self.alive_at) > self.watchdog:
+                raise TimeoutError(f"client {self.client_id}: no PAUSE and no server heartbeat for {self.watchdog}s")
+
+    def _idle_too_long(self, since: float) -> bool:
+        return time.monotonic() - max(since, self.alive_at) > self.watchdog
+
+    def _check_stop(self) -> None:
+        """While blocked on the data plane, keep reading the control queue: heartbeats refresh the watchdog, STOP (the
+        server aborting the run, e.g. a dead peer) ends the loop instead of waiting for data that will never come."""
+        for _ in range(64):                       # drain the beacons that piled up while this loop was busy
+            if self._poll_pause(0.0):
+                if self.pause_msg.get("action") == M.STOP:
+                    raise RuntimeError(f"client {self.client_id}: server stopped the run")
+                return
+            if self.ch.queue_depth(self.reply_q) == 0:
+                return
 
     # ------------------------------------------------------------------
     def train_on_first_layer(self, learning: dict, train_loader, cluster=None, local_round: int = 1,
@@ -95,7 +118,10 @@ class StageTrainer:
                         self.ex.backward(g["data_id"], g["data"])
                         nb += 1
                         last_progress = time.monotonic()
-                    elif time.monotonic() - last_progress > self.watchdog:
+                    elif self._idle_too_long(last_progress):
+                        self._check_stop()            # read the control queue (heartbeats / STOP) before giving up
+                        if not self._idle_too_long(last_progress):
+                            continue
                         raise TimeoutError(f"stage-1 client {self.client_id}: gradient never arrived "
                                            f"({nf} sent / {nb} received)")
                 else:
@@ -151,8 +177,8 @@ class StageTrainer:
                 if pending:                       # flush a partial SDA group before leaving
                     self._sda_step(pending)
                 break
-            if time.monotonic() - idle_since > self.watchdog:
-                raise TimeoutError(f"last-stage client {self.client_id}: idle for {self.watchdog}s without PAUSE")
+            if self._idle_too_long(idle_since):
+                raise TimeoutError(f"last-stage client {self.client_id}: idle for {self.watchdog}s without PAUSE or heartbeat")
         return (not self.ex.nan_detected()), self.data_count
 
     def _sda_step(self, group: List[dict]) -> None:
@@ -188,6 +214,6 @@ class StageTrainer:
                 continue
             if not traces and self._poll_pause(0.0):
                 break
-            if time.monotonic() - idle_since > self.watchdog:
+            if self._idle_too_long(idle_since):
                 raise TimeoutError(f"middle-stage client {self.client_id}: idle for {self.watchdog}s")
         return (not self.ex.nan_detected()), self.data_count

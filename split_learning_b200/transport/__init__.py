@@ -7,6 +7,7 @@ single-process runs/tests; for one-process-per-GPU runs the native C++ daemon ``
 fallback — one binary length-prefixed protocol, ``TcpChannel`` on the client side.  On CUDA the *data plane* does not go
 through here at all (see ``parallel/mailbox.py``); only the seven control verbs do.
 """
+from . import codec
 from .broker import Channel, InProcBroker, NativeBroker, TcpBroker, TcpChannel, build_native_broker, connect, make_broker
 
-__all__ = ["Channel", "InProcBroker", "NativeBroker", "TcpBroker", "TcpChannel", "build_native_broker", "connect", "make_broker"]
+__all__ = ["codec", "Channel", "InProcBroker", "NativeBroker", "TcpBroker", "TcpChannel", "build_native_broker", "connect", "make_broker"]

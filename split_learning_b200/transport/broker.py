@@ -24,13 +24,20 @@ class Channel:
     def list_queues(self): ...
     def close(self) -> None: ...
 
-    # convenience
+    # convenience: messages are pickled dicts (the reference's wire format) written / read by ``codec`` — tensors as raw
+    # bytes and a *restricted* unpickler, so bytes arriving on a queue can never execute code (see transport/codec.py)
     def publish_obj(self, routing_key: str, obj) -> None:
-        self.basic_publish(routing_key, pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL))
+        from . import codec
+        self.basic_publish(routing_key, codec.dumps(obj))
 
     def get_obj(self, queue: str, timeout: float = 0.0):
+        from . import codec
         body = self.basic_get(queue, timeout)
-        return None if body is None else pickle.loads(body)
+        return None if body is None else codec.loads(body)
+
+    def clone(self) -> "Channel":
+        """A channel usable concurrently from another thread (heartbeats): the in-process broker is thread-safe as is."""
+        return self
 
 
 class InProcBroker(Channel):
@@ -90,7 +97,33 @@ class InProcBroker(Channel):
 #   request : u8 op | u32 queue_len | u64 arg_len | queue bytes | arg bytes
 #   reply   : u8 status | u64 len | payload            (no reply for PUB)
 # ---------------------------------------------------------------------------
-OP_PUB, OP_GET, OP_DECLARE, OP_DELETE, OP_PURGE, OP_DEPTH, OP_LIST, OP_PING, OP_SHUTDOWN = range(1, 10)
+#   OP_AUTH (arg = shared token) must be the first request of a connection when the broker was started with a token;
+#   OP_SHUTDOWN is honoured for loopback peers only.
+OP_PUB, OP_GET, OP_DECLARE, OP_DELETE, OP_PURGE, OP_DEPTH, OP_LIST, OP_PING, OP_SHUTDOWN, OP_AUTH = range(1, 11)
+
+
+def is_loopback(host: str) -> bool:
+    return host in ("127.0.0.1", "localhost", "::1") or host.startswith("127.")
+
+
+def broker_token(cfg) -> str:
+    """Shared secret of the broker: ``b200.broker-token`` (or ``rabbit.password`` when a non-loopback ``rabbit.address``
+    is configured — the reference's RabbitMQ credential doubles as ours), overridden by ``SLB200_BROKER_TOKEN``."""
+    env = os.environ.get("SLB200_BROKER_TOKEN")
+    if env:
+        return env
+    tok = str(cfg.b200.get("broker-token") or "")
+    rabbit = cfg.raw.get("rabbit", {}) or {}
+    if not tok and not is_loopback(str(rabbit.get("address", "127.0.0.1"))):
+        tok = str(rabbit.get("password") or "")
+    return tok
+
+
+def check_bind(host: str, token: str) -> None:
+    """The broker carries the control plane and (host plane) the training tensors: never expose it unauthenticated."""
+    if not is_loopback(host) and not token:
+        raise PermissionError(f"refusing to bind the broker to {host!r} without a shared token: set b200.broker-token "
+                              "(or SLB200_BROKER_TOKEN) on the server and every client, or bind to 127.0.0.1")
 _REQ = struct.Struct("<BIQ")
 _REP = struct.Struct("<BQ")
 
@@ -124,7 +157,9 @@ class TcpBroker:
 
     kind = "python"
 
-    def __init__(self, host: str = "127.0.0.1", port: int = 29777):
+    def __init__(self, host: str = "127.0.0.1", port: int = 29777, token: Optional[str] = None):
+        self.token = token if token is not None else os.environ.get("SLB200_BROKER_TOKEN", "")
+        check_bind(host, self.token)
         self.store = InProcBroker()
         self._srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
         self._srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
@@ -140,15 +175,17 @@ class TcpBroker:
     def _accept_loop(self):
         while not self._stop:
             try:
-                conn, _ = self._srv.accept()
+                conn, peer = self._srv.accept()
             except OSError:
                 return
             conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
-            t = threading.Thread(target=self._serve, args=(conn,), daemon=True)
+            t = threading.Thread(target=self._serve, args=(conn, peer[0]), daemon=True)
             t.start()
 
-    def _serve(self, conn: socket.socket):
+    def _serve(self, conn: socket.socket, peer_host: str = "127.0.0.1"):
+        import hmac
         s = self.store
+        authed = not self.token
 
         def reply(status: int, payload: bytes = b""):
             conn.sendall(_REP.pack(status, len(payload)) + payload)
@@ -157,6 +194,14 @@ class TcpBroker:
                 op, qlen, alen = _REQ.unpack(_recv_exact(conn, _REQ.size))
                 queue = _recv_exact(conn, qlen).decode() if qlen else ""
                 arg = _recv_exact(conn, alen) if alen else b""
+                if op == OP_AUTH:
+                    authed = (not self.token) or hmac.compare_digest(arg, self.token.encode())
+                    reply(1 if authed else 0)
+                    if not authed:
+                        return
+                    continue
+                if not authed:                            # unauthenticated peer: drop the connection
+                    return
                 if op == OP_PUB:
                     s.basic_publish(queue, arg)           # fire-and-forget, like basic_publish
                 elif op == OP_GET:
@@ -178,6 +223,8 @@ class TcpBroker:
                 elif op == OP_PING:
                     reply(1)
                 elif op == OP_SHUTDOWN:
+                    if not is_loopback(peer_host):        # only the box itself may stop the broker
+                        return
                     reply(1)
                     self.close()
                     return
@@ -201,7 +248,7 @@ class TcpBroker:
 
 
 class TcpChannel(Channel):
-    def __init__(self, host: str = "127.0.0.1", port: int = 29777, retry_seconds: float = 60.0):
+    def __init__(self, host: str = "127.0.0.1", port: int = 29777, retry_seconds: float = 60.0, token: Optional[str] = None):
         deadline = time.monotonic() + retry_seconds
         last = None
         while True:
@@ -216,6 +263,15 @@ class TcpChannel(Channel):
         self._sock.settimeout(None)
         self._sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
         self._lock = threading.Lock()
+        self._addr = (host, port)
+        self._token = token if token is not None else os.environ.get("SLB200_BROKER_TOKEN", "")
+        if self._token:
+            status, _ = self._call(OP_AUTH, "", self._token.encode())
+            if status != 1:
+                raise ConnectionError("broker rejected the shared token (b200.broker-token / SLB200_BROKER_TOKEN)")
+
+    def clone(self) -> "TcpChannel":
+        return TcpChannel(self._addr[0], self._addr[1], retry_seconds=5.0, token=self._token)
 
     def _call(self, op: int, queue: str, arg: bytes = b"", reply: bool = True):
         with self._lock:
@@ -288,9 +344,13 @@ class NativeBroker:
 
     kind = "native"
 
-    def __init__(self, host: str = "127.0.0.1", port: int = 29777):
+    def __init__(self, host: str = "127.0.0.1", port: int = 29777, token: Optional[str] = None):
+        self.token = token if token is not None else os.environ.get("SLB200_BROKER_TOKEN", "")
+        check_bind(host, self.token)
         exe = build_native_broker()
-        self._proc = subprocess.Popen([exe, "--host", host, "--port", str(port)], stdout=subprocess.PIPE, text=True)
+        env = dict(os.environ)
+        env["SLB200_BROKER_TOKEN"] = self.token           # the token travels in the environment, not on the command line
+        self._proc = subprocess.Popen([exe, "--host", host, "--port", str(port)], stdout=subprocess.PIPE, text=True, env=env)
         line = self._proc.stdout.readline()
         if not line.startswith("SLB_BROKER_READY"):
             self._proc.kill()
@@ -299,14 +359,15 @@ class NativeBroker:
         self._channels = []
 
     def channel(self) -> TcpChannel:
-        ch = TcpChannel(self.host, self.port, retry_seconds=5.0)
+        ch = TcpChannel(self.host, self.port, retry_seconds=5.0, token=self.token)
         self._channels.append(ch)
         return ch
 
     def close(self):
         if self._proc.poll() is None:
             try:
-                TcpChannel(self.host, self.port, retry_seconds=1.0).shutdown_broker()
+                TcpChannel("127.0.0.1" if self.host == "0.0.0.0" else self.host, self.port, retry_seconds=1.0,
+                           token=self.token).shutdown_broker()
             except (ConnectionError, OSError):
                 pass
             try:
@@ -317,19 +378,21 @@ class NativeBroker:
             ch.close()
 
 
-def make_broker(host: str = "127.0.0.1", port: int = 29777, kind: str = "native"):
+def make_broker(host: str = "127.0.0.1", port: int = 29777, kind: str = "native", token: Optional[str] = None):
     """The box-local broker replacing RabbitMQ: the C++ daemon, or the Python thread broker when asked for / when no
     compiler is available (both speak the same protocol, clients do not care)."""
+    tok = token if token is not None else os.environ.get("SLB200_BROKER_TOKEN", "")
+    check_bind(host, tok)
     if kind == "native":
         try:
-            return NativeBroker(host, port)
+            return NativeBroker(host, port, token=tok)
         except (RuntimeError, OSError) as e:
             print(f"[broker] native daemon unavailable ({e}); using the Python broker", flush=True)
-    return TcpBroker(host, port)
+    return TcpBroker(host, port, token=tok)
 
 
-def connect(address: str = "127.0.0.1", port: int = 29777, retry_seconds: float = 60.0) -> TcpChannel:
-    return TcpChannel(address, port, retry_seconds)
+def connect(address: str = "127.0.0.1", port: int = 29777, retry_seconds: float = 60.0, token: Optional[str] = None) -> TcpChannel:
+    return TcpChannel(address, port, retry_seconds, token=token)
 
 
 def delete_old_queues(channel: Channel) -> bool:

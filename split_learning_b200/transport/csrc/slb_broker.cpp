@@ -9,7 +9,10 @@
 //   request : u8 op | u32 queue_len | u64 arg_len | queue bytes | arg bytes
 //   reply   : u8 status | u64 len | payload            (no reply for PUB)
 //   ops     : 1 PUB(arg = body)  2 GET(arg = f64 timeout seconds)  3 DECLARE  4 DELETE  5 PURGE
-//             6 DEPTH(-> u64)  7 LIST(-> names joined by '\n')  8 PING  9 SHUTDOWN
+//             6 DEPTH(-> u64)  7 LIST(-> names joined by '\n')  8 PING  9 SHUTDOWN (loopback peers only)
+//             10 AUTH(arg = shared token): when the daemon has a token (environment SLB200_BROKER_TOKEN) this must be
+//                the first request of every connection; any other request on an unauthenticated connection closes it.
+//                The daemon refuses to bind a non-loopback address without a token.
 //
 //   slb_broker --host 127.0.0.1 --port 29777      prints "SLB_BROKER_READY <port>" once listening
 #include <arpa/inet.h>
@@ -34,6 +37,22 @@
 #include <unordered_map>
 
 namespace {
+
+std::string g_token;
+
+bool peer_is_loopback(int fd) {
+  sockaddr_in a{};
+  socklen_t n = sizeof(a);
+  if (::getpeername(fd, reinterpret_cast<sockaddr*>(&a), &n) != 0 || a.sin_family != AF_INET) return false;
+  return (ntohl(a.sin_addr.s_addr) >> 24) == 127;
+}
+
+bool token_equal(const std::string& a, const std::string& b) {     // constant-time compare
+  if (a.size() != b.size()) return false;
+  unsigned char d = 0;
+  for (size_t i = 0; i < a.size(); ++i) d |= static_cast<unsigned char>(a[i] ^ b[i]);
+  return d == 0;
+}
 
 struct Store {
   std::mutex m;
@@ -74,6 +93,7 @@ bool reply(int fd, uint8_t status, const std::string& payload) {
 void serve(int fd) {
   int one = 1;
   ::setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+  bool authed = g_token.empty();
   for (;;) {
     uint8_t hdr[13];
     if (!read_exact(fd, hdr, 13)) break;
@@ -93,6 +113,12 @@ void serve(int fd) {
     if (qlen && !read_exact(fd, &queue[0], qlen)) break;
     if (alen && !read_exact(fd, &arg[0], alen)) break;
     bool ok = true;
+    if (op == 10) {                                               // AUTH
+      authed = g_token.empty() || token_equal(arg, g_token);
+      if (!reply(fd, authed ? 1 : 0, "") || !authed) break;
+      continue;
+    }
+    if (!authed) break;                                           // unauthenticated peer: drop the connection
     switch (op) {
       case 1: {  // PUB
         {
@@ -180,7 +206,8 @@ void serve(int fd) {
       case 8:  // PING
         ok = reply(fd, 1, "");
         break;
-      case 9:  // SHUTDOWN
+      case 9:  // SHUTDOWN: only the box itself may stop the broker
+        if (!peer_is_loopback(fd)) { ok = false; break; }
         reply(fd, 1, "");
         ::_exit(0);
       default:
@@ -199,6 +226,11 @@ int main(int argc, char** argv) {
   for (int i = 1; i + 1 < argc; i += 2) {
     if (!std::strcmp(argv[i], "--host")) host = argv[i + 1];
     else if (!std::strcmp(argv[i], "--port")) port = std::atoi(argv[i + 1]);
+  }
+  if (const char* t = std::getenv("SLB200_BROKER_TOKEN")) g_token = t;
+  if (g_token.empty() && host.rfind("127.", 0) != 0) {
+    std::fprintf(stderr, "slb_broker: refusing to bind %s without SLB200_BROKER_TOKEN\n", host.c_str());
+    return 3;
   }
   ::prctl(PR_SET_PDEATHSIG, SIGTERM);            // never outlive the server process that started us
   ::signal(SIGPIPE, SIG_IGN);

@@ -12,8 +12,10 @@ def selftest():
     return selftest
 
 
-@pytest.mark.parametrize("name", ["conv_fwd", "conv_dgrad", "conv_dgrad_bn_stats", "conv_wgrad", "linear_all", "bn_fwd_bwd", "conv1_direct",
-                                  "ce_and_linear_epilogues", "optimizers_and_fedavg", "flags_and_peer"])
+@pytest.mark.parametrize("name", ["conv_fwd_tf32", "conv_dgrad_tf32", "conv_wgrad_tf32", "fused_cut_tail_tf32", "linear_f32", "bn_fwd_bwd_f32",
+                                  "conv1_direct_f32", "conv_fwd", "conv_dgrad", "conv_dgrad_bn_stats", "conv_wgrad", "fused_cut_tail",
+                                  "linear_all", "bn_fwd_bwd", "conv1_direct", "ce_and_linear_epilogues", "optimizers_and_fedavg",
+                                  "flags_and_peer"])
 def test_kernel(selftest, name):
     err, tol = selftest.CHECKS[name]()
     assert err <= tol, f"{name}: err {err} > tol {tol}"
