@@ -100,35 +100,39 @@ def child_main(layer_id: int, port: int, W: int, K: int, out_path: str, device: 
         json.dump({"layer": layer_id, "ms": ms, "wall_ms": (marks[1][0] - marks[0][0]) * 1e3 if len(marks) == 2 else 0.0}, f)
 
 
-def _single_box_processes(args, cfg, port: int, W: int, K: int) -> float:
-    """N = 1: server + broker here, one subprocess per client, both clients on cuda:0."""
+def _single_box_processes(args, cfg, port: int, W: int, K: int, device: str = "cuda:0", host_server: bool = True) -> float:
+    """One GPU's share of the ring / N = 1 deployment: (rank 0: server + broker here,) one subprocess per client — a
+    first-stage and a last-stage client — both on ``device``."""
     import subprocess
     import tempfile
     import pika
-    from src.Server import Server
-    pika.serve("127.0.0.1", port)
-    os.chdir("/tmp")
+    th = None
+    if host_server:
+        from src.Server import Server
+        pika.serve("127.0.0.1", port)
+        os.chdir("/tmp")
 
-    def serve():
-        try:
-            Server(copy.deepcopy(cfg)).start()
-        except SystemExit:
-            pass
-    th = threading.Thread(target=serve, daemon=True, name="ref-server")
-    th.start()
+        def serve():
+            try:
+                Server(copy.deepcopy(cfg)).start()
+            except SystemExit:
+                pass
+        th = threading.Thread(target=serve, daemon=True, name="ref-server")
+        th.start()
     outs, procs = [], []
     for layer in (1, 2):
         out = tempfile.mktemp(prefix=f"ref_l{layer}_", suffix=".json")
         outs.append(out)
         log = open(out + ".log", "w")
         procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--child", str(layer), str(port), str(W), str(K),
-                                       out, "cuda:0"], stdout=subprocess.DEVNULL, stderr=log))
+                                       out, device], stdout=subprocess.DEVNULL, stderr=log))
     for p in procs:
         try:
             p.wait(args.timeout)
         except subprocess.TimeoutExpired:
             p.kill()
-    th.join(60)
+    if th is not None:
+        th.join(60)
     ms = 0.0
     for o in outs:
         if os.path.exists(o):
@@ -164,8 +168,12 @@ def main(args, transport: str = "broker") -> dict:
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
     W, K = args.warmup, args.steps
-    n_first = max(1, n // 2)
-    n_last = max(1, n - n_first) if n > 1 else 1
+    ring = transport == "broker" and getattr(args, "placement", "ring") == "ring" and n > 1
+    if ring:                                     # same deployment as our arm: N chains, 2 clients (stage 1 + stage 2) per GPU
+        n_first = n_last = n
+    else:
+        n_first = max(1, n // 2)
+        n_last = max(1, n - n_first) if n > 1 else 1
     batches = W + K + 4
     cfg = _config(n_first, n_last, batches)
     port = 29655 + (int(os.environ.get("MASTER_PORT", "0")) % 97)
@@ -179,6 +187,25 @@ def main(args, transport: str = "broker") -> dict:
             return {"impl": "reference", "unavailable": "timing marks missing (single-box process mode)"}
         return _result(n, n_first, n_last, K, W, ms_total, outcome, time.perf_counter() - t_wall,
                        "one OS process per client (both on cuda:0) + server/broker process")
+    if ring:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(device))
+        t_wall = time.perf_counter()
+        ms_local = _single_box_processes(args, cfg, port, W, K, device=device, host_server=(rank == 0))
+        t = torch.tensor([ms_local], device=device)
+        bad = torch.tensor([float(ms_local <= 0)], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return {}
+        if float(bad.item()) > 0:
+            return {"impl": "reference", "unavailable": "timing marks missing on some rank (ring deployment)"}
+        res = _result(n, n_first, n_last, K, W, float(t.item()), outcome, time.perf_counter() - t_wall,
+                      "ring: one first-stage and one last-stage client process per GPU (+ server/broker on rank 0)")
+        res["config"]["placement"] = "ring"
+        return res
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16"],
                     help="tf32 (default) = the reference's precision: fp32 tensors, tcgen05 kind::tf32 convolutions with fp32 "
                          "accumulation, fp32 Linear/BN/SGD; bf16 = opt-in fast mode")
+    ap.add_argument("--placement", default="ring", choices=["ring", "split"],
+                    help="N > 1: ring = N chains, GPU r hosts stage 1 of chain r and stage 2 of chain r-1 (default; per-GPU work "
+                         "constant in N); split = clients [N/2, N/2], one stage replica per GPU (BASELINE configs #2/#3)")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the cross-GPU vs single-GPU loss-trajectory check")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--timeout", type=float, default=1500.0)
     ap.add_argument("--breakdown", action="store_true", help="also report device time per stage program (F / L / B)")

@@ -51,7 +51,8 @@ struct FusedSmem {
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int MAX_TILES = 512 / BLOCK_N;
   static constexpr int TAIL_BYTES = 4096;
-  static constexpr int TOTAL = TILE_BYTES + TAIL_BYTES + 1024;
+  static constexpr int TR_BYTES = 4 * 32 * 33 * 4;   // warp-private transpose tiles of the statistics reduction
+  static constexpr int TOTAL = TILE_BYTES + TAIL_BYTES + TR_BYTES + 1024;
   static_assert(TILE_BYTES >= 128 * 33 * 4, "staging tile must fit in the pipeline buffers");
 };
 
@@ -78,14 +79,17 @@ conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   using OT = OperandTraits<T>;
   constexpr int KE = OT::KE;          // K elements (channels) per 128-byte pipeline stage: 64 bf16 / 32 tf32
   pdl_trigger();
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // __align__(1024): the dynamic shared-memory window starts on a swizzle-atom boundary, and — unlike rounding the pointer
+  // up by hand through an integer cast — the compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::TILE_BYTES);
   uint64_t* empty_bar = full_bar + L::STAGES;
   uint64_t* accum_bar = empty_bar + L::STAGES;                  // [MAX_TILES]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + L::MAX_TILES);
   float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);     // [BLOCK_N]
   float* s_shift = s_scale + BLOCK_N;                           // [BLOCK_N]
+  float* s_bias = s_shift + BLOCK_N;                            // [BLOCK_N] bias of the current tile's columns
+  float* s_tr_all = reinterpret_cast<float*>(smem + L::TILE_BYTES + L::TAIL_BYTES);   // 4 x [32][33]
   float* s_stage = reinterpret_cast<float*>(smem);              // [128][33] fp32, reuses the pipeline buffers
 
   const int warp = threadIdx.x >> 5;
@@ -170,24 +174,34 @@ conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int m0 = (t / p.tiles_n) * 128, n0 = (t % p.tiles_n) * BLOCK_N;
       const int row = m0 + lrow;
       const bool row_ok = row < p.M;
+      asm volatile("bar.sync 1, 128;");                 // previous tile's readers are done with s_bias
+      for (int i = et; i < BLOCK_N; i += 128) s_bias[i] = __ldg(p.bias + n0 + i);   // overlaps the tile's MMAs
+      asm volatile("bar.sync 1, 128;");
       mbar_wait(&accum_bar[j], 0);
       tc_fence_after();
+      float* s_tr = s_tr_all + (warp - 2) * (32 * 33);
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * BLOCK_N + c, v);
         tmem_ld_wait();
-        float s1[32], s2[32];
+        float s1[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = row_ok ? __uint_as_float(v[i]) + __ldg(p.bias + n0 + c + i) : 0.f;
-          s1[i] = x;
-          s2[i] = x * x;
-        }
+        for (int i = 0; i < 32; ++i) s1[i] = row_ok ? __uint_as_float(v[i]) + s_bias[c + i] : 0.f;
         if (p.y != nullptr && row_ok)
           store_row32(reinterpret_cast<T*>(p.y) + static_cast<long long>(row) * p.N + n0 + c, s1);
-        const float c1 = warp_col_reduce32f(s1);
-        const float c2 = warp_col_reduce32f(s2);
+        // column sums through the warp-private transpose tile (lane l writes its row, reads column l)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s_tr[lane_id() * 33 + i] = s1[i];
+        __syncwarp();
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const float x = s_tr[r * 33 + lane_id()];
+          c1 += x;
+          c2 = fmaf(x, x, c2);
+        }
+        __syncwarp();
         atomicAdd(p.sum + n0 + c + lane_id(), c1);
         atomicAdd(p.sumsq + n0 + c + lane_id(), c2);
       }
@@ -215,6 +229,7 @@ conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int m0 = mt * 128, n0 = (t % p.tiles_n) * BLOCK_N;
       for (int c = et; c < BLOCK_N; c += 128) {
         const int ch = n0 + c;
+        s_bias[c] = __ldg(p.bias + ch);
         const float mean = __ldcg(p.sum + ch) * invM;
         const float var = fmaxf(__ldcg(p.sumsq + ch) * invM - mean * mean, 0.f);
         const float invstd = rsqrtf(var + p.eps);
@@ -243,7 +258,7 @@ conv_bn_act_p2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         float z[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float x = fmaf(__uint_as_float(v[i]) + __ldg(p.bias + n0 + c + i), s_scale[c + i], s_shift[c + i]);
+          float x = fmaf(__uint_as_float(v[i]) + s_bias[c + i], s_scale[c + i], s_shift[c + i]);
           if (p.relu) x = fmaxf(x, 0.f);
           z[i] = x;
         }

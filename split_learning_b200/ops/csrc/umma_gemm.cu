@@ -65,6 +65,7 @@ struct GemmParams {
   int bnb_pool;                   // 1: the upstream block ends in MaxPool2 — dX lives on the pooled grid (H x W here),
                                   //    bnb_y on the 2H x 2W grid; the gradient goes to the window's (first) maximum
   // transformer epilogue (EPI_BF16, MODE_GEMM): out = act(acc + bias + residual); aux_out keeps the pre-activation
+  long long* trace;               // optional [16] cycle stamps of CTA (0,0,0) (tools/trace_gemm.py): where a launch spends its time
   int act;                        // 0 none, 1 ReLU, 2 GELU (erf), 3 tanh
   __nv_bfloat16* aux_out;         // [M][ldo] or nullptr
   const __nv_bfloat16* residual;  // [M][ldo] or nullptr
@@ -102,6 +103,26 @@ __device__ __forceinline__ float warp_col_reduce32(float (&v)[32]) {
     }
   }
   return v[0];
+}
+
+// Column sums of a 32 x 32 block held one row per lane (f[j] = column j of this lane's row), through a warp-private
+// [32][33] shared-memory tile: lane l writes its row, then reads column l top to bottom.  Returns sum and sum of squares
+// of column `lane` — about a third of the instructions of the register butterfly (measured 0.78 us -> ~0.25 us per chunk).
+__device__ __forceinline__ void warp_col_sums_smem(float* tile, const float (&f)[32], float& c1, float& c2) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = f[j];
+  __syncwarp();
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const float x = tile[r * 33 + lane];
+    a += x;
+    b = fmaf(x, x, b);
+  }
+  __syncwarp();
+  c1 = a;
+  c2 = b;
 }
 
 // Per-element terms of the two column reductions of an epilogue chunk (row = pixel, 32 consecutive channels):
@@ -201,8 +222,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   static_assert(!BNB || !OT::TF32, "the fused BatchNorm-backward epilogue is a bf16-only option");
   constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   pdl_trigger();                      // the next kernel may start its prologue now
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // __align__(1024): the dynamic shared-memory window starts on a swizzle-atom boundary, and — unlike rounding the pointer
+  // up by hand through an integer cast — the compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::TILE_BYTES);
   uint64_t* empty_bar = full_bar + L::STAGES;
   uint64_t* accum_bar = empty_bar + L::STAGES;
@@ -212,6 +234,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int m_tile = blockIdx.x, n_tile = blockIdx.y, z = blockIdx.z;
   const int m0 = m_tile * 128, n0 = n_tile * BLOCK_N;
+  long long* const tr = (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.trace : nullptr;
+#define SLB_STAMP(i) do { if (tr != nullptr) tr[i] = clock64(); } while (0)
+  if (threadIdx.x == 0) SLB_STAMP(0);
 
   // K range of this CTA (split-K)
   const int per = (p.k_iters + p.k_split - 1) / p.k_split;
@@ -235,7 +260,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) SLB_STAMP(1);
   pdl_wait();                         // predecessor grids complete + visible; prologue above overlapped with their tail
+  if (threadIdx.x == 0) SLB_STAMP(2);
 
   if (my_iters > 0) {
     if (warp == 0) {
@@ -244,6 +271,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         for (int it = k_begin; it < k_end; ++it) {
+          if (it == k_begin + L::STAGES) SLB_STAMP(3);        // producer: the first ring of loads is in flight
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
@@ -316,6 +344,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int it = 0; it < my_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (it == 0 && lane_id() == 0) SLB_STAMP(4);          // first operands have landed
+        if (it == my_iters - 1 && lane_id() == 0) SLB_STAMP(5);  // last operands have landed
         if (elect_one()) {
           const uint32_t a_base = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t b_base = a_base + L::A_BYTES;
@@ -337,12 +367,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = m0 + q * 32 + lane_id();      // output row of this thread
       const int et = (warp - 2) * 32 + lane_id();   // 0..127 epilogue thread id
       const bool want_stats = (p.col_sum != nullptr);
-      if (want_stats) {
-        for (int i = et; i < 2 * BLOCK_N; i += 128) s_stats[i] = 0.f;
-        asm volatile("bar.sync 1, 128;");
-      }
+      // the bias of this tile's columns is staged in shared memory while the mainloop runs (32 dependent-latency global
+      // loads per 32-column chunk used to sit on the epilogue's critical path: 1.3 us per chunk)
+      float* s_bias = s_stats + 2 * BLOCK_N;
+      for (int i = et; i < 2 * BLOCK_N; i += 128) s_stats[i] = 0.f;
+      for (int i = et; i < BLOCK_N; i += 128) s_bias[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 128;");
+      // warp-private transpose tile for the statistics: the pipeline buffers are free once the accumulator is complete
+      float* s_tr = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+      static_assert(L::TILE_BYTES >= 4 * 32 * 33 * 4, "transpose tiles must fit in the pipeline buffers");
       mbar_wait(accum_bar, 0);
       tc_fence_after();
+      if (et == 0) SLB_STAMP(6);                               // accumulator complete
       const bool row_ok = row < p.M;
       long long row_off;
       bool row_store = row_ok;
@@ -358,15 +394,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
         tmem_ld_wait();
+        if (et == 0 && c == 0) SLB_STAMP(11);
         const int col0 = n0 + c;
         if (p.epi == EPI_BF16) {
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]);
-            if (p.bias != nullptr && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
-            f[j] = x;
-          }
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c + j];
+          if (et == 0 && c == 0) SLB_STAMP(12);
           if constexpr (MODE == MODE_GEMM && !OT::TF32) {
             if (p.residual != nullptr && row_store) {
               const __nv_bfloat16* rs = p.residual + row_off + col0;
@@ -383,7 +417,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   }
                 }
               } else {
-                for (int j = 0; j < 32 && col0 + j < p.N; ++j) f[j] += __bfloat162float(rs[j]);
+                {
+_Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) f[j] += __bfloat162float(rs[j]); }
               }
             }
             if (p.aux_out != nullptr && row_store) {
@@ -395,7 +430,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   a4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                                      pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
               } else {
-                for (int j = 0; j < 32 && col0 + j < p.N; ++j) ao[j] = __float2bfloat16(f[j]);
+                {
+_Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) ao[j] = __float2bfloat16(f[j]); }
               }
             }
             if (p.act != 0) {
@@ -408,18 +444,30 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (col0 + 32 <= p.N) {
               store_row32(o, f);
             } else {
-              for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = static_cast<T>(f[j]);
+              {
+_Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) o[j] = static_cast<T>(f[j]); }
             }
           }
+          if (et == 0 && c == 0) SLB_STAMP(13);
           if (want_stats) {
             // statistics of the values that were stored (what the consumer normalises; bf16-rounded in bf16 mode)
-            float s1[32], s2[32];
-            stat_terms<BNB, T>(p, row, row_ok, col0, f, s1, s2);
-            const float c1 = warp_col_reduce32(s1);
-            const float c2 = warp_col_reduce32(s2);
+            float c1, c2;
+            if constexpr (BNB) {
+              float s1[32], s2[32];
+              stat_terms<BNB, T>(p, row, row_ok, col0, f, s1, s2);
+              c1 = warp_col_reduce32(s1);
+              c2 = warp_col_reduce32(s2);
+            } else {
+              float s1[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s1[j] = row_ok ? stored_value(f[j], static_cast<const T*>(nullptr)) : 0.f;
+              warp_col_sums_smem(s_tr, s1, c1, c2);
+            }
+            if (et == 0 && c == 0) SLB_STAMP(14);
             atomicAdd(&s_stats[c + lane_id()], c1);
             atomicAdd(&s_stats[BLOCK_N + c + lane_id()], c2);
           }
+          if (et == 0 && c == 0) SLB_STAMP(15);
         } else if (p.epi == EPI_F32_ATOMIC) {
           if (row_store) {
             float* o = reinterpret_cast<float*>(p.out) + row_off + col0;
@@ -452,14 +500,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
             } else {
-              for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = __uint_as_float(v[j]);
+              {
+_Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) o[j] = __uint_as_float(v[j]); }
             }
           }
         }
       }
+      if (et == 0) SLB_STAMP(7);                               // TMEM drained / stores or reds issued
       if (p.epi == EPI_F32_ATOMIC && p.tile_counters != nullptr) {
         // ---- serial split-K tail: last slice of this tile finalises it ----
         __threadfence();
+        if (et == 0) SLB_STAMP(8);                             // reds globally visible
         asm volatile("bar.sync 1, 128;");
         if (et == 0) {
           const uint32_t tix = blockIdx.x * gridDim.y + blockIdx.y;
@@ -486,16 +537,22 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = 0.f;
             }
-            if (p.bias != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
-            }
+            for (int j = 0; j < 32; ++j) f[j] += s_bias[c + j];
             if (row_ok) store_row32(reinterpret_cast<T*>(p.fin_out) + static_cast<long long>(row) * p.fin_ld + col0, f);
             if (want_stats) {
-              float s1[32], s2[32];
-              stat_terms<BNB, T>(p, row, row_ok, col0, f, s1, s2);
-              const float c1 = warp_col_reduce32(s1);
-              const float c2 = warp_col_reduce32(s2);
+              float c1, c2;
+              if constexpr (BNB) {
+                float s1[32], s2[32];
+                stat_terms<BNB, T>(p, row, row_ok, col0, f, s1, s2);
+                c1 = warp_col_reduce32(s1);
+                c2 = warp_col_reduce32(s2);
+              } else {
+                float s1[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s1[j] = row_ok ? stored_value(f[j], static_cast<const T*>(nullptr)) : 0.f;
+                warp_col_sums_smem(s_tr, s1, c1, c2);
+              }
               atomicAdd(&s_stats[c + lane_id()], c1);
               atomicAdd(&s_stats[BLOCK_N + c + lane_id()], c2);
             }
@@ -513,15 +570,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   }
+  if (threadIdx.x == 64) SLB_STAMP(9);                         // epilogue thread 0 done
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
+  if (threadIdx.x == 0) SLB_STAMP(10);
+#undef SLB_STAMP
 }
 
 // ----------------------------------------------------------------------------- host side
+static long long* g_gemm_trace = nullptr;
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -752,11 +813,15 @@ static int conv_igemm_impl(const void* x, const void* w, void* y, const float* b
     p.bnb_y = reinterpret_cast<const __nv_bfloat16*>(bnb->y);
     p.bnb_mean = bnb->mean; p.bnb_istd = bnb->istd; p.bnb_gamma = bnb->gamma; p.bnb_beta = bnb->beta; p.bnb_relu = bnb->relu; p.bnb_pool = bnb->pool;
   }
+  p.trace = g_gemm_trace;
   dim3 grid((M + 127) / 128, Nout / bn, k_split);
   return dispatch_bn<MODE_CONV>(bn, dtype, ta, tbm, p, grid, st);
 }
 
 extern "C" {
+
+// debugging aid: device buffer of 16 int64 that CTA (0,0,0) of the conv / wgrad kernels fills with clock64() stamps
+void slb_set_gemm_trace(long long* buf) { g_gemm_trace = buf; }
 
 // dw[Cout][3][3][Cin] (fp32, accumulated with red.add; caller zeroes) += sum_pixels dy (x) x ; x / dy typed by dtype
 int slb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int k_split,
@@ -796,6 +861,7 @@ int slb_conv3x3_wgrad(const void* x, const void* dy, float* dw, int B, int H, in
   p.a_mn = 1; p.b_mn = 1; p.epi = k_split > 1 ? EPI_F32_ATOMIC : EPI_F32_STORE; p.out = dw; p.ldo = Cin;
   p.rmod = Cout; p.rmul1 = (long long)9 * Cin; p.rmul2 = Cin; p.m_valid_mod = 9;
   p.C = Cout; p.tw = tw; p.th = th; p.tb = tb; p.H = H; p.W = W; p.Cout = Cout;
+  p.trace = g_gemm_trace;
   dim3 grid(m_tiles, n_tiles, k_split);
   return dispatch_bn<MODE_WGRAD>(bn, dtype, ta, tbm, p, grid, st);
 }

@@ -48,7 +48,7 @@ def preload(device=None) -> None:
         return
     with torch.cuda.device(d):
         bad = (lib().slb_preload_gemm() + lib().slb_preload_fused() + lib().slb_preload_elementwise()
-               + lib().slb_preload_transformer())
+               + lib().slb_preload_transformer() + lib().slb_preload_allreduce())
     if bad:
         raise NativeError(f"{bad} kernels failed to load (wrong GPU architecture? this library is sm_100a only)")
     _preloaded.add(d)
@@ -115,7 +115,7 @@ def conv_tiling(M: int, N: int, Ca: int, target_ctas: int = 96, flip: int = 0, k
     """(block_n, k_split) for the implicit-GEMM conv: these problems are latency- not FLOP-bound at microbatch 32,
     so spread every layer over ~all SMs — narrow N tiles first, then split K (fp32 vector red.add + finalize).
     A measured entry of ``conv_tuning.json`` for exactly this shape wins over the heuristic."""
-    hit = _tuning()["conv" if ke == 64 else "conv_f32"].get(f"{M},{N},{Ca},{flip}") if ("conv_f32" in _tuning() or ke == 64) else None
+    hit = _tuning().get("conv" if ke == 64 else "conv_f32", {}).get(f"{M},{N},{Ca},{flip}")
     if hit:
         return int(hit["bn"]), int(hit["ks"])
     m_tiles = (M + 127) // 128
@@ -192,8 +192,8 @@ def conv3x3_wgrad(x, dy, dw_f32, k_split: int = 0, block_n: int = 0):
     whose K fits one slice is written with plain stores."""
     B, H, W, Cin = x.shape
     Cout = dy.shape[3]
-    if k_split == 0 and block_n == 0 and _ke(x) == 64:
-        hit = _tuning()["wgrad"].get(f"{B * H * W},{Cin},{Cout}")
+    if k_split == 0 and block_n == 0:
+        hit = _tuning().get("wgrad" if _ke(x) == 64 else "wgrad_f32", {}).get(f"{B * H * W},{Cin},{Cout}")
         if hit:
             block_n, k_split = int(hit["bn"]), int(hit["ks"])
     _check(lib().slb_conv3x3_wgrad(_p(x), _p(dy), _p(dw_f32), c_int(B), c_int(H), c_int(W), c_int(Cin), c_int(Cout),

@@ -41,7 +41,16 @@ class DeviceRpcClient(RpcClient):
         finally:
             self.send_to_server = super_ready
         try:
-            self._wire(msg)
+            # resident round (same executor, same peers): the stages, graphs and mailboxes of the previous round stay
+            key = (id(self.executor), repr(msg.get("peers")), int(self.learning["batch-size"]), int(self.learning.get("control-count", 3)))
+            if getattr(self, "_wired_key", None) == key and getattr(self, "dstages", None):
+                self.dstage = self.dstages[self._lane_info[0][0]]
+                for st in self.dstages.values():
+                    st._posted = {"F": 0, "B": 0, "L": 0}
+            else:
+                self._wired_key = None
+                self._wire(msg)
+                self._wired_key = key
         except Exception as e:          # topology not supported on the device plane → host plane
             print_with_color(f"[device plane] falling back to host data plane: {e}", "yellow")
             self.dstage = None
@@ -84,17 +93,28 @@ class DeviceRpcClient(RpcClient):
         self.channel.queue_declare(my_q)
         fwd_in: Dict[int, Mailbox] = {}
         grad_in: Dict[int, Mailbox] = {}
+        # Mailboxes I own are allocated once per (edge, geometry) and re-used by every later round (a START re-wires the
+        # stages — the executor may be new — but must not leak cudaMalloc'ed rings or IPC mappings round after round).
+        cache = self.__dict__.setdefault("_mailbox_cache", {})
+
+        def own(kind: str, lane: int, spec: MailboxSpec):
+            key = (kind, lane, spec.depth, spec.batch, spec.payload_shape, spec.itemsize)
+            if key not in cache:
+                cache[key] = Mailbox.allocate_exportable(spec, dev)
+            mb, hdl = cache[key]
+            mb.base[spec.flags_off: spec.flags_off + 4 * spec.depth].zero_()      # fresh sequence numbers for fresh stages
+            return mb, hdl
         for lane, up, down in lanes:
             if up is not None:                                     # I consume this lane's activations
                 c, h, w = ex.in_shape
                 spec_in = MailboxSpec(depth, B, (B, h, w, c), itemsize=isz)
-                fwd_in[lane], hdl = Mailbox.allocate_exportable(spec_in, dev)
+                fwd_in[lane], hdl = own("act", lane, spec_in)
                 self.channel.publish_obj(f"ipc_{up}", {"kind": "act", "lane": lane, "handle": hdl,
                                                        "shape": spec_in.payload_shape})
             if down is not None:                                   # I consume the gradients of this lane's output
                 c, h, w = ex.out_shape
                 spec_out = MailboxSpec(depth, B, (B, h, w, c), itemsize=isz)
-                grad_in[lane], hdl = Mailbox.allocate_exportable(spec_out, dev)
+                grad_in[lane], hdl = own("grad", lane, spec_out)
                 self.channel.publish_obj(f"ipc_{down}", {"kind": "grad", "lane": lane, "handle": hdl,
                                                          "shape": spec_out.payload_shape})
         need = sum(int(up is not None) + int(down is not None) for _, up, down in lanes)
@@ -203,45 +223,30 @@ class DeviceRpcClient(RpcClient):
         return [cid for cid, _ in self.start_msg["peers"]["members"][self.layer_id]]
 
     def upload(self, result: bool, size: int, send: bool = True) -> None:
-        """Round end.  With several replicas of this stage (single cluster) the weighted FedAvg runs in place over
-        peer memory (``parallel.fedavg``): every replica ends the round holding the averaged parameters, only the
-        group leader uploads a state-dict (for validation / checkpoint), and the next START carries no payload."""
-        members = self._replicas() if self.dstage is not None else []
-        single_cluster = int(self.start_msg.get("num_clusters", 1)) == 1
-        if len(members) < 2 or not single_cluster or not self.opts.get("device-fedavg", True):
+        """Round end on the device plane: every trainable client of every cluster joins ONE device all-reduce
+        (``parallel/allreduce.py``) that applies the reference's per-cluster weighted FedAvg and the cross-cluster mean
+        (src/Server.py:398-434) in place over NVLink — also between stages of clusters cut at different layers.  Every
+        replica ends the round holding the global model for its layers, so the next START carries no parameters; only
+        the stage leaders of the first cluster upload a state-dict (validation / checkpoint on the server)."""
+        everyone = (self.start_msg.get("peers") or {}).get("all") or []
+        members = sorted(str(cid) for cid, _, _ in everyone)
+        if self.dstage is None or len(members) < 2 or not self.opts.get("device-fedavg", True):
             return super().upload(result, size, send)
-        from .fedavg import BrokerComm, PeerFedAvg
+        from .allreduce import DeviceFedAvg
+        from .fedavg import BrokerComm
         ex = self.executor
         me = str(self.client_id)
-        if getattr(self, "_fa_members", None) != members:
-            comm = BrokerComm(self.channel, f"fa_{self.cluster}_{self.layer_id}", members, me, timeout=self.watchdog)
-            stats = [t for bn in ex.bn_state.values() for t in (bn["running_mean"], bn["running_var"])]
-            n_stats = (sum(t.numel() for t in stats) + 3) // 4 * 4
-            self._fa = (comm, PeerFedAvg(ex.n_params, ex.device, comm=comm),
-                        PeerFedAvg(max(n_stats, 4), ex.device, comm=comm) if stats else None)
-            self._fa_members = members
-        comm, fa_p, fa_s = self._fa
-        done = fa_p.average(ex.P, ex.PB, float(size), ok=bool(result))
-        if done and fa_s is not None:
-            stats = [t for bn in ex.bn_state.values() for t in (bn["running_mean"], bn["running_var"])]
-            flat = torch.zeros(fa_s.n, device=ex.device)
-            o = 0
-            for t in stats:
-                flat[o:o + t.numel()].copy_(t.reshape(-1))
-                o += t.numel()
-            fa_s.average(flat, None, float(size), ok=True)
-            o = 0
-            for t in stats:
-                t.copy_(flat[o:o + t.numel()].view_as(t))
-                o += t.numel()
-        sizes = comm.all_gather_object((int(size), {k: int(v["num_batches_tracked"]) for k, v in ex.bn_state.items()}))
-        total = sum(s for s, _ in sizes) or 1
-        if done:
-            for k, v in ex.bn_state.items():         # integer counters: weighted mean, rounded (src/Utils.py:59-60)
-                v["num_batches_tracked"].fill_(round(sum(s * c[k] for s, c in sizes) / total))
-        leader = members and sorted(members)[0] == me
+        key = (tuple(members), id(ex))
+        if getattr(self, "_fa_key", None) != key:
+            comm = BrokerComm(self.channel, "fa_all", members, me, timeout=self.watchdog)
+            self._fa = DeviceFedAvg(ex, me, int(self.cluster or 0), comm)
+            self._fa.setup()                                 # one handle exchange; later rounds are device-only
+            self._fa_key = key
+        done = self._fa.run(float(size), ok=bool(result))
+        mine = sorted(str(cid) for cid, cl, lid in everyone if int(cl) == int(self.cluster or 0) and int(lid) == self.layer_id)
+        first_cluster = min(int(cl) for _, cl, _ in everyone)
+        leader = bool(mine) and mine[0] == me and int(self.cluster or 0) == first_cluster
         sd = None
         if leader and send:
             sd = {k: v.detach().to("cpu") for k, v in ex.state_dict().items()}
-        self.send_to_server(M.update(self.client_id, self.layer_id, bool(result) and done, total if leader else size,
-                                     self.cluster, sd, resident=True))
+        self.send_to_server(M.update(self.client_id, self.layer_id, bool(result) and done, size, self.cluster, sd, resident=True))

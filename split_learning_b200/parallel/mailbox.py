@@ -132,6 +132,43 @@ class HostGate:
                 raise TimeoutError("producer thread never enqueued the matching publish")
 
 
+_OPENED: dict = {}         # IPC handle -> mapped pointer (cudaIpcOpenMemHandle may be called once per handle and process)
+
+
+def alloc_exportable(nbytes: int, device) -> Tuple[torch.Tensor, bytes, int]:
+    """cudaMalloc'ed (not caching-allocator) zeroed memory + its 64-byte CUDA-IPC handle: (uint8 tensor view, handle, ptr)."""
+    lib = N.lib()
+    nbytes = _align(max(int(nbytes), 256))
+    with torch.cuda.device(device):
+        ptr = ctypes.c_void_p()
+        rc = lib.slb_malloc(ctypes.byref(ptr), ctypes.c_longlong(nbytes))
+        if rc != 0:
+            raise N.NativeError(f"slb_malloc({nbytes}) failed: {rc}")
+        handle = (ctypes.c_uint8 * 64)()
+        rc = lib.slb_ipc_get_handle(ptr, handle)
+        if rc != 0:
+            raise N.NativeError(f"cudaIpcGetMemHandle failed: {rc}")
+    _SAME_PROCESS[bytes(handle)] = (ptr.value, None)
+    return tensor_from_ptr(ptr.value, nbytes, device), bytes(handle), ptr.value
+
+
+def open_exported(handle: bytes, device) -> int:
+    """Device pointer of a peer's exported allocation (the raw pointer itself when the exporter lives in this process)."""
+    if handle in _SAME_PROCESS:
+        return _SAME_PROCESS[handle][0]
+    if handle in _OPENED:
+        return _OPENED[handle]
+    lib = N.lib()
+    with torch.cuda.device(device):
+        q = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+        rc = lib.slb_ipc_open(buf, ctypes.byref(q))
+        if rc != 0:
+            raise N.NativeError(f"cudaIpcOpenMemHandle failed: {rc}")
+    _OPENED[handle] = q.value
+    return q.value
+
+
 class Mailbox:
     """View of a mailbox allocation (owner side or a peer-mapped producer side)."""
 
@@ -192,13 +229,7 @@ class Mailbox:
             if owner_mb.gate is None:
                 owner_mb.gate = HostGate()
             return Mailbox(spec, None, owner=False, raw_ptr=raw, gate=owner_mb.gate)
-        lib = N.lib()
-        ptr = ctypes.c_void_p()
-        buf = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
-        rc = lib.slb_ipc_open(buf, ctypes.byref(ptr))
-        if rc != 0:
-            raise N.NativeError(f"cudaIpcOpenMemHandle failed: {rc}")
-        return Mailbox(spec, None, owner=False, raw_ptr=ptr.value)
+        return Mailbox(spec, None, owner=False, raw_ptr=open_exported(handle, device))     # one mapping per handle and process
 
 
 class EdgeCounters:

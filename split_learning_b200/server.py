@@ -275,7 +275,8 @@ class Server:
         layers = self.topology.layers_for(c.cluster, c.layer_id)
         if self.topology.clusters[c.cluster].cut_layers[:1] == [0] and c.layer_id == 1:
             layers = [0, 0]
-        resident = bool(getattr(self, "all_resident", False)) and len(self.topology.clusters) == 1
+        # every client averaged in place on the device (all clusters joined one all-reduce): nothing to ship
+        resident = bool(getattr(self, "all_resident", False))
         params = None if resident else self.stage_parameters_for(c, layers)
         return M.start(params, layers, self.model_name, self.data_name,
                        self.learning, c.label_counts, self.refresh, c.cluster,
@@ -289,7 +290,8 @@ class Server:
         table = {}
         for s, ids in enumerate(cl.members):
             table[s + 1] = [(cid, next((x.rank for x in self.clients if x.client_id == cid), None)) for cid in ids]
-        return {"members": table, "cut_layers": list(cl.cut_layers)}
+        everyone = [(x.client_id, int(x.cluster), int(x.layer_id)) for x in self.clients if x.train]
+        return {"members": table, "cut_layers": list(cl.cut_layers), "all": everyone}
 
     def notify_clients(self, start: bool = True) -> None:
         if not start:

@@ -173,6 +173,35 @@ def _align(n: int, a: int = 128) -> int:
     return (n + a - 1) // a * a
 
 
+def flat_layouts(model_cls, start_layer: int, end_layer: int):
+    """Flat-buffer layouts of the stage ``model_cls(start, end)`` — exactly what ``B200Executor`` allocates — computed
+    from the layer table alone (meta device, nothing is allocated): {"P": {key: (offset, numel)}, "S": ..., "I": ...}
+    with 128-float aligned entries (4 floats per entry in "I").  Every replica derives every other replica's layout
+    from (model, layers), which is how the FedAvg all-reduce finds the same layer inside stages cut at different points."""
+    with torch.device("meta"):
+        model = model_cls(start_layer, end_layer)
+    _, blocks, _ = compile_plan(model)
+    P: Dict[str, Tuple[int, int]] = {}
+    S: Dict[str, Tuple[int, int]] = {}
+    I: Dict[str, Tuple[int, int]] = {}
+    off = so = io = 0
+    for b in blocks:
+        if isinstance(b, ConvBlock):
+            if b.conv is not None:
+                P[f"layer{b.conv}.weight"] = (off, _align(b.cout * 9 * b.cin)); off += _align(b.cout * 9 * b.cin)
+                P[f"layer{b.conv}.bias"] = (off, _align(b.cout)); off += _align(b.cout)
+            if b.bn is not None:
+                P[f"layer{b.bn}.weight"] = (off, _align(b.cout)); off += _align(b.cout)
+                P[f"layer{b.bn}.bias"] = (off, _align(b.cout)); off += _align(b.cout)
+                S[f"layer{b.bn}.running_mean"] = (so, _align(b.cout)); so += _align(b.cout)
+                S[f"layer{b.bn}.running_var"] = (so, _align(b.cout)); so += _align(b.cout)
+                I[f"layer{b.bn}.num_batches_tracked"] = (io, 4); io += 4
+        elif isinstance(b, LinearBlock):
+            P[f"layer{b.lin}.weight"] = (off, _align(b.fout * b.fin)); off += _align(b.fout * b.fin)
+            P[f"layer{b.lin}.bias"] = (off, _align(b.fout)); off += _align(b.fout)
+    return {"P": P, "S": S, "I": I}
+
+
 # ----------------------------------------------------------------------------- executor
 class B200Executor(StageExecutor):
     def __init__(self, model: SplitModel, model_name: str, learning: dict, device, is_first=False, is_last=False,
@@ -271,16 +300,40 @@ class B200Executor(StageExecutor):
                 hi = max(_align(self.entries[k][0] + math.prod(self.entries[k][1])) for k in keys)
                 self.block_range[bi] = (lo, hi)
         dev = self.device
-        self.P = torch.zeros(self.n_params, device=dev)
+        # The fp32 master lives in an IPC-exportable allocation: the round-end FedAvg all-reduce (parallel/allreduce.py)
+        # reads and writes the replicas' masters in place over NVLink — no staging copy, no START payload next round.
+        from ..parallel.mailbox import alloc_exportable
+        raw, self.P_handle, _ = alloc_exportable(self.n_params * 4, dev)
+        self.P = raw.view(torch.float32)[:self.n_params]
         self.G = torch.zeros(self.n_params, device=dev)
         self.M = torch.zeros(self.n_params, device=dev)
         self.PB = None if self.fp32 else torch.zeros(self.n_params, device=dev, dtype=torch.bfloat16)
+        # BatchNorm running statistics: one flat exportable buffer S (mean | var per BN, 128-aligned entries) plus a float
+        # mirror I of the integer counters (4 floats per BN) that the all-reduce averages-and-rounds (src/Utils.py:59-60)
+        self.stat_entries: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        self.int_entries: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        so = io = 0
+        for b in self.blocks:
+            if isinstance(b, ConvBlock) and b.bn is not None:
+                self.stat_entries[f"layer{b.bn}.running_mean"] = (so, (b.cout,))
+                so += _align(b.cout)
+                self.stat_entries[f"layer{b.bn}.running_var"] = (so, (b.cout,))
+                so += _align(b.cout)
+                self.int_entries[f"layer{b.bn}.num_batches_tracked"] = (io, (1,))
+                io += 4
+        self.n_stats, self.n_ints = max(so, 128), max(io, 4)
+        raw, self.S_handle, _ = alloc_exportable(self.n_stats * 4, dev)
+        self.S = raw.view(torch.float32)[:self.n_stats]
+        raw, self.I_handle, _ = alloc_exportable(self.n_ints * 4, dev)
+        self.I = raw.view(torch.float32)[:self.n_ints]
         self.bn_state: Dict[int, Dict[str, torch.Tensor]] = {}
         for b in self.blocks:
             if isinstance(b, ConvBlock) and b.bn is not None:
-                self.bn_state[b.bn] = {"running_mean": torch.zeros(b.cout, device=dev),
-                                       "running_var": torch.ones(b.cout, device=dev),
+                om = self.stat_entries[f"layer{b.bn}.running_mean"][0]
+                ov = self.stat_entries[f"layer{b.bn}.running_var"][0]
+                self.bn_state[b.bn] = {"running_mean": self.S[om:om + b.cout], "running_var": self.S[ov:ov + b.cout],
                                        "num_batches_tracked": torch.zeros((), device=dev, dtype=torch.int64)}
+                self.bn_state[b.bn]["running_var"].fill_(1.0)
 
     def view(self, buf: torch.Tensor, key: str) -> torch.Tensor:
         off, shape = self.entries[key]

@@ -37,3 +37,29 @@ def test_bench_two_gpus():
 def test_peer_fedavg_two_gpus():
     r = _torchrun(2, ["tools/check_fedavg_peer.py"])
     assert r.returncode == 0 and "FEDAVG_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_device_allreduce_two_gpus():
+    """Two-shot FedAvg all-reduce kernel vs the reference aggregation done with torch (weights, NaN scrub, int rounding, NaN vote)."""
+    r = _torchrun(2, ["tools/check_allreduce.py"])
+    assert r.returncode == 0 and "ALLREDUCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.skipif(_ngpu() < 4, reason="needs 4 GPUs")
+def test_device_allreduce_two_clusters_four_gpus():
+    """Clusters cut at 7 / 14 (BASELINE config #4): layers 8-14 are averaged between stage 2 of one cluster and stage 1 of the other."""
+    r = _torchrun(4, ["tools/check_allreduce.py"])
+    assert r.returncode == 0 and "ALLREDUCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_ring_bench_selfcheck_and_litmus():
+    """bench.py --gpus 2 (ring placement): cross-GPU loss trajectory == single-GPU replica, 10^5-iteration payload/flag litmus clean,
+    FedAvg all-reduce matches the NCCL mean."""
+    r = _torchrun(2, ["bench.py", "--gpus", "2", "--steps", "20", "--warmup", "5"])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["selfcheck"]["ok"], out["selfcheck"]
+    assert out["litmus"]["ok"], out["litmus"]
+    assert out["fedavg_round"]["max_abs_err_vs_nccl_mean"] < 1e-5 and out["fedavg_round"]["aggregated"]

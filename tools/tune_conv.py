@@ -52,22 +52,31 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--iters", type=int, default=15)
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16"])
     a = ap.parse_args()
     B = a.batch
-    table = {"batch": B, "conv": {}, "wgrad": {}}
+    dt = torch.float32 if a.precision == "tf32" else torch.bfloat16
+    ke = 32 if a.precision == "tf32" else 64
+    ckey, wkey = ("conv_f32", "wgrad_f32") if a.precision == "tf32" else ("conv", "wgrad")
+    dst = os.path.join(ROOT, "gpurun_out", f"conv_tuning_b{B}.json")
+    try:
+        table = json.load(open(dst))
+    except (OSError, ValueError):
+        table = {"batch": B}
+    table[ckey], table[wkey] = {}, {}
     ctr = torch.zeros(4096, device="cuda", dtype=torch.int32)
     for (HW, Cin, Cout) in SHAPES:
         M = B * HW * HW
-        x = torch.randn(B, HW, HW, Cin, device="cuda").to(torch.bfloat16)
-        dy = torch.randn(B, HW, HW, Cout, device="cuda").to(torch.bfloat16)
-        w = (torch.randn(Cout, 3, 3, Cin, device="cuda") * 0.05).to(torch.bfloat16)
+        x = torch.randn(B, HW, HW, Cin, device="cuda").to(dt)
+        dy = torch.randn(B, HW, HW, Cout, device="cuda").to(dt)
+        w = (torch.randn(Cout, 3, 3, Cin, device="cuda") * 0.05).to(dt)
         bias = torch.zeros(Cout, device="cuda")
         for flip in (0, 1):
             Nn, Ca = (Cout, Cin) if not flip else (Cin, Cout)
-            out = torch.empty(B, HW, HW, Nn, device="cuda", dtype=torch.bfloat16)
+            out = torch.empty(B, HW, HW, Nn, device="cuda", dtype=dt)
             acc = torch.zeros(M, Nn, device="cuda")
             s1, s2 = torch.zeros(Nn, device="cuda"), torch.zeros(Nn, device="cuda")
-            k_iters = 9 * (Ca // 64)
+            k_iters = 9 * (Ca // ke)
             best = None
             for bn in (64, 128, 256):
                 if Nn % bn or (flip and bn > 128 and False):
@@ -86,10 +95,10 @@ def main():
                     if best is None or t < best[0]:
                         best = (t, bn, ks)
             key = f"{M},{Nn},{Ca},{flip}"
-            table["conv"][key] = {"bn": best[1], "ks": best[2], "us": round(best[0], 2)}
-            print("conv", "dgrad" if flip else "fwd", (HW, Cin, Cout), table["conv"][key], "default", N.conv_tiling(M, Nn, Ca), flush=True)
+            table[ckey][key] = {"bn": best[1], "ks": best[2], "us": round(best[0], 2)}
+            print("conv", "dgrad" if flip else "fwd", (HW, Cin, Cout), table[ckey][key], "default", N.conv_tiling(M, Nn, Ca, ke=ke), flush=True)
         dw = torch.zeros(Cout, 3, 3, Cin, device="cuda")
-        k_iters = (M + 63) // 64
+        k_iters = (M + ke - 1) // ke
         best = None
         for bn in (64, 128, 256):
             if Cin % bn:
@@ -102,9 +111,8 @@ def main():
                 if best is None or t < best[0]:
                     best = (t, bn, ks)
         key = f"{M},{Cin},{Cout}"
-        table["wgrad"][key] = {"bn": best[1], "ks": best[2], "us": round(best[0], 2)}
-        print("wgrad", (HW, Cin, Cout), table["wgrad"][key], flush=True)
-    dst = os.path.join(ROOT, "gpurun_out", f"conv_tuning_b{B}.json")
+        table[wkey][key] = {"bn": best[1], "ks": best[2], "us": round(best[0], 2)}
+        print("wgrad", (HW, Cin, Cout), table[wkey][key], flush=True)
     os.makedirs(os.path.dirname(dst), exist_ok=True)
     json.dump(table, open(dst, "w"), indent=1)
     print("wrote", dst)
