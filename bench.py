@@ -48,6 +48,11 @@ def parse():
     ap.add_argument("--placement", default="ring", choices=["ring", "split"],
                     help="N > 1: ring = N chains, GPU r hosts stage 1 of chain r and stage 2 of chain r-1 (default; per-GPU work "
                          "constant in N); split = clients [N/2, N/2], one stage replica per GPU (BASELINE configs #2/#3)")
+    ap.add_argument("--scenario", default=None, choices=["split", "clusters", "three-stage"],
+                    help="run ONLY the public-API path on a named BASELINE.json configuration, one client per GPU: split = [N/2, N/2] "
+                         "cut 7 (#2/#3), clusters = two clusters cut 7 / 14 (#4), three-stage = cuts [5, 10], non-IID 0.5 (#5)")
+    ap.add_argument("--no-api", action="store_true", help="skip the run through the public API (server + client FSMs over the broker)")
+    ap.add_argument("--rounds", type=int, default=3, help="public-API run: global rounds (the first one pays graph capture and wiring)")
     ap.add_argument("--no-selfcheck", action="store_true", help="skip the cross-GPU vs single-GPU loss-trajectory check")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--timeout", type=float, default=1500.0)
@@ -251,10 +256,49 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "baseline"))
         from run_reference import main as ref_main
         out = ref_main(args, transport="nccl" if args.impl == "reference-nccl" else "broker")
+    elif args.scenario:
+        from split_learning_b200.parallel.api_bench import run_api
+        api = run_api(args)
+        out = None
+        if api:
+            r = api.get("steady_round") or {}
+            out = {"metric": "VGG16/CIFAR10 split images/sec", "value": r.get("images_per_s_device"), "unit": "images/s",
+                   "n_gpus": args.gpus, "steps": api.get("microbatches_per_client_per_round"), "warmup": 0,
+                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_LABEL[args.precision],
+                   "data": "synthetic", "impl": "ours", "measured_through": "public API (server + clients over the broker)",
+                   "config": {"model": "VGG16_CIFAR10", "scenario": args.scenario, "clients": api.get("clients"),
+                              "cut_layers": api.get("cut_layers"), "non_iid_rate": api.get("non_iid_rate"), "microbatch": args.batch,
+                              "control_count": args.depth},
+                   "e2e": {"value": r.get("images_per_s_device"), "round_wall_ms": r.get("wall_ms"),
+                           "round_overhead_ms": r.get("overhead_ms"), "images_per_s_whole_round": r.get("images_per_s_round")},
+                   "api": api}
     else:
         out = run_ours(args)
+        if not args.no_api and not args.cuts and (args.gpus == 1 or args.placement == "ring"):
+            # the same metric end to end through the public API (what a user runs): server + client FSMs over the broker,
+            # pinned-host inputs copied in every step, every step's loss copied out, FedAvg + UPDATE at round end
+            from split_learning_b200.parallel.api_bench import run_api
+            api = run_api(args)
+            if out and api and "steady_round" in api:
+                r = api["steady_round"]
+                out["e2e_pipeline_loop"] = out.get("e2e")
+                out["e2e"] = {"value": r["images_per_s_device"], "unit": "images/s", "path": api["path"],
+                              "ms_per_step": r["device_ms"] / api["microbatches_per_client_per_round"],
+                              "h2d_bytes_per_step": api["h2d_bytes_per_step"], "d2h_bytes_per_step": api["d2h_bytes_per_step"],
+                              "round_wall_ms": r["wall_ms"], "round_overhead_ms": r["overhead_ms"],
+                              "images_per_s_whole_round": r["images_per_s_round"], "train_loss": r["train_loss"]}
+                out["api"] = api
+            elif out is not None and api:
+                out["api"] = api
     if out and int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(out), flush=True)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

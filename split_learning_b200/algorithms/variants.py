@@ -42,6 +42,8 @@ class SequentialServer(Server):
 
     ALGORITHM = "vanilla_sl"
     STRICT_VALIDATION = True
+    STOP_ON_VALIDATION_FAILURE = False        # Vanilla_SL / Cluster_FSL retry the round; DCSL stops (see DCSLServer)
+    MAX_ROUND_RETRIES = 5                     # a persistently diverging run must not loop forever (the reference would)
 
     def cluster_and_selection(self) -> None:
         cfg = self.cfg
@@ -149,6 +151,9 @@ class SequentialServer(Server):
                 self.round -= 1
             else:
                 self.logger.log_warning("Training failed!")
+                self._retries = getattr(self, "_retries", 0) + 1
+                if self.STOP_ON_VALIDATION_FAILURE or self._retries > self.MAX_ROUND_RETRIES:
+                    self.round = 0                    # other/DCSL/src/Server.py:213 — stop instead of retrying
         else:
             self.round -= 1
         self.history.append(metrics)
@@ -170,6 +175,7 @@ class ClusterFSLServer(SequentialServer):
 
 class DCSLServer(SequentialServer):
     ALGORITHM = "dcsl"
+    STOP_ON_VALIDATION_FAILURE = True         # reference DCSL sets round = 0 when validation fails (other/DCSL/src/Server.py:213)
 
     def extra_start(self, c: ClientInfo) -> dict:
         last = [x.client_id for x in self.clients if x.layer_id == self.num_stages]

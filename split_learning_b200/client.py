@@ -81,7 +81,9 @@ class RpcClient:
 
     def wait_response(self, idle_timeout: Optional[float] = None) -> None:
         last = time.monotonic()
-        limit = idle_timeout if idle_timeout is not None else max(4 * self.watchdog, 600.0)
+        # the server relays a heartbeat every few seconds: its silence for a watchdog period means it is gone
+        limit = idle_timeout if idle_timeout is not None else (max(self.watchdog, 3 * self.heartbeat) if self.heartbeat > 0
+                                                               else max(4 * self.watchdog, 600.0))
         while True:
             m = self.channel.get_obj(M.reply_queue(self.client_id), 0.25)
             if m is None:
@@ -144,8 +146,10 @@ class RpcClient:
                                     watchdog=self.watchdog, verbose=self.verbose)
         self.trainer.data_count = 0
         if is_first and (self.train_loader is None or msg.get("refresh", True)):
+            import zlib
             self.train_loader = data_loader(self.data_name, int(self.learning["batch-size"]), self.label_count,
                                             train=True, synthetic=True if self.opts.get("synthetic-data") else None,
+                                            seed=zlib.crc32(str(self.client_id).encode()) & 0x7FFFFFFF,   # every client its own samples
                                             device=self.device, gpu_loader=bool(self.opts.get("gpu-loader", False)))
         self.is_first, self.is_last = is_first, is_last
         self.start_msg = msg

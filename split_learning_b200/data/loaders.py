@@ -166,6 +166,9 @@ def gpu_image_loader(name: str, batch_size: int, distribution: Sequence[int], de
     return GpuImageLoader(images, y, batch_size, device, mean, std, augment=(name == "CIFAR10"), seed=seed)
 
 
+_WARNED: set = set()
+
+
 def data_loader(data_name: Optional[str] = None, batch_size: Optional[int] = None,
                 distribution: Optional[Sequence[int]] = None, train: bool = True,
                 synthetic: Optional[bool] = None, root: str = "./data", seed: int = 0, device=None,
@@ -173,8 +176,20 @@ def data_loader(data_name: Optional[str] = None, batch_size: Optional[int] = Non
     name = str(data_name).upper()
     if name not in DATASET_SHAPES:
         raise ValueError(f"Dataset {data_name} not supported.")
+    explicit = synthetic is not None or os.environ.get("SLB200_SYNTHETIC", "0") == "1"
     if synthetic is None:
         synthetic = os.environ.get("SLB200_SYNTHETIC", "0") == "1" or not real_data_available(name, root)
+    if synthetic and not explicit and name not in _WARNED:
+        # never train on noise silently: the reference would download the dataset or fail (src/dataset/dataloader.py:61-84)
+        _WARNED.add(name)
+        import warnings
+        msg = (f"dataset {name} not found under {root!r}: using SYNTHETIC {name}-shaped samples (random, class-dependent mean). "
+               "Accuracy / loss numbers of this run are meaningless; set b200.synthetic-data: true (or SLB200_SYNTHETIC=1) to "
+               "acknowledge, or place the real dataset files.")
+        warnings.warn(msg, RuntimeWarning, stacklevel=2)
+        print("\033[93m[WARNING] " + msg + "\033[0m", flush=True)
+    if not train:
+        seed = seed + 7919                     # held-out stream: validation never re-draws the training samples
     if (gpu_loader and train and name in ("CIFAR10", "MNIST") and device is not None and torch.device(device).type == "cuda"
             and distribution is not None and len(distribution) > 0):
         return gpu_image_loader(name, int(batch_size), distribution, device, bool(synthetic), root, seed)

@@ -11,8 +11,8 @@ from typing import Any, Dict, List, Optional
 
 RPC_QUEUE = "rpc_queue"
 
-REGISTER, START, SYN, NOTIFY, PAUSE, UPDATE, STOP, READY, HEARTBEAT = (
-    "REGISTER", "START", "SYN", "NOTIFY", "PAUSE", "UPDATE", "STOP", "READY", "HEARTBEAT")
+REGISTER, START, SYN, NOTIFY, PAUSE, UPDATE, STOP, READY, HEARTBEAT, CHECKPOINT = (
+    "REGISTER", "START", "SYN", "NOTIFY", "PAUSE", "UPDATE", "STOP", "READY", "HEARTBEAT", "CHECKPOINT")
 
 
 def reply_queue(client_id) -> str:
@@ -67,6 +67,13 @@ def heartbeat(client_id=None) -> Dict[str, Any]:
     timers — waits are bounded by *silence of the peer*, not by how long a healthy round takes."""
     import time
     return {"action": HEARTBEAT, "client_id": client_id, "message": "alive", "t": time.time()}
+
+
+def checkpoint(client_id, layer_id: int, cluster, round_no: int, parameters) -> Dict[str, Any]:
+    """Device plane, ``resident`` rounds: the stage leader ships the (already aggregated) stage state-dict *after* its
+    UPDATE, off the round's critical path; the server assembles the full checkpoint of ``round_no`` in a writer thread."""
+    return {"action": CHECKPOINT, "client_id": client_id, "layer_id": layer_id, "cluster": cluster, "round": round_no,
+            "parameters": parameters, "message": "stage parameters for the checkpoint"}
 
 
 def ready(client_id, layer_id: int) -> Dict[str, Any]:

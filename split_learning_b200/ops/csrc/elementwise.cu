@@ -70,6 +70,28 @@ __global__ void zero_kernel(float4* p, long long n4) {
     p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// First kernel of a stage program that consumes a mailbox slot: zero the scratch region AND acquire the slot flag (block 0,
+// thread 0 spins with ld.acquire.sys while the other blocks zero) — the stand-alone one-thread wait launch disappears
+// from every F / B / L program.  No pdl_trigger(), like wait_flag_kernel: dependents must not occupy SM slots while we spin.
+__global__ void zero_wait_kernel(float4* p, long long n4, const uint32_t* flag, uint32_t* expect_ctr, unsigned long long max_spins,
+                                 int* status) {
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const uint32_t expected = *expect_ctr + 1;
+    unsigned long long spins = 0;
+    while (ld_acquire_sys(flag) < expected) {
+      __nanosleep(64);
+      if (++spins > max_spins) {
+        if (status) *status = 1;
+        return;
+      }
+    }
+    *expect_ctr = expected;
+  }
+}
+
 // Spin until *flag >= expected (acquire, system scope).  `expect_ctr` (nullable): device counter; the
 // kernel waits for *expect_ctr + 1 and stores it back (graph-replay friendly).  `status` (nullable)
 // receives 1 on timeout so a dead producer turns into an error instead of a hung GPU.
@@ -1148,7 +1170,7 @@ int slb_preload_elementwise() {
   { auto k = dropout_fwd_kernel<T>; SLB_PRELOAD(k); } { auto k = dropout_bwd_kernel<T>; SLB_PRELOAD(k); }
   SLB_PRELOAD_T(bf)
   SLB_PRELOAD_T(float)
-  SLB_PRELOAD(zero_kernel); SLB_PRELOAD(wait_flag_kernel); SLB_PRELOAD(set_flag_kernel); SLB_PRELOAD(counter_inc_kernel);
+  SLB_PRELOAD(zero_kernel); SLB_PRELOAD(zero_wait_kernel); SLB_PRELOAD(wait_flag_kernel); SLB_PRELOAD(set_flag_kernel); SLB_PRELOAD(counter_inc_kernel);
   SLB_PRELOAD(linear_fwd_f32_kernel); SLB_PRELOAD(linear_dgrad_f32_kernel); SLB_PRELOAD(linear_wgrad_f32_kernel);
   SLB_PRELOAD(sumsq_kernel); SLB_PRELOAD(clip_scale_kernel);
   SLB_PRELOAD(ce_fwd_bwd_kernel); SLB_PRELOAD(sgd_momentum_kernel); SLB_PRELOAD(adamw_kernel); SLB_PRELOAD(cast_f32_bf16_kernel);
@@ -1161,6 +1183,18 @@ int slb_preload_elementwise() {
 int slb_zero(void* p, long long bytes, cudaStream_t st) {
   if (bytes % 16) return -1;
   launch_k(zero_kernel, grid_for(bytes / 16, 256), 256, 0, st, reinterpret_cast<float4*>(p), bytes / 16);
+  return last_err();
+}
+int slb_zero_wait(void* p, long long bytes, const uint32_t* flag, uint32_t* expect_ctr, unsigned long long max_spins, int* status,
+                  cudaStream_t st) {
+  if (bytes % 16) return -1;
+  static bool carve = false;
+  if (!carve) {
+    cudaFuncSetAttribute(zero_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carve = true;
+  }
+  launch_k(zero_wait_kernel, grid_for(bytes / 16, 256, 64), 256, 0, st, reinterpret_cast<float4*>(p), bytes / 16, flag, expect_ctr,
+           max_spins, status);
   return last_err();
 }
 int slb_wait_flag(const uint32_t* flag, uint32_t expected, uint32_t* expect_ctr, unsigned long long max_spins, int* status,

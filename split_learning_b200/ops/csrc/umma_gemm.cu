@@ -65,6 +65,11 @@ struct GemmParams {
   int bnb_pool;                   // 1: the upstream block ends in MaxPool2 — dX lives on the pooled grid (H x W here),
                                   //    bnb_y on the 2H x 2W grid; the gradient goes to the window's (first) maximum
   // transformer epilogue (EPI_BF16, MODE_GEMM): out = act(acc + bias + residual); aux_out keeps the pre-activation
+  // cut-head dgrad: the gradient tiles land in the upstream stage's mailbox (peer pointer); the last CTA of the grid
+  // publishes the slot flag itself (st.release.sys) — no separate flag kernel on the backward edge
+  uint32_t* pub_ticket;           // zero at rest (self-resetting)
+  uint32_t* pub_flag;             // mailbox flag (may be a peer pointer) or nullptr
+  uint32_t* pub_seq;              // device sequence counter of the edge
   long long* trace;               // optional [16] cycle stamps of CTA (0,0,0) (tools/trace_gemm.py): where a launch spends its time
   int act;                        // 0 none, 1 ReLU, 2 GELU (erf), 3 tanh
   __nv_bfloat16* aux_out;         // [M][ldo] or nullptr
@@ -570,6 +575,21 @@ _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) o[j] = __uint
       }
     }
   }
+  if (p.pub_flag != nullptr && warp >= 2 && my_iters > 0) {
+    // ---- publish: every CTA fences its (peer) stores; the last one to arrive releases the mailbox flag system-wide ----
+    asm volatile("bar.sync 1, 128;");
+    if (threadIdx.x == 64) {
+      __threadfence_system();
+      const uint32_t t = atomicAdd(p.pub_ticket, 1u);
+      if (t == gridDim.x * gridDim.y * gridDim.z - 1u) {
+        *p.pub_ticket = 0;
+        const uint32_t value = *p.pub_seq + 1;
+        *p.pub_seq = value;
+        __threadfence_system();
+        st_release_sys(p.pub_flag, value);
+      }
+    }
+  }
   if (threadIdx.x == 64) SLB_STAMP(9);                         // epilogue thread 0 done
   tc_fence_before();
   __syncthreads();
@@ -741,9 +761,22 @@ int slb_preload_gemm() {
 // caller) with vector red.add instead of writing y — the last K slice of a tile (tile_counters) or slb_conv_finalize
 // then produces y.
 struct BnbArgs { const void* y; const float *mean, *istd, *gamma, *beta; int relu, pool; };
+struct PubArgs { uint32_t *ticket, *flag, *seq; };
 static int conv_igemm_impl(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
                            int B, int H, int W, int Ca, int Nout, int flip, int w_cin, int w_cout, int block_n, int k_split,
-                           float* acc, uint32_t* tile_counters, const BnbArgs* bnb, int dtype, cudaStream_t st);
+                           float* acc, uint32_t* tile_counters, const BnbArgs* bnb, int dtype, cudaStream_t st,
+                           const PubArgs* pub = nullptr);
+
+// conv / dgrad whose last CTA also publishes a mailbox flag (cut-head dgrad storing dX into the upstream stage's HBM)
+int slb_conv3x3_igemm_pub(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
+                          int B, int H, int W, int Ca, int Nout, int flip, int w_cin, int w_cout, int block_n, int k_split,
+                          float* acc, uint32_t* tile_counters, int dtype, uint32_t* pub_ticket, uint32_t* pub_flag,
+                          uint32_t* pub_seq, cudaStream_t st) {
+  if (k_split > 1 && tile_counters == nullptr) return -18;      // the flag must follow the *final* dX stores
+  PubArgs pa = {pub_ticket, pub_flag, pub_seq};
+  return conv_igemm_impl(x, w, y, bias, col_sum, col_sumsq, B, H, W, Ca, Nout, flip, w_cin, w_cout, block_n, k_split, acc,
+                         tile_counters, nullptr, dtype, st, pub_flag != nullptr ? &pa : nullptr);
+}
 
 int slb_conv3x3_igemm(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
                       int B, int H, int W, int Ca /*channels of A*/, int Nout /*output channels*/, int flip,
@@ -769,7 +802,8 @@ int slb_conv3x3_dgrad_bnstats(const void* dy, const void* w, void* dx, int B, in
 
 static int conv_igemm_impl(const void* x, const void* w, void* y, const float* bias, float* col_sum, float* col_sumsq,
                            int B, int H, int W, int Ca, int Nout, int flip, int w_cin, int w_cout, int block_n, int k_split,
-                           float* acc, uint32_t* tile_counters, const BnbArgs* bnb, int dtype, cudaStream_t st) {
+                           float* acc, uint32_t* tile_counters, const BnbArgs* bnb, int dtype, cudaStream_t st,
+                           const PubArgs* pub) {
   const int KE = 128 / esize(dtype);
   if (Ca % KE != 0 || Nout % 32 != 0) return -10;
   const int M = B * H * W;
@@ -814,6 +848,7 @@ static int conv_igemm_impl(const void* x, const void* w, void* y, const float* b
     p.bnb_mean = bnb->mean; p.bnb_istd = bnb->istd; p.bnb_gamma = bnb->gamma; p.bnb_beta = bnb->beta; p.bnb_relu = bnb->relu; p.bnb_pool = bnb->pool;
   }
   p.trace = g_gemm_trace;
+  if (pub != nullptr) { p.pub_ticket = pub->ticket; p.pub_flag = pub->flag; p.pub_seq = pub->seq; }
   dim3 grid((M + 127) / 128, Nout / bn, k_split);
   return dispatch_bn<MODE_CONV>(bn, dtype, ta, tbm, p, grid, st);
 }

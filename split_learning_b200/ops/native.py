@@ -153,7 +153,7 @@ def conv3x3_fwd(x, w_bf16, y, bias=None, col_sum=None, col_sumsq=None, acc=None,
         conv_finalize(acc, bias, y, col_sum, col_sumsq)
 
 
-def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None, bn_stats=None):
+def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None, bn_stats=None, publish=None):
     """dy [B,H,W,Cout] bf16, w [Cout,3,3,Cin] bf16 -> dx [B,H,W,Cin] bf16.
     ``bn_stats``: (y, mean, invstd, gamma, beta, relu, pool, dgamma, dbeta) of the *upstream* ConvBlock (BN + ReLU
     [+ MaxPool2]) whose output gradient is dx: the epilogue then also reduces that block's BatchNorm-backward sums."""
@@ -172,6 +172,14 @@ def conv3x3_dgrad(dy, w_bf16, dx, acc=None, tiling=None, counters=None, bn_stats
                                                c_int(Cin), c_int(Cout), c_int(bn), c_int(ks), _p(acc), _p(counters), _p(uy),
                                                _p(mean), _p(istd), _p(gamma), _p(beta), c_int(int(relu)), c_int(int(pool)), _p(dbeta), _p(dgamma),
                                                _stream()), "conv3x3_dgrad_bnstats")
+        return
+    if publish is not None:
+        # ``publish = (ticket, flag_ptr, seq)``: the kernel's last CTA releases the mailbox flag of the slot ``dx`` points into
+        ticket, flag, seq = publish
+        _check(lib().slb_conv3x3_igemm_pub(_p(dy), _p(w_bf16), _p(dx), _p(None), _p(None), _p(None), c_int(B), c_int(H), c_int(W),
+                                           c_int(Cout), c_int(Cin), c_int(1), c_int(Cin), c_int(Cout), c_int(bn), c_int(ks),
+                                           _p(acc), _p(counters), _dt(dy), _p(ticket), _p(flag), _p(seq), _stream()),
+               "conv3x3_dgrad_pub")
         return
     _check(lib().slb_conv3x3_igemm(_p(dy), _p(w_bf16), _p(dx), _p(None), _p(None), _p(None), c_int(B), c_int(H), c_int(W),
                                    c_int(Cout), c_int(Cin), c_int(1), c_int(Cin), c_int(Cout), c_int(bn), c_int(ks), _p(acc),
@@ -270,7 +278,14 @@ def fused_cut_supported(B, H, W, Cin, Cout, pool, ke: int = 64) -> bool:
 
 
 # ------------------------------------------------------------------ memory-bound ops
-def zero_(t):
+def zero_(t, wait=None):
+    """Zero a scratch tensor.  ``wait = (flag_ptr, expect_ctr, max_spins, status)``: the same launch also acquires a mailbox
+    slot flag (``zero_wait_kernel``) — the first kernel of a program that consumes a slot."""
+    if wait is not None:
+        flag_ptr, expect_ctr, max_spins, status = wait
+        _check(lib().slb_zero_wait(_p(t), c_longlong(t.numel() * t.element_size()), c_void_p(flag_ptr), _p(expect_ctr),
+                                   c_uint64(max_spins), _p(status), _stream()), "zero_wait")
+        return
     _check(lib().slb_zero(_p(t), c_longlong(t.numel() * t.element_size()), _stream()), "zero")
 
 

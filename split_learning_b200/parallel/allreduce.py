@@ -42,14 +42,16 @@ class Member:
     end_layer: int
     handles: Dict[str, bytes]      # "P" / "S" / "I" / "sync" -> CUDA IPC handle
     n: Dict[str, int]              # floats in each buffer
+    gpu: str = ""                  # physical GPU (uuid): replicas sharing a GPU must all fit on it at once (see run)
 
     def wire(self) -> dict:
         return {"uid": self.uid, "cluster": self.cluster, "start": self.start_layer, "end": self.end_layer,
-                "handles": self.handles, "n": self.n}
+                "handles": self.handles, "n": self.n, "gpu": self.gpu}
 
     @staticmethod
     def from_wire(d: dict) -> "Member":
-        return Member(str(d["uid"]), int(d["cluster"]), int(d["start"]), int(d["end"]), dict(d["handles"]), dict(d["n"]))
+        return Member(str(d["uid"]), int(d["cluster"]), int(d["start"]), int(d["end"]), dict(d["handles"]), dict(d["n"]),
+                      str(d.get("gpu", "")))
 
 
 @dataclass
@@ -99,7 +101,7 @@ class DeviceFedAvg:
     ``TorchDistComm`` / ``BrokerComm`` from parallel/fedavg.py, or any object with ``all_gather_object``); ``run`` is a
     pure device operation."""
 
-    def __init__(self, ex, uid: str, cluster: int, comm, spin_limit: int = 1 << 26):
+    def __init__(self, ex, uid: str, cluster: int, comm, spin_limit: int = 1 << 28):
         self.ex, self.uid, self.cluster, self.comm = ex, str(uid), int(cluster), comm
         self.device = ex.device
         self.spin_limit = spin_limit
@@ -118,7 +120,8 @@ class DeviceFedAvg:
         ex = self.ex
         me = Member(self.uid, self.cluster, ex.start_layer, ex.end_layer,
                     {"P": ex.P_handle, "S": ex.S_handle, "I": ex.I_handle, "sync": self.sync_handle},
-                    {"P": ex.n_params, "S": ex.n_stats, "I": ex.n_ints})
+                    {"P": ex.n_params, "S": ex.n_stats, "I": ex.n_ints},
+                    gpu=str(torch.cuda.get_device_properties(self.device).uuid))
         wires = self.comm.all_gather_object(me.wire())
         self.members = sorted((Member.from_wire(w) for w in wires), key=lambda m: m.uid)
         if len(self.members) > MAX_PARTICIPANTS:
@@ -135,6 +138,12 @@ class DeviceFedAvg:
                 self.ptrs[(q, kind)] = (self.sync_ptr if kind == "sync" else getattr(ex, kind).data_ptr()) if q == self.me \
                     else open_exported(m.handles[kind], self.device)
         self.clusters = sorted({m.cluster for m in self.members})
+        # Every kernel of a round spins (thread 0 of each CTA) until its peers' kernels have started.  Replicas that share
+        # one physical GPU (threads / processes of a single-GPU run) must therefore be resident together: split the SM's
+        # CTA slots (4 x 512 threads) between them, with slack.  One replica per GPU gets the full 2 CTAs per SM.
+        coloc = max(1, sum(1 for m in self.members if m.gpu == self.members[self.me].gpu))
+        sms = N.num_sms(self.device)
+        self.grid = 2 * sms if coloc == 1 else max(1, int(4 * sms / 1.5 / coloc))
 
     # ------------------------------------------------------------------ one round
     def run(self, weight: float, ok: bool = True, timed: bool = False) -> bool:
@@ -142,7 +151,15 @@ class DeviceFedAvg:
         peer never showed up); the parameters are then untouched."""
         ex = self.ex
         lib = N.lib()
-        stream = torch.cuda.current_stream(self.device)
+        # The replica's own (non-blocking) stream: it already orders the round's last optimizer step before us, and —
+        # unlike the legacy default stream, which every thread of a process shares — a kernel spinning here for its peers
+        # can never sit in front of a co-located peer's kernel in the same queue.
+        stream = ex.stream
+        with torch.cuda.stream(stream):
+            return self._run_on(stream, lib, weight, ok, timed)
+
+    def _run_on(self, stream, lib, weight: float, ok: bool, timed: bool) -> bool:
+        ex = self.ex
         for bn, st in ex.bn_state.items():                              # integer counters -> float mirrors
             o = ex.int_entries[f"layer{bn}.num_batches_tracked"][0]
             ex.I[o:o + 1].copy_(st["num_batches_tracked"].to(torch.float32).reshape(1))
@@ -163,7 +180,7 @@ class DeviceFedAvg:
                                           ctypes.c_int(ncl), ctypes.c_longlong(s.n), ctypes.c_longlong(0),
                                           ctypes.c_longlong(s.n if s.kind == "I" else 0), ctypes.c_uint32(epoch),
                                           ctypes.c_float(float(weight)), ctypes.c_int(int(bool(ok))),
-                                          ctypes.c_uint64(self.spin_limit), ctypes.c_int(N.num_sms(self.device) * 2),
+                                          ctypes.c_uint64(self.spin_limit), ctypes.c_int(self.grid),
                                           ctypes.c_void_p(stream.cuda_stream))
             N._check(rc, "fedavg_allreduce", 2)
         self.round += 1

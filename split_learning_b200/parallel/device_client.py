@@ -12,9 +12,9 @@ with the downstream stage multiplexing its lanes on one executor (fan-in).  If a
 divide its predecessor, or the stage has no native plan, the client keeps the host data plane —
 a *topology* fallback (logged), never a kernel fallback.
 
-Only full microbatches go through the device plane (mailbox geometry is static): a trailing
-partial batch of the loader is dropped, which the reference's sample counts (multiples of the
-batch size) never produce.
+A trailing partial batch of the loader (``num-sample`` not a multiple of the batch size) is not dropped: it runs
+through a second program set compiled for its size on the *same* mailboxes (prefix views of the slots, shared sequence
+counters), so microbatch counts — the FedAvg weights, src/train/VGG16.py:109 — match the reference's.
 """
 from __future__ import annotations
 
@@ -144,12 +144,31 @@ class DeviceRpcClient(RpcClient):
                                              slot_offset=k * depth if multi else 0, bind_inputs=not multi)
         self._lane_info = lanes
         self.dstage = self.dstages[lanes[0][0]]
+        self._edges = (fwd_in, grad_in, fwd_out, grad_out, multi, depth)
+        self._tail_stages: Dict[tuple, DeviceStage] = {}
+
+    def _tail_stage(self, lane: int, b: int) -> DeviceStage:
+        """Program set of lane ``lane`` for a microbatch of ``b`` < batch-size samples, on the lane's own mailboxes."""
+        key = (lane, b)
+        if key not in self._tail_stages:
+            fwd_in, grad_in, fwd_out, grad_out, multi, depth = self._edges
+            ex = self.executor
+            lanes = self._lane_info
+            k = [l for l, _, _ in lanes].index(lane)
+            view = lambda d: d[lane].view(b) if lane in d else None
+            if multi and not any(kk[1] == b for kk in self._tail_stages):
+                ex.plan(b).bind_inputs([t for l, _, _ in lanes for t in fwd_in[l].view(b).payload])
+            self._tail_stages[key] = DeviceStage(ex, b, depth, fwd_in=view(fwd_in), grad_in=view(grad_in), fwd_out=view(fwd_out),
+                                                 grad_out=view(grad_out), slot_offset=k * depth if multi else 0,
+                                                 bind_inputs=not multi, counters_from=self.dstages[lane])
+        return self._tail_stages[key]
 
     # ------------------------------------------------------------------
     def _collect_plans(self, lanes) -> Dict[int, int]:
         """Batch counts announced by the first-stage client of every lane I serve."""
         plan_q = f"plan_{self.client_id}"
         counts: Dict[int, int] = {}
+        self._tails: Dict[int, int] = {}
         t0 = time.monotonic()
         while len(counts) < len(lanes):
             m = self.channel.get_obj(plan_q, 0.25)
@@ -158,6 +177,7 @@ class DeviceRpcClient(RpcClient):
                     raise TimeoutError("upstream never announced its batch count")
                 continue
             counts[int(m["lane"])] = int(m["batches"])
+            self._tails[int(m["lane"])] = int(m.get("tail", 0))
         return counts
 
     def run_stage(self):
@@ -166,52 +186,80 @@ class DeviceRpcClient(RpcClient):
         lanes = self._lane_info
         B = self.dstage.B
         ex = self.executor
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(self.dstage.stream)
+        # the reference prints the loss of every microbatch (src/train/VGG16.py:168, a host sync per step); here every step
+        # copies it to pinned host memory asynchronously and the round reports the mean
+        loss_log: List[torch.Tensor] = []
+
+        def log_loss(st):
+            if self.is_last and self.opts.get("loss-every-step", True):
+                h = self._loss_pool[len(loss_log)] if len(loss_log) < len(self._loss_pool) else torch.zeros(4).pin_memory()
+                with torch.cuda.stream(st.stream):
+                    h.copy_(ex.loss_buf, non_blocking=True)
+                loss_log.append(h)
+        if not hasattr(self, "_loss_pool"):
+            self._loss_pool = [torch.zeros(4).pin_memory() for _ in range(512)] if self.is_last else []
         if self.is_first:
             lane, _, down = lanes[0]
             st = self.dstages[lane]
-            batches = []
+            batches, tail = [], None
             for batch in self.train_loader:
                 x, y = batch if not isinstance(batch, dict) else (batch["input_ids"], batch["labels"])
+                item = (x.float(), torch.as_tensor(y).long()) if x.is_cuda else \
+                    (x.float().pin_memory(), torch.as_tensor(y).long().pin_memory())     # GPU-resident loader: already in HBM
                 if x.shape[0] == B:
-                    if x.is_cuda:                       # GPU-resident loader: the microbatch already lives in HBM
-                        batches.append((x.float(), torch.as_tensor(y).long()))
-                    else:
-                        batches.append((x.float().pin_memory(), torch.as_tensor(y).long().pin_memory()))
+                    batches.append(item)
+                elif 0 < x.shape[0] < B:
+                    tail = item                         # trailing partial microbatch: own program set, same mailboxes
             n = len(batches)
-            self.channel.publish_obj(f"plan_{down}", {"lane": lane, "batches": n})
+            tb = int(tail[0].shape[0]) if tail is not None else 0
+            self.channel.publish_obj(f"plan_{down}", {"lane": lane, "batches": n, "tail": tb})
+            if tail is not None:
+                batches.append(tail)
+            stage_of = lambda it: st if it < n else self._tail_stage(lane, tb)
             it_b = 0
-            for it in range(n):
+            for it in range(len(batches)):
                 if it - it_b >= st.depth:
-                    st.backward(it_b)
+                    stage_of(it_b).backward(it_b)
                     it_b += 1
-                st.stage_input(it, *batches[it])
-                st.forward(it)
-            while it_b < n:
-                st.backward(it_b)
+                stage_of(it).stage_input(it, *batches[it])
+                stage_of(it).forward(it)
+            while it_b < len(batches):
+                stage_of(it_b).backward(it_b)
                 it_b += 1
-            total = n
+            total = len(batches)
         else:
             counts = self._collect_plans(lanes)
+            tails = self._tails
             if not self.is_last:
                 for lane, _, down in lanes:
-                    self.channel.publish_obj(f"plan_{down}", {"lane": lane, "batches": counts[lane]})
+                    self.channel.publish_obj(f"plan_{down}", {"lane": lane, "batches": counts[lane], "tail": tails.get(lane, 0)})
             depth = self.dstage.depth
-            most = max(counts.values()) if counts else 0
+            n_of = {lane: counts[lane] + (1 if tails.get(lane, 0) else 0) for lane, _, _ in lanes}
+            most = max(n_of.values()) if n_of else 0
+
+            def stage_of(lane, it):
+                return self.dstages[lane] if it < counts[lane] else self._tail_stage(lane, tails[lane])
             # lanes are interleaved microbatch by microbatch (round-robin over the upstream replicas)
             for it in range(most + (0 if self.is_last else depth)):
                 for lane, _, _ in lanes:
-                    st, n = self.dstages[lane], counts[lane]
+                    n = n_of[lane]
                     if self.is_last:
                         if it < n:
-                            st.last(it)
+                            stage_of(lane, it).last(it)
+                            log_loss(stage_of(lane, it))
                     else:
                         if 0 <= it - depth < n:
-                            st.backward(it - depth)
+                            stage_of(lane, it - depth).backward(it - depth)
                         if it < n:
-                            st.forward(it)
-            total = sum(counts.values())
+                            stage_of(lane, it).forward(it)
+            total = sum(n_of.values())
+        ev1.record(self.dstage.stream)
         self.dstage.stream.synchronize()
-        for st in self.dstages.values():
+        self.last_device_ms = ev0.elapsed_time(ev1)
+        self.last_loss = (sum(float(h[0]) for h in loss_log) / len(loss_log)) if loss_log else None
+        for st in list(self.dstages.values()) + list(self._tail_stages.values()):
             st.check()
         if self.is_first:
             self.send_to_server(M.notify(self.client_id, self.layer_id, self.cluster))
@@ -246,7 +294,32 @@ class DeviceRpcClient(RpcClient):
         mine = sorted(str(cid) for cid, cl, lid in everyone if int(cl) == int(self.cluster or 0) and int(lid) == self.layer_id)
         first_cluster = min(int(cl) for _, cl, _ in everyone)
         leader = bool(mine) and mine[0] == me and int(self.cluster or 0) == first_cluster
-        sd = None
-        if leader and send:
-            sd = {k: v.detach().to("cpu") for k, v in ex.state_dict().items()}
-        self.send_to_server(M.update(self.client_id, self.layer_id, bool(result) and done, size, self.cluster, sd, resident=True))
+        want = leader and send and done and bool(self.start_msg.get("save_parameters", True))
+        rnd = int(self.start_msg.get("round", self.rounds_done + 1))
+        extra = dict(resident=True, device_ms=getattr(self, "last_device_ms", None), loss=getattr(self, "last_loss", None))
+        if want and self.start_msg.get("async_checkpoint"):
+            # the checkpoint copy leaves the round's critical path: snapshot on the device now (the next round may already
+            # be training when the bytes cross PCIe), UPDATE without a payload, CHECKPOINT from a background thread
+            snap = {k: v.detach().clone() for k, v in ex.state_dict().items()}
+            self.send_to_server(M.update(self.client_id, self.layer_id, bool(result) and done, size, self.cluster, None,
+                                         checkpoint_follows=rnd, **extra))
+            self._ship_checkpoint(snap, rnd)
+            return
+        sd = {k: v.detach().to("cpu") for k, v in ex.state_dict().items()} if want else None
+        self.send_to_server(M.update(self.client_id, self.layer_id, bool(result) and done, size, self.cluster, sd, **extra))
+
+    def _ship_checkpoint(self, snap: dict, rnd: int) -> None:
+        import threading
+        ch = self.__dict__.get("_ckpt_channel")
+        if ch is None:
+            ch = self._ckpt_channel = self.channel.clone()
+        prev = self.__dict__.get("_ckpt_thread")
+
+        def ship():
+            if prev is not None:
+                prev.join()                                   # rounds arrive in order
+            with torch.cuda.device(self.executor.device):
+                host = {k: v.to("cpu") for k, v in snap.items()}
+            ch.publish_obj(M.RPC_QUEUE, M.checkpoint(self.client_id, self.layer_id, self.cluster, rnd, host))
+        self._ckpt_thread = threading.Thread(target=ship, name=f"slb200-ckpt-upload-{rnd}")     # non-daemon: finishes before exit
+        self._ckpt_thread.start()

@@ -199,6 +199,24 @@ class Mailbox:
     def flag_ptr(self, slot: int) -> int:
         return self.raw_ptr + self.spec.flags_off + 4 * slot
 
+    def view(self, batch: int) -> "Mailbox":
+        """The same ring seen with a smaller microbatch (the trailing partial batch of an epoch): payload and label slots
+        are prefixes of the full slots (batch is the outermost dimension), flags / gate / sequence numbers are shared."""
+        if batch == self.spec.batch:
+            return self
+        assert 0 < batch < self.spec.batch
+        v = object.__new__(Mailbox)
+        v.spec, v.base, v.owner, v.gate, v.raw_ptr = self.spec, self.base, self.owner, self.gate, self.raw_ptr
+        shape = (batch,) + tuple(self.spec.payload_shape[1:])
+        if self.base is None:
+            v.payload = [DevPtr(p.data_ptr(), shape, self.spec.itemsize) for p in self.payload]
+            v.labels = [DevPtr(l.data_ptr(), (batch,), 8) for l in self.labels]
+        else:
+            v.payload = [p[:batch] for p in self.payload]
+            v.labels = [l[:batch] for l in self.labels]
+        v.flags, v.header = self.flags, self.header
+        return v
+
     # ---- allocation / export --------------------------------------------------------
     @staticmethod
     def allocate_local(spec: MailboxSpec, device) -> "Mailbox":

@@ -43,7 +43,7 @@ class DeviceStage:
                  fwd_in: Optional[Mailbox] = None, grad_in: Optional[Mailbox] = None,
                  fwd_out: Optional[Mailbox] = None, grad_out: Optional[Mailbox] = None,
                  stream: Optional[torch.cuda.Stream] = None, wait_spins: Optional[int] = None,
-                 slot_offset: int = 0, bind_inputs: bool = True):
+                 slot_offset: int = 0, bind_inputs: bool = True, counters_from: Optional["DeviceStage"] = None):
         """``slot_offset`` / ``bind_inputs=False``: one of several *lanes* multiplexed on the same executor (fan-in: a
         stage fed by several upstream replicas).  The caller binds the plan's input slots to the concatenated mailbox
         payloads of all lanes once; this lane's slot ``s`` is plan slot ``slot_offset + s``."""
@@ -53,10 +53,16 @@ class DeviceStage:
         self.stream = stream or ex.stream
         self.plan = ex.plan(batch)
         dev = ex.device
-        self.seq_fwd = EdgeCounters(depth, dev)       # values I publish downstream
-        self.seq_grad = EdgeCounters(depth, dev)      # values I publish upstream
-        self.exp_fwd = EdgeCounters(depth, dev)       # values I have consumed from upstream activations
-        self.exp_grad = EdgeCounters(depth, dev)      # values I have consumed from downstream gradients
+        if counters_from is not None:
+            # a second program set on the same edges (another batch size: the trailing partial microbatch of an epoch) keeps
+            # counting where the main stage stands — mailbox flags are monotonic per edge, not per program
+            self.seq_fwd, self.seq_grad = counters_from.seq_fwd, counters_from.seq_grad
+            self.exp_fwd, self.exp_grad = counters_from.exp_fwd, counters_from.exp_grad
+        else:
+            self.seq_fwd = EdgeCounters(depth, dev)       # values I publish downstream
+            self.seq_grad = EdgeCounters(depth, dev)      # values I publish upstream
+            self.exp_fwd = EdgeCounters(depth, dev)       # values I have consumed from upstream activations
+            self.exp_grad = EdgeCounters(depth, dev)      # values I have consumed from downstream gradients
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
         import os
         self.wait_spins = wait_spins if wait_spins is not None else int(os.environ.get("SLB200_WAIT_SPINS", str(1 << 28)))
@@ -72,9 +78,14 @@ class DeviceStage:
         self.launches_per: Dict[str, int] = {}
 
     # ---- program bodies ----------------------------------------------------------------
+    def _wait(self, mb: Mailbox, ctr: EdgeCounters, slot: int):
+        """Flag acquisition of a slot, fused into the first kernel of the consuming pass (see ``_Plan._forward``)."""
+        return (mb.flag_ptr(slot), ctr.at(slot), self.wait_spins, self.status)
+
     def _F(self, slot: int) -> None:
+        wait = None
         if self.fwd_in is not None:
-            N.wait_flag(self.fwd_in.flag_ptr(slot), 0, self.exp_fwd.at(slot), self.wait_spins, self.status)
+            wait = self._wait(self.fwd_in, self.exp_fwd, slot)
             labels = self.fwd_in.labels[slot]
         else:
             labels = self.labels_slots[slot]
@@ -84,25 +95,35 @@ class DeviceStage:
             N.memcpy_async(self.fwd_out.labels[slot].data_ptr(), labels.data_ptr(), self.B * 8)
             out = self.fwd_out.payload[slot]
             pub = {"flag": self.fwd_out.flag_ptr(slot), "seq": self.seq_fwd.at(slot)}
-        self.plan._forward(self.off + slot, out_ptr_override=out, publish=pub)
+        if wait is not None and self.fwd_out is not None:
+            # a middle stage copies the labels downstream before its first kernel: the slot must be acquired first
+            N.wait_flag(*wait[:1], 0, wait[1], wait[2], wait[3])
+            wait = None
+        self.plan._forward(self.off + slot, out_ptr_override=out, publish=pub, wait=wait)
+
+    def _publish_grad(self, slot: int):
+        return (self.grad_out.flag_ptr(slot), self.seq_grad.at(slot)) if self.grad_out is not None else None
 
     def _B(self, slot: int) -> None:
-        N.wait_flag(self.grad_in.flag_ptr(slot), 0, self.exp_grad.at(slot), self.wait_spins, self.status)
+        wait = self._wait(self.grad_in, self.exp_grad, slot)
         if self.ex.recompute:
-            self.plan._forward(self.off + slot)       # faithful recompute with current weights, no publish
+            self.plan._forward(self.off + slot, wait=wait)   # faithful recompute with current weights, no publish
+        else:
+            N.wait_flag(wait[0], 0, wait[1], wait[2], wait[3])
         gout = self.grad_out.payload[slot] if self.grad_out is not None else None
-        self.plan._backward(self.grad_in.payload[slot], grad_out_override=gout)
-        if self.grad_out is not None:
+        self.plan._backward(self.grad_in.payload[slot], grad_out_override=gout, publish_grad=self._publish_grad(slot))
+        if self.grad_out is not None and not self.plan.grad_published:
             N.set_flag(self.grad_out.flag_ptr(slot), 0, self.seq_grad.at(slot))
 
     def _L(self, slot: int) -> None:
         labels = self.labels_slots[slot]
+        wait = None
         if self.fwd_in is not None:
-            N.wait_flag(self.fwd_in.flag_ptr(slot), 0, self.exp_fwd.at(slot), self.wait_spins, self.status)
+            wait = self._wait(self.fwd_in, self.exp_fwd, slot)
             labels = self.fwd_in.labels[slot]
         gout = self.grad_out.payload[slot] if self.grad_out is not None else None
-        self.plan._last(self.off + slot, labels=labels, grad_out_override=gout)
-        if self.grad_out is not None:
+        self.plan._last(self.off + slot, labels=labels, grad_out_override=gout, wait=wait, publish_grad=self._publish_grad(slot))
+        if self.grad_out is not None and not self.plan.grad_published:
             N.set_flag(self.grad_out.flag_ptr(slot), 0, self.seq_grad.at(slot))
 
     # ---- execution ----------------------------------------------------------------------

@@ -341,7 +341,6 @@ def bench_ring(args) -> dict:
     loss = torch.tensor([float(loss_host[0])], device=dev)
     dist.all_reduce(loss, op=dist.ReduceOp.SUM)
     dist.barrier()
-    dist.destroy_process_group()
     if rank != 0:
         return {}
     images = world * K * B
@@ -430,7 +429,6 @@ def bench_multi_gpu(args) -> dict:
     loss = torch.tensor([float(loss_host[0]) if not st.ex.is_first else 0.0], device=dev)
     dist.all_reduce(loss, op=dist.ReduceOp.SUM)
     dist.barrier()
-    dist.destroy_process_group()
     if rank != 0:
         return {}
     images = n * K * B

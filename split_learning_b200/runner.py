@@ -36,6 +36,12 @@ def run_inproc(cfg: Config, devices: Optional[Sequence[str]] = None, profiles: O
                 traceback.print_exc()
                 errors.append(e)
                 server.done = True
+                try:                            # a failed role must not leave the others waiting out their watchdogs
+                    from . import messages as M
+                    for c in list(server.clients):
+                        server.send_to_response(c.client_id, M.stop("run aborted"))
+                except Exception:
+                    pass
         return run
 
     info = cfg.infor_cluster if (cfg.cluster_mode and cfg.infor_cluster_given) else None

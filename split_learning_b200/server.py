@@ -101,6 +101,16 @@ class Server:
                 continue
             last = now
             self.on_request(m)
+        self._finish_checkpoints()
+
+    def _finish_checkpoints(self, timeout: float = 180.0) -> None:
+        """Training is over; stage leaders may still be shipping the last rounds' parameters for the checkpoint."""
+        deadline = time.monotonic() + timeout
+        while self.__dict__.get("_ckpt_pending") and time.monotonic() < deadline:
+            m = self.ch.get_obj(M.RPC_QUEUE, 0.25)
+            if m is not None and m.get("action") == M.CHECKPOINT:
+                self.on_checkpoint(m)
+        self.drain_checkpoints()
 
     def _beacon(self, now: float) -> None:
         """Relay liveness to every client and check that every beaconing client is still there."""
@@ -119,7 +129,7 @@ class Server:
             self.last_seen[str(message.get("client_id"))] = time.monotonic()
             return
         handler = {M.REGISTER: self.on_register, M.NOTIFY: self.on_notify, M.UPDATE: self.on_update,
-                   M.READY: self.on_ready}.get(action)
+                   M.READY: self.on_ready, M.CHECKPOINT: self.on_checkpoint}.get(action)
         if handler is None:
             self.logger.log_warning(f"unknown action {action}")
             return
@@ -185,7 +195,10 @@ class Server:
         else:
             for c in self.clients:
                 c.cluster, c.train = 0, True
-            members = [[c.client_id for c in self.clients if c.layer_id == s + 1] for s in range(self.num_stages)]
+            # members of a stage in GPU-ordinal order when the clients announced one (REGISTER ``rank``): the device data
+            # plane pairs lane i with member i % n of the next stage, so the launcher decides the placement (ring / split)
+            order = sorted(self.clients, key=lambda c: (c.rank is None, c.rank if c.rank is not None else 0))
+            members = [[c.client_id for c in order if c.layer_id == s + 1] for s in range(self.num_stages)]
             self.topology = Topology(self.num_stages, [ClusterPlan(0, list(cfg.no_cluster_cut_layers), members)])
         self._reset_round_buffers()
 
@@ -281,7 +294,10 @@ class Server:
         return M.start(params, layers, self.model_name, self.data_name,
                        self.learning, c.label_counts, self.refresh, c.cluster,
                        num_layers=self.num_stages, round=self.global_round - self.round + 1,
-                       peers=self._peer_table(c), num_clusters=len(self.topology.clusters), resident=resident)
+                       peers=self._peer_table(c), num_clusters=len(self.topology.clusters), resident=resident,
+                       save_parameters=bool(self.save_parameters),
+                       async_checkpoint=bool(self.save_parameters and not self.validation
+                                             and self.cfg.b200.get("async-checkpoint", True)))
 
     def _peer_table(self, c: ClientInfo) -> dict:
         """Who is upstream/downstream of this client (ranks + ids): lets the GPU data plane
@@ -344,6 +360,12 @@ class Server:
         sd = message.get("parameters")
         self._resident_votes = getattr(self, "_resident_votes", [])
         self._resident_votes.append(bool(message.get("resident", False)))
+        if message.get("checkpoint_follows"):
+            self.__dict__.setdefault("_ckpt_pending", set()).add(int(message["checkpoint_follows"]))
+        if message.get("device_ms") is not None:
+            self._device_ms = getattr(self, "_device_ms", []) + [float(message["device_ms"])]
+        if message.get("loss") is not None:
+            self._losses = getattr(self, "_losses", []) + [float(message["loss"])]
         if self.save_parameters and self.round_result and sd is not None:
             if has_nan(sd):
                 self.round_result = False
@@ -363,6 +385,11 @@ class Server:
         self._resident_votes = []
         metrics = {"round": self.global_round - self.round + 1, "ok": self.round_result,
                    "seconds": time.monotonic() - self._round_t0}
+        if getattr(self, "_device_ms", None):         # device time of the training loops (CUDA events), max over clients
+            metrics["device_ms"] = max(self._device_ms)
+        if getattr(self, "_losses", None):
+            metrics["train_loss"] = sum(self._losses) / len(self._losses)
+        self._device_ms, self._losses = [], []
         if self.save_parameters and self.round_result:
             for k in range(len(self.topology.clusters)):
                 self.avg_all_parameters(k)
@@ -390,6 +417,34 @@ class Server:
         else:
             self.logger.log_info("Stop training !!!")
             self.notify_clients(start=False)
+
+    # ---------------------------------------------------------- asynchronous checkpoint (device plane)
+    def on_checkpoint(self, message: dict) -> None:
+        """Stage state-dicts of an already finished ``resident`` round: collected per round, written by a background thread
+        once every stage of the (first) cluster has arrived — the next round is not held up by a 134 MB upload + torch.save."""
+        import threading
+        rnd = int(message["round"])
+        parts = self.__dict__.setdefault("_ckpt_parts", {}).setdefault(rnd, {})
+        parts[int(message["layer_id"])] = message["parameters"]
+        if len(parts) < self.num_stages:
+            return
+        full: Dict[str, torch.Tensor] = {}
+        for s in sorted(parts):
+            full.update(parts[s])
+        del self._ckpt_parts[rnd]
+        self.__dict__.setdefault("_ckpt_pending", set()).discard(rnd)
+        path = checkpoint_path(self.model_name, self.data_name, self.workdir)
+
+        def write():
+            save_checkpoint(full, path, meta={"round": rnd})
+            self.logger.log_info(f"checkpoint of round {rnd} written ({len(full)} entries)")
+        t = threading.Thread(target=write, daemon=True, name=f"slb200-ckpt-{rnd}")
+        self.__dict__.setdefault("_ckpt_threads", []).append(t)
+        t.start()
+
+    def drain_checkpoints(self, timeout: float = 60.0) -> None:
+        for t in self.__dict__.get("_ckpt_threads", []):
+            t.join(timeout)
 
     # ---------------------------------------------------------- aggregation
     def avg_all_parameters(self, cluster: int) -> None:

@@ -582,9 +582,11 @@ class _Plan:
         return a["dx_bf16"]
 
     # ---- the kernel sequences ------------------------------------------------------
-    def _forward(self, slot: int, out_ptr_override: Optional[torch.Tensor] = None, publish=None) -> None:
+    def _forward(self, slot: int, out_ptr_override: Optional[torch.Tensor] = None, publish=None, wait=None) -> None:
+        """``wait``: (flag_ptr, expect_ctr, max_spins, status) of the mailbox slot this pass consumes — acquired inside the
+        pass's first kernel (the scratch zeroing) instead of a stand-alone wait launch."""
         ex = self.ex
-        N.zero_(self.scratch)
+        N.zero_(self.scratch, wait=wait)
         x: torch.Tensor = self.x_in[slot]
         nb = len(ex.blocks)
         for bi, b in enumerate(ex.blocks):
@@ -673,9 +675,12 @@ class _Plan:
                                   b.drop, ex.seed + b.lin, ex.step_ctr)
                 x = a["out"]
 
-    def _backward(self, dout: torch.Tensor, grad_out_override: Optional[torch.Tensor] = None) -> None:
-        """dout: gradient w.r.t. the stage output (bf16) — or fp32 dlogits on the last stage."""
+    def _backward(self, dout: torch.Tensor, grad_out_override: Optional[torch.Tensor] = None, publish_grad=None) -> None:
+        """dout: gradient w.r.t. the stage output — or fp32 dlogits on the last stage.  ``publish_grad = (flag_ptr, seq)``:
+        when the stage input gradient is produced by the cut-head conv dgrad (stored straight into the upstream stage's
+        mailbox), that kernel's last CTA also publishes the slot flag; ``self.grad_published`` tells the caller."""
         ex = self.ex
+        self.grad_published = False
         g: Any = dout
         main = torch.cuda.current_stream()
         side = self.side
@@ -779,8 +784,12 @@ class _Plan:
                                          ex.view(ex.P, f"layer{up.bn}.bias"), up.relu, up.pool, ex.view(ex.G, f"layer{up.bn}.weight"),
                                          ex.view(ex.G, f"layer{up.bn}.bias"))
                                 bn_reduced.add(bi - 1)
+                            pub = None
+                            if bi == 0 and grad_out_override is not None and publish_grad is not None and stats is None:
+                                pub = (self.ticket[1:2], publish_grad[0], publish_grad[1])
+                                self.grad_published = True
                             N.conv3x3_dgrad(dy, ex.W(f"layer{b.conv}.weight"), dx, acc=dacc, counters=self.tile_counters,
-                                            bn_stats=stats)
+                                            bn_stats=stats, publish=pub)
                             g = dx
                 else:
                     g = dy
@@ -796,13 +805,14 @@ class _Plan:
             N.sgd_momentum(ex.P, ex.G, ex.M, ex.PB, ex.lr, ex.mu)
         N.counter_inc(ex.step_ctr)
 
-    def _last(self, slot: int = 0, labels: Optional[torch.Tensor] = None, grad_out_override=None) -> None:
+    def _last(self, slot: int = 0, labels: Optional[torch.Tensor] = None, grad_out_override=None, wait=None,
+              publish_grad=None) -> None:
         ex = self.ex
-        self._forward(slot)
+        self._forward(slot, wait=wait)
         logits = self.act[-1]["logits"]
         N.zero_(ex.loss_buf)
         N.ce_fwd_bwd(logits, self.labels if labels is None else labels, self.dlogits, ex.loss_buf, ex.nan_flag)
-        self._backward(self.dlogits, grad_out_override)
+        self._backward(self.dlogits, grad_out_override, publish_grad=publish_grad)
 
     def bind_inputs(self, tensors) -> None:
         """Use externally owned buffers (mailbox slots) as the stage-input slots."""

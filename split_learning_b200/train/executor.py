@@ -264,7 +264,14 @@ def make_executor(model: SplitModel, model_name: str, learning: dict, device, is
     if kind in ("auto", "b200") and dev.type == "cuda":
         from .b200_executor import B200Executor, supports
         if supports(model):
-            return B200Executor(model, model_name, learning, device=dev, is_first=is_first, is_last=is_last,
+            # ``b200.precision`` (tf32 = the reference's precision, default; bf16 = fast mode); ``clip-grad-norm`` applies
+            # on the last stage only, as in other/Vanilla_SL/src/Scheduler.py:204-205
+            lrn = dict(learning)
+            if opts.get("precision") and not lrn.get("precision"):
+                lrn["precision"] = opts["precision"]
+            if not is_last:
+                lrn["clip-grad-norm"] = 0.0
+            return B200Executor(model, model_name, lrn, device=dev, is_first=is_first, is_last=is_last,
                                 recompute=bool(opts.get("recompute", True)))
         from .cnn_native import supports as cnn_supports
         from .token_native import supports as token_supports

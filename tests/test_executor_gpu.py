@@ -36,8 +36,19 @@ def _cos(a, b):
     return float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
 
 
+# tolerances per compute precision: tf32 (default; the reference's precision: fp32 tensors, TF32 convolutions, fp32 Linear)
+# must track the torch executor closely; bf16 (opt-in fast mode) takes different ReLU / max-pool decisions near thresholds
+# (cut gradient: torch's own TF32 run sits at cos 0.988 against torch fp32 on this random-init net — ReLU / max-pool decision
+# flips amplify operand rounding, tools/debug_parity.py — so two TF32 engines are compared at 0.97, not 0.999)
+TOL = {"tf32": dict(act0=4e-3, act_cos=0.999, grad_cos=0.97, loss_rel=0.005, loss_abs=0.003, w_cos=0.999),
+       "bf16": dict(act0=3e-2, act_cos=0.95, grad_cos=0.5, loss_rel=0.03, loss_abs=0.02, w_cos=0.98)}
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
 @pytest.mark.parametrize("cuts", [(7,), (5, 10), (14,)])
-def test_trajectory_matches_torch_executor(cuts):
+def test_trajectory_matches_torch_executor(cuts, precision):
+    tol = TOL[precision]
+    learning = dict(LEARNING, precision=precision)
     from split_learning_b200.models import VGG16_CIFAR10
     from split_learning_b200.train.b200_executor import B200Executor
     from split_learning_b200.train.executor import TorchExecutor
@@ -51,7 +62,7 @@ def test_trajectory_matches_torch_executor(cuts):
         r = _no_dropout_torch(VGG16_CIFAR10(bounds[i], bounds[i + 1]))
         r.load_state_dict(m.state_dict())
         ref.append(TorchExecutor(r, "VGG16", LEARNING, dev, first, last, recompute=True))
-        nat.append(_no_dropout_native(B200Executor(m, "VGG16", LEARNING, dev, first, last, recompute=True)))
+        nat.append(_no_dropout_native(B200Executor(m, "VGG16", learning, dev, first, last, recompute=True)))
     g = torch.Generator().manual_seed(1)
     losses = []
     for step in range(6):
@@ -70,15 +81,15 @@ def test_trajectory_matches_torch_executor(cuts):
             outs[name] = (h, grads, chain[-1].last_loss())
         losses.append((outs["nat"][2], outs["ref"][2]))
         if step == 0:                       # identical weights only at step 0; later steps drift apart (chaotic net)
-            assert _rel(outs["nat"][0], outs["ref"][0]) < 3e-2, "cut activation"
+            assert _rel(outs["nat"][0], outs["ref"][0]) < tol["act0"], ("cut activation", _rel(outs["nat"][0], outs["ref"][0]))
         else:
-            assert _cos(outs["nat"][0], outs["ref"][0]) > 0.95, f"cut activation step {step}"
+            assert _cos(outs["nat"][0], outs["ref"][0]) > tol["act_cos"], f"cut activation step {step}"
         # bf16 vs fp32 pipelines take different ReLU / max-pool decisions for near-threshold values, so deep
         # gradients are compared by direction, not pointwise (single blocks are checked pointwise in selftest)
         # (a deep random-init net on noise inputs amplifies perturbations ~1.2x per block in both directions)
         if step == 0:
-            assert _cos(outs["nat"][1][0], outs["ref"][1][0]) > 0.5, "cut gradient"
-        assert abs(outs["nat"][2] - outs["ref"][2]) < 0.03 * abs(outs["ref"][2]) + 0.02, losses
+            assert _cos(outs["nat"][1][0], outs["ref"][1][0]) > tol["grad_cos"], ("cut gradient", _cos(outs["nat"][1][0], outs["ref"][1][0]))
+        assert abs(outs["nat"][2] - outs["ref"][2]) < tol["loss_rel"] * abs(outs["ref"][2]) + tol["loss_abs"], losses
     for a, b in zip(nat, ref):
         sa, sb = a.state_dict(), b.state_dict()
         assert list(sa) == list(sb)
@@ -86,9 +97,9 @@ def test_trajectory_matches_torch_executor(cuts):
             if sa[k].dtype == torch.int64:
                 assert int(sa[k]) == int(sb[k]), k          # num_batches_tracked (2x on recomputing stages)
             elif "running" in k:
-                assert _cos(sa[k], sb[k]) > 0.98, k               # drifted weights => slightly different batch statistics
+                assert _cos(sa[k], sb[k]) > tol["w_cos"], k       # drifted weights => slightly different batch statistics
             elif k.endswith("weight") and sa[k].dim() >= 2:
-                assert _cos(sa[k], sb[k]) > 0.98, k           # weights after 6 SGD steps
+                assert _cos(sa[k], sb[k]) > tol["w_cos"], k   # weights after 6 SGD steps
 
 
 def test_linear_stage_backward_pointwise():
@@ -141,8 +152,8 @@ def test_shallow_stage_gradients_match_autograd(rng):
     out_ref.backward(g)
     out = ex.forward_only(0, x)
     gin = ex.backward(0, g)
-    assert _l2(out, out_ref) < 1e-2
-    assert _cos(gin, xr.grad) > 0.99 and _l2(gin, xr.grad) < 0.12, (_cos(gin, xr.grad), _l2(gin, xr.grad))
+    assert _l2(out, out_ref) < 3e-3
+    assert _cos(gin, xr.grad) > 0.995 and _l2(gin, xr.grad) < 0.1, (_cos(gin, xr.grad), _l2(gin, xr.grad))
     convs_under_bn = {f"layer{blk.conv}.bias" for blk in ex.blocks if getattr(blk, "conv", None) and blk.bn}
     for name, prm in ref.named_parameters():
         if name in convs_under_bn:                       # analytically zero gradient (autograd returns fp32 noise)
@@ -404,3 +415,60 @@ def test_public_api_device_fedavg_resident_params(tmp_path, monkeypatch):
         assert a.rounds_done == 2
     sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
     assert len(sd) == 97 and int(sd["layer9.num_batches_tracked"]) == 10     # 5 microbatches per replica per round, averaged
+
+
+def test_clip_grad_norm_native_matches_torch():
+    """``clip-grad-norm`` (other/Vanilla_SL/src/Scheduler.py:204-205) on the native executor: global-norm clipping of the flat
+    gradient + SGD == torch.nn.utils.clip_grad_norm_ + torch.optim.SGD on the reference-math module."""
+    from split_learning_b200.models import VGG16_CIFAR10
+    from split_learning_b200.train.b200_executor import B200Executor
+    dev = torch.device("cuda:0")
+    torch.manual_seed(8)
+    m = VGG16_CIFAR10(44, 52)
+    ref = _no_dropout_torch(VGG16_CIFAR10(44, 52)).to(dev).train()
+    ref.load_state_dict(m.state_dict())
+    learning = dict(LEARNING, **{"learning-rate": 0.1, "momentum": 0.5, "clip-grad-norm": 0.05})
+    ex = _no_dropout_native(B200Executor(m, "VGG16", learning, dev, False, True))
+    assert ex.clip == 0.05
+    opt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.5)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for step in range(3):
+        x = torch.randn(32, 512, 1, 1, device=dev, generator=g)
+        y = torch.randint(0, 10, (32,), device=dev, generator=g)
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(ref(x), y)
+        loss.backward()
+        total = float(torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05))
+        assert total > 0.05, "the test must exercise an active clip"
+        opt.step()
+        ex.forward_backward_last(x, y)
+    sd = ex.state_dict()
+    for name, prm in ref.named_parameters():
+        assert _rel(sd[name], prm.data) < 2e-5, (name, _rel(sd[name], prm.data))
+
+
+def test_public_api_device_plane_trailing_partial_batch(tmp_path, monkeypatch):
+    """num-sample not a multiple of the batch size: the trailing partial microbatch runs through its own program set on
+    the same mailboxes (not dropped), so batch counts — the FedAvg weights — equal the reference's."""
+    import yaml
+    monkeypatch.setenv("SLB200_WAIT_SPINS", str(1 << 23))
+    from split_learning_b200.checkpoint import load_checkpoint
+    from split_learning_b200.config import normalize
+    from split_learning_b200.parallel.device_client import DeviceRpcClient
+    from split_learning_b200.runner import run_inproc
+    raw = yaml.safe_load(open("config.yaml"))
+    raw["server"].update({"clients": [1, 1], "global-round": 2, "validation": False})
+    raw["server"]["data-distribution"]["num-sample"] = 80            # 2 full microbatches of 32 + one of 16
+    raw["server"]["manual"]["no-cluster"]["cut-layers"] = [7]
+    raw["log_path"] = str(tmp_path)
+    raw["learning"].update({"batch-size": 32, "control-count": 3, "learning-rate": 0.01})
+    raw["b200"] = {"synthetic-data": True, "data-plane": "device", "watchdog-seconds": 120}
+    srv = run_inproc(normalize(raw), devices=["cuda:0"], workdir=str(tmp_path), timeout=600)
+    assert [h["ok"] for h in srv.history] == [True, True]
+    cl = srv.clients_objs
+    assert all(isinstance(c, DeviceRpcClient) and c.dstage is not None for c in cl)
+    assert all(len(c._tail_stages) == 1 for c in cl), "both stages must have run the 16-sample program set"
+    sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    assert int(sd["layer9.num_batches_tracked"]) == 2 * 3                 # 3 microbatches per round on the last stage
+    assert int(sd["layer2.num_batches_tracked"]) == 2 * 6                 # forward + recompute on the first stage
+    assert all(torch.isfinite(v.float()).all() for v in sd.values())
