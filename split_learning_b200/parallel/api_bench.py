@@ -41,7 +41,8 @@ def api_config(n_chains: int, steps: int, batch: int, depth: int, cut, precision
         "log_path": workdir, "debug_mode": False,
         "learning": {"learning-rate": 0.0005, "weight-decay": 0.01, "momentum": 0.5, "batch-size": batch, "control-count": depth,
                      "precision": precision},
-        "b200": {"synthetic-data": True, "data-plane": "device", "port": port, "watchdog-seconds": 180, "precision": precision},
+        "b200": {"synthetic-data": True, "data-plane": "device", "port": port, "watchdog-seconds": 180, "precision": precision,
+                 "profile-host": os.environ.get("SLB200_PROFILE_HOST", "0") == "1"},
     }
     if clusters:
         raw["server"]["manual"].update(clusters["manual"])
@@ -158,10 +159,11 @@ def run_api(args, roles=None, cfg=None) -> dict:
     n_first = cfg.clients[0]
     per_round = []
     for h in hist:
-        images = n_first * K * args.batch
+        images = (h.get("first_stage_microbatches") or n_first * K) * args.batch
         dms = h.get("device_ms")
         per_round.append({"round": h["round"], "ok": h["ok"], "wall_ms": h["seconds"] * 1e3, "device_ms": dms,
                           "overhead_ms": (h["seconds"] * 1e3 - dms) if dms else None, "train_loss": h.get("train_loss"),
+                          "phases_ms": h.get("phases_ms"), "client_timing_ms": h.get("client_timing_ms"),
                           "images_per_s_device": images / (dms / 1e3) if dms else None,
                           "images_per_s_round": images / h["seconds"]})
     steady = per_round[1:] or per_round

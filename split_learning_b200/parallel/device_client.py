@@ -32,6 +32,8 @@ from .pipeline import DeviceStage
 
 class DeviceRpcClient(RpcClient):
     def on_start(self, msg: dict) -> None:
+        t_start = time.perf_counter()
+        self.timing: Dict[str, float] = {}
         self.dstage: Optional[DeviceStage] = None
         super_ready = self.send_to_server
         sent: List[dict] = []
@@ -54,8 +56,23 @@ class DeviceRpcClient(RpcClient):
         except Exception as e:          # topology not supported on the device plane → host plane
             print_with_color(f"[device plane] falling back to host data plane: {e}", "yellow")
             self.dstage = None
+        self.timing["on_start"] = (time.perf_counter() - t_start) * 1e3
         for m in sent:
             self.send_to_server(m)
+
+    def _pinned(self, it: int, x: torch.Tensor, y: torch.Tensor):
+        """Pinned staging slot ``it`` of this client's input pool (allocated once, re-used by every round: all H2D copies of
+        a round have completed when the round's stream synchronize returns)."""
+        if x.is_cuda or (x.is_pinned() and y.is_pinned() and x.dtype == torch.float32 and y.dtype == torch.long):
+            return x, y
+        pool = self.__dict__.setdefault("_pin_pool", {})
+        key = (it, tuple(x.shape))
+        if key not in pool:
+            pool[key] = (torch.empty(x.shape, dtype=torch.float32).pin_memory(), torch.empty(y.shape, dtype=torch.long).pin_memory())
+        px, py = pool[key]
+        px.copy_(x)
+        py.copy_(y)
+        return px, py
 
     # ------------------------------------------------------------------
     def _lanes(self, msg: dict):
@@ -203,32 +220,67 @@ class DeviceRpcClient(RpcClient):
         if self.is_first:
             lane, _, down = lanes[0]
             st = self.dstages[lane]
-            batches, tail = [], None
-            for batch in self.train_loader:
-                x, y = batch if not isinstance(batch, dict) else (batch["input_ids"], batch["labels"])
-                item = (x.float(), torch.as_tensor(y).long()) if x.is_cuda else \
-                    (x.float().pin_memory(), torch.as_tensor(y).long().pin_memory())     # GPU-resident loader: already in HBM
-                if x.shape[0] == B:
-                    batches.append(item)
-                elif 0 < x.shape[0] < B:
-                    tail = item                         # trailing partial microbatch: own program set, same mailboxes
-            n = len(batches)
-            tb = int(tail[0].shape[0]) if tail is not None else 0
+            loader = self.train_loader
+            t_l = time.perf_counter()
+            n_samples = None
+            if getattr(loader, "batch_size", None) == B and not getattr(loader, "drop_last", False) and hasattr(loader, "dataset"):
+                try:
+                    n_samples = len(loader.dataset)
+                except TypeError:
+                    n_samples = None
+            if n_samples is not None:
+                # batch count known up front: announce it, then stream — the loader assembles microbatch i+1 on the host
+                # while the device runs microbatch i (the short trailing batch, if any, comes last)
+                n, tb = n_samples // B, n_samples % B
+                source = loader
+            else:                                                   # opaque iterable: materialise it to learn the counts
+                full, tail = [], None
+                for batch in loader:
+                    x = batch[0] if not isinstance(batch, dict) else batch["input_ids"]
+                    if x.shape[0] == B:
+                        full.append(batch)
+                    elif 0 < x.shape[0] < B:
+                        tail = batch
+                n, tb = len(full), (int((tail[0] if not isinstance(tail, dict) else tail["input_ids"]).shape[0]) if tail is not None else 0)
+                source = full + ([tail] if tail is not None else [])
             self.channel.publish_obj(f"plan_{down}", {"lane": lane, "batches": n, "tail": tb})
-            if tail is not None:
-                batches.append(tail)
+            total = n + (1 if tb else 0)
             stage_of = lambda it: st if it < n else self._tail_stage(lane, tb)
-            it_b = 0
-            for it in range(len(batches)):
+            it = it_b = 0
+            prof = {"loader": 0.0, "stage": 0.0, "fwd": 0.0, "bwd": 0.0} if self.opts.get("profile-host") else None
+            pc = time.perf_counter
+            t_prev = pc()
+            for batch in source:
+                if prof is not None:
+                    prof["loader"] += pc() - t_prev
+                x, y = batch if not isinstance(batch, dict) else (batch["input_ids"], batch["labels"])
+                if it >= total or int(x.shape[0]) != (B if it < n else tb):
+                    raise RuntimeError(f"loader produced microbatch {it} of {int(x.shape[0])} samples; announced {n} x {B} + {tb}")
+                if not x.is_cuda:
+                    x, y = x.float(), torch.as_tensor(y).long()
+                x, y = self._pinned(it, x, y)
+                t0 = pc()
                 if it - it_b >= st.depth:
                     stage_of(it_b).backward(it_b)
                     it_b += 1
-                stage_of(it).stage_input(it, *batches[it])
+                t1 = pc()
+                stage_of(it).stage_input(it, x, y)
+                t2 = pc()
                 stage_of(it).forward(it)
-            while it_b < len(batches):
+                it += 1
+                t_prev = pc()
+                if prof is not None:
+                    prof["bwd"] += t1 - t0
+                    prof["stage"] += t2 - t1
+                    prof["fwd"] += t_prev - t2
+            if it != total:
+                raise RuntimeError(f"loader produced {it} microbatches; announced {total}")
+            while it_b < total:
                 stage_of(it_b).backward(it_b)
                 it_b += 1
-            total = len(batches)
+            self.timing["loader_and_launch"] = (time.perf_counter() - t_l) * 1e3
+            if prof is not None:
+                self.timing.update({f"host_{k}": v * 1e3 for k, v in prof.items()})
         else:
             counts = self._collect_plans(lanes)
             tails = self._tails
@@ -242,6 +294,7 @@ class DeviceRpcClient(RpcClient):
             def stage_of(lane, it):
                 return self.dstages[lane] if it < counts[lane] else self._tail_stage(lane, tails[lane])
             # lanes are interleaved microbatch by microbatch (round-robin over the upstream replicas)
+            t_l = time.perf_counter()
             for it in range(most + (0 if self.is_last else depth)):
                 for lane, _, _ in lanes:
                     n = n_of[lane]
@@ -255,15 +308,22 @@ class DeviceRpcClient(RpcClient):
                         if it < n:
                             stage_of(lane, it).forward(it)
             total = sum(n_of.values())
+            self.timing["launch_downstream"] = (time.perf_counter() - t_l) * 1e3
         ev1.record(self.dstage.stream)
+        t_s = time.perf_counter()
         self.dstage.stream.synchronize()
+        self.timing["final_sync"] = (time.perf_counter() - t_s) * 1e3
         self.last_device_ms = ev0.elapsed_time(ev1)
+        t_c = time.perf_counter()
         self.last_loss = (sum(float(h[0]) for h in loss_log) / len(loss_log)) if loss_log else None
         for st in list(self.dstages.values()) + list(self._tail_stages.values()):
             st.check()
+        self.timing["check"] = (time.perf_counter() - t_c) * 1e3
         if self.is_first:
             self.send_to_server(M.notify(self.client_id, self.layer_id, self.cluster))
+        t_p = time.perf_counter()
         self.trainer._wait_pause()
+        self.timing["wait_pause"] = (time.perf_counter() - t_p) * 1e3
         return (not ex.nan_detected()), total
 
     # ------------------------------------------------------------------ round end
@@ -290,17 +350,22 @@ class DeviceRpcClient(RpcClient):
             self._fa = DeviceFedAvg(ex, me, int(self.cluster or 0), comm)
             self._fa.setup()                                 # one handle exchange; later rounds are device-only
             self._fa_key = key
+        t_f = time.perf_counter()
         done = self._fa.run(float(size), ok=bool(result))
+        self.timing["fedavg"] = (time.perf_counter() - t_f) * 1e3
         mine = sorted(str(cid) for cid, cl, lid in everyone if int(cl) == int(self.cluster or 0) and int(lid) == self.layer_id)
         first_cluster = min(int(cl) for _, cl, _ in everyone)
         leader = bool(mine) and mine[0] == me and int(self.cluster or 0) == first_cluster
         want = leader and send and done and bool(self.start_msg.get("save_parameters", True))
         rnd = int(self.start_msg.get("round", self.rounds_done + 1))
-        extra = dict(resident=True, device_ms=getattr(self, "last_device_ms", None), loss=getattr(self, "last_loss", None))
+        extra = dict(resident=True, device_ms=getattr(self, "last_device_ms", None), loss=getattr(self, "last_loss", None),
+                     timing=dict(self.timing))
         if want and self.start_msg.get("async_checkpoint"):
             # the checkpoint copy leaves the round's critical path: snapshot on the device now (the next round may already
             # be training when the bytes cross PCIe), UPDATE without a payload, CHECKPOINT from a background thread
+            t_s = time.perf_counter()
             snap = {k: v.detach().clone() for k, v in ex.state_dict().items()}
+            extra["timing"]["snapshot"] = (time.perf_counter() - t_s) * 1e3
             self.send_to_server(M.update(self.client_id, self.layer_id, bool(result) and done, size, self.cluster, None,
                                          checkpoint_follows=rnd, **extra))
             self._ship_checkpoint(snap, rnd)

@@ -265,8 +265,14 @@ class Server:
     # ------------------------------------------------------------ rounds
     def begin_round(self) -> None:
         self._round_t0 = time.monotonic()
+        self._phase = {}
         self.logger.log_info(f"Start training round {self.global_round - self.round + 1}")
         self.notify_clients(start=True)
+        self._mark("start_sent")
+
+    def _mark(self, name: str) -> None:
+        """Milliseconds since the round began at which a protocol phase completed (round-overhead accounting)."""
+        self.__dict__.setdefault("_phase", {})[name] = (time.monotonic() - self._round_t0) * 1e3
 
     def stage_parameters_for(self, c: ClientInfo, layers: List[int]):
         """Resume path (src/Server.py:230-254): slice the full checkpoint for this stage."""
@@ -332,6 +338,7 @@ class Server:
             for c in self.clients:
                 if c.train:
                     self.send_to_response(c.client_id, M.syn())
+            self._mark("syn_sent")
 
     # -------------------------------------------------------------- NOTIFY
     def on_notify(self, message: dict) -> None:
@@ -345,6 +352,7 @@ class Server:
             for c in self.clients:
                 if c.train and c.cluster == cluster:
                     self.send_to_response(c.client_id, self.pause_payload(c))
+            self._mark("pause_sent")
 
     def pause_payload(self, c: ClientInfo) -> dict:
         return M.pause()
@@ -364,8 +372,14 @@ class Server:
             self.__dict__.setdefault("_ckpt_pending", set()).add(int(message["checkpoint_follows"]))
         if message.get("device_ms") is not None:
             self._device_ms = getattr(self, "_device_ms", []) + [float(message["device_ms"])]
+        if layer_id == 1:
+            self._first_mb = self.__dict__.get("_first_mb", 0) + int(message.get("size") or 0)
         if message.get("loss") is not None:
             self._losses = getattr(self, "_losses", []) + [float(message["loss"])]
+        if message.get("timing"):
+            acc = self.__dict__.setdefault("_client_timing", {})
+            for k, v in message["timing"].items():
+                acc[k] = max(acc.get(k, 0.0), float(v))
         if self.save_parameters and self.round_result and sd is not None:
             if has_nan(sd):
                 self.round_result = False
@@ -390,6 +404,13 @@ class Server:
         if getattr(self, "_losses", None):
             metrics["train_loss"] = sum(self._losses) / len(self._losses)
         self._device_ms, self._losses = [], []
+        metrics["first_stage_microbatches"] = self.__dict__.get("_first_mb", 0)       # the round's training volume
+        self._first_mb = 0
+        self._mark("updates_in")
+        metrics["phases_ms"] = dict(self._phase)
+        if self.__dict__.get("_client_timing"):
+            metrics["client_timing_ms"] = dict(self._client_timing)       # max over clients, per client-side phase
+            self._client_timing = {}
         if self.save_parameters and self.round_result:
             for k in range(len(self.topology.clusters)):
                 self.avg_all_parameters(k)

@@ -28,7 +28,16 @@ class Channel:
     # bytes and a *restricted* unpickler, so bytes arriving on a queue can never execute code (see transport/codec.py)
     def publish_obj(self, routing_key: str, obj) -> None:
         from . import codec
-        self.basic_publish(routing_key, codec.dumps(obj))
+        segs = codec.dump_segments(obj)
+        if len(segs) == 1:
+            self.basic_publish(routing_key, segs[0])
+        else:
+            self.basic_publish_segments(routing_key, segs)
+
+    def basic_publish_segments(self, routing_key: str, segments) -> None:
+        """One message whose body is the concatenation of ``segments`` (bytes-like); socket channels send them without
+        joining."""
+        self.basic_publish(routing_key, b"".join(segments))
 
     def get_obj(self, queue: str, timeout: float = 0.0):
         from . import codec
@@ -137,7 +146,7 @@ def _recv_exact(sock: socket.socket, n: int) -> bytes:
         if r == 0:
             raise ConnectionError("peer closed")
         got += r
-    return bytes(buf)
+    return bytes(buf) if n < (1 << 20) else buf          # large bodies stay in the (writable) receive buffer: no second copy
 
 
 def _send_request(sock: socket.socket, op: int, queue: str, arg: bytes = b"") -> None:
@@ -283,7 +292,15 @@ class TcpChannel(Channel):
         self._call(OP_DECLARE, queue)
 
     def basic_publish(self, routing_key, body, exchange=""):
-        self._call(OP_PUB, routing_key, bytes(body), reply=False)
+        self._call(OP_PUB, routing_key, body if isinstance(body, (bytes, bytearray, memoryview)) else bytes(body), reply=False)
+
+    def basic_publish_segments(self, routing_key, segments):
+        q = routing_key.encode()
+        total = sum(memoryview(s).nbytes for s in segments)
+        with self._lock:
+            self._sock.sendall(_REQ.pack(OP_PUB, len(q), total) + q)
+            for seg in segments:                          # sendall releases the GIL; tensor memory is never joined / copied
+                self._sock.sendall(seg)
 
     def basic_get(self, queue, timeout=0.0):
         status, body = self._call(OP_GET, queue, struct.pack("<d", float(timeout)))

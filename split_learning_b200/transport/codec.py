@@ -28,7 +28,14 @@ class UnsafePayload(pickle.UnpicklingError):
     pass
 
 
-def _rebuild_tensor(raw: np.ndarray, dtype: str, shape) -> torch.Tensor:
+def _rebuild_tensor(raw, dtype: str, shape) -> torch.Tensor:
+    if 0 in tuple(shape):
+        return torch.empty(tuple(shape), dtype=getattr(torch, dtype))
+    if not isinstance(raw, np.ndarray):                  # out-of-band buffer: a view of the receive buffer (zero copy)
+        mv = memoryview(raw)
+        raw = np.frombuffer(mv, dtype=np.uint8) if not mv.readonly else np.frombuffer(mv, dtype=np.uint8).copy()
+    elif not raw.flags.writeable:                        # small in-band array rebuilt from immutable bytes
+        raw = raw.copy()
     t = torch.from_numpy(np.ascontiguousarray(raw)).view(getattr(torch, dtype))
     return t.view(tuple(shape))
 
@@ -49,6 +56,55 @@ def dumps(obj: Any) -> bytes:
     buf = io.BytesIO()
     _Pickler(buf, protocol=pickle.HIGHEST_PROTOCOL).dump(obj)
     return buf.getvalue()
+
+
+# Large payloads (state-dicts: 134 MB for VGG16) travel as *segments*: a small pickle plus the tensors' memory as
+# out-of-band buffers (pickle protocol 5).  The sender hands the segments to ``socket.sendall`` one by one and the receiver
+# rebuilds tensors as views of the receive buffer — no byte of tensor data is copied while holding the GIL, so a checkpoint
+# upload running in a background thread does not stall the threads that are launching the next round's kernels.
+_MAGIC = b"SLB5"
+_SEG_MIN = 1 << 16           # tensors smaller than this stay in-band
+
+
+class _OobPickler(_Pickler):
+    def reducer_override(self, obj):
+        r = super().reducer_override(obj)
+        if r is not NotImplemented:
+            fn, (raw, dtype, shape) = r
+            # small tensors stay in-band as bytes (an ndarray would also be sent out of band under protocol 5)
+            return fn, (pickle.PickleBuffer(raw) if raw.nbytes >= _SEG_MIN else raw.tobytes(), dtype, shape)
+        return r
+
+
+def dump_segments(obj: Any) -> list:
+    """[bytes-like, ...] whose concatenation ``loads`` understands; one element (a plain pickle) when nothing is large."""
+    import struct
+    buf = io.BytesIO()
+    oob: list = []
+    _OobPickler(buf, protocol=5, buffer_callback=oob.append).dump(obj)
+    if not oob:
+        return [buf.getvalue()]
+    views = [b.raw() for b in oob]
+    pick = buf.getvalue()
+    head = _MAGIC + struct.pack(f"<IQ{len(views)}Q", len(views), len(pick), *[v.nbytes for v in views])
+    return [head + pick] + views
+
+
+def _loads_segments(data, unpickler) -> Any:
+    import struct
+    mv = memoryview(data)
+    n, plen = struct.unpack_from("<IQ", mv, 4)
+    lens = struct.unpack_from(f"<{n}Q", mv, 16)
+    off = 16 + 8 * n
+    pick = mv[off: off + plen]
+    off += plen
+    bufs = []
+    for ln in lens:
+        bufs.append(mv[off: off + ln])
+        off += ln
+    if off != len(mv):
+        raise UnsafePayload("segmented payload: lengths do not add up")
+    return unpickler(io.BytesIO(pick), buffers=bufs).load()
 
 
 _NUMPY_MODS = ("numpy.core.multiarray", "numpy._core.multiarray", "numpy.core.numeric", "numpy._core.numeric", "numpy")
@@ -89,7 +145,9 @@ class _Unpickler(pickle.Unpickler):
         return c
 
 
-def loads(data: bytes) -> Any:
+def loads(data) -> Any:
+    if bytes(data[:4]) == _MAGIC:
+        return _loads_segments(data, _Unpickler)
     return _Unpickler(io.BytesIO(data)).load()
 
 
@@ -112,5 +170,7 @@ class _IpcUnpickler(_Unpickler):
     extra = staticmethod(_cuda_ipc_class)
 
 
-def loads_cuda_ipc(data: bytes) -> Any:
+def loads_cuda_ipc(data) -> Any:
+    if bytes(data[:4]) == _MAGIC:
+        return _loads_segments(data, _IpcUnpickler)
     return _IpcUnpickler(io.BytesIO(data)).load()
