@@ -62,14 +62,25 @@ class RpcClient:
         def beat():
             while not self._hb_stop.wait(self.heartbeat):
                 try:
-                    ch.publish_obj(M.RPC_QUEUE, M.heartbeat(self.client_id))
+                    ch.publish_obj(M.RPC_QUEUE, M.heartbeat(self.client_id, progress=self.progress()))
                 except Exception:
                     return
         self._hb_thread = threading.Thread(target=beat, daemon=True, name=f"slb200-heartbeat-{self.client_id}")
         self._hb_thread.start()
 
+    def progress(self) -> int:
+        """Monotonic count of work done by this client: control messages handled + microbatches trained."""
+        t = self.trainer
+        return int(self.__dict__.get("_handled", 0)) + (int(getattr(t, "data_count", 0)) if t is not None else 0)
+
     def stop_heartbeat(self) -> None:
+        """Also joins the beacon thread: a daemon thread that is still alive when the interpreter finalises is killed with
+        ``pthread_exit`` inside whatever native frame it sits in (observed: ``terminate called without an active
+        exception`` + SIGABRT at client exit)."""
         self._hb_stop.set()
+        t = self._hb_thread
+        if t is not None and t is not threading.current_thread():
+            t.join(5.0)
 
     # ------------------------------------------------------------------
     def send_to_server(self, message) -> None:
@@ -80,6 +91,12 @@ class RpcClient:
         self.start_heartbeat()
 
     def wait_response(self, idle_timeout: Optional[float] = None) -> None:
+        try:
+            self._serve(idle_timeout)
+        finally:
+            self.stop_heartbeat()
+
+    def _serve(self, idle_timeout: Optional[float]) -> None:
         last = time.monotonic()
         # the server relays a heartbeat every few seconds: its silence for a watchdog period means it is gone
         limit = idle_timeout if idle_timeout is not None else (max(self.watchdog, 3 * self.heartbeat) if self.heartbeat > 0
@@ -94,12 +111,12 @@ class RpcClient:
             if m.get("action") == M.HEARTBEAT:          # the server (and through it every peer) is alive
                 continue
             if not self.response_message(m):
-                self.stop_heartbeat()
                 return
 
     # ------------------------------------------------------------------
     def response_message(self, msg: dict) -> bool:
         self.response = msg
+        self._handled = self.__dict__.get("_handled", 0) + 1
         action = msg["action"]
         print_with_color(f"[<<<] Client received: {msg.get('message')}", "blue")
         if action == M.START:

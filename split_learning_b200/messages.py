@@ -10,6 +10,7 @@ from __future__ import annotations
 from typing import Any, Dict, List, Optional
 
 RPC_QUEUE = "rpc_queue"
+CKPT_QUEUE = "rpc_queue_ckpt"      # CHECKPOINT bodies (a stage state-dict, up to 134 MB) must not sit in front of a NOTIFY
 
 REGISTER, START, SYN, NOTIFY, PAUSE, UPDATE, STOP, READY, HEARTBEAT, CHECKPOINT = (
     "REGISTER", "START", "SYN", "NOTIFY", "PAUSE", "UPDATE", "STOP", "READY", "HEARTBEAT", "CHECKPOINT")
@@ -61,12 +62,15 @@ def stop(message: str = "Stop training!") -> Dict[str, Any]:
     return {"action": STOP, "message": message, "parameters": None}
 
 
-def heartbeat(client_id=None) -> Dict[str, Any]:
+def heartbeat(client_id=None, progress=None) -> Dict[str, Any]:
     """Liveness beacon (no counterpart in the reference, where a dead peer is a silent deadlock): clients publish it to
     ``rpc_queue`` every few seconds, the server relays one to every ``reply_{id}``.  Receivers only refresh their idle
-    timers — waits are bounded by *silence of the peer*, not by how long a healthy round takes."""
+    timers — waits are bounded by *silence of the peer*, not by how long a healthy round takes.  ``progress``: a counter of
+    work done (messages handled + microbatches trained); the server relays the sum over all clients, and a blocked client
+    keeps waiting only while that sum moves — a peer that still beacons but no longer trains (hung, or alive-but-deaf) is a
+    dead-lock like any other and ends in the watchdog."""
     import time
-    return {"action": HEARTBEAT, "client_id": client_id, "message": "alive", "t": time.time()}
+    return {"action": HEARTBEAT, "client_id": client_id, "message": "alive", "t": time.time(), "progress": progress}
 
 
 def checkpoint(client_id, layer_id: int, cluster, round_no: int, parameters) -> Dict[str, Any]:

@@ -617,59 +617,83 @@ __global__ void __launch_bounds__(128) conv3x3_small_fwd_kernel(const float* __r
   }
 }
 
-// dw[Cout][9*CIN] += sum_pix dy[pix][Cout] * patch[pix][9*CIN].  A block walks several 128-pixel chunks and keeps its
-// partial sums in registers, so the global reds are per block, not per chunk.
+// dw[Cout][9*CIN] += sum_pix dy[pix][Cout] * patch[pix][9*CIN]  (first conv of the network: CIN = 3 or 1, Cout <= 64).
+// A [Cout x KK] x [pix] GEMM with K = all pixels.  Per 128-pixel chunk the block stages the im2col patch [128][KP] and dy
+// [128][Cout] in shared memory; thread (slice, cg, kg) owns a 4 (channels) x KG (taps) register tile and walks the pixels
+// of its slice: one LDS.128 of dy + KG scalar patch loads feed 4*KG FMAs (the previous one-output-per-thread version
+// issued two shared loads per FMA and ran at the LDS limit: 140 us for conv1 of VGG16 at batch 32).  Partial tiles of
+// the pixel slices are combined with shared-memory atomics, then one global red per output and block.
 template <int CIN, typename T>
 __global__ void __launch_bounds__(256) conv3x3_small_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                                  float* dw, int B, int H, int W, int Cout) {
   pdl_trigger();
   pdl_wait();
   constexpr int KK = 9 * CIN;
-  constexpr int MAXO = 8;                         // outputs per thread: Cout*KK <= 256*8
-  extern __shared__ float s_buf[];               // patch[128][KK] + dy[128][Cout]
+  constexpr int KG = (KK + 3) / 4;                // taps per thread (4 tap groups)
+  constexpr int KP = 4 * KG;                      // padded patch row
+  extern __shared__ float s_buf[];                // patch[128][KP] | dy[128][Cout] | out[Cout][KP]
   float* s_patch = s_buf;
-  float* s_dy = s_buf + 128 * KK;
-  const long long P = (long long)B * H * W;
-  const int n_out = Cout * KK;
-  float acc[MAXO];
+  float* s_dy = s_buf + 128 * KP;
+  float* s_out = s_dy + 128 * Cout;
+  const int P = B * H * W;
+  const int HW = H * W;
+  const int n_cg = Cout / 4;                      // channel groups of 4
+  const int lanes = n_cg * 4;                     // threads that cover every output once
+  const int slices = 256 / lanes;                 // pixel slices processed in parallel (Cout = 64 -> 4)
+  const int slice = threadIdx.x / lanes, within = threadIdx.x % lanes;
+  const int cg = within >> 2, kg = within & 3;
+  const bool active = slice < slices;
+  float acc[4][KG];
 #pragma unroll
-  for (int j = 0; j < MAXO; ++j) acc[j] = 0.f;
-  for (long long pix0 = blockIdx.x * 128LL; pix0 < P; pix0 += (long long)gridDim.x * 128) {
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int j = 0; j < KG; ++j) acc[a][j] = 0.f;
+  for (int i = threadIdx.x; i < Cout * KP; i += blockDim.x) s_out[i] = 0.f;
+  for (int pix0 = blockIdx.x * 128; pix0 < P; pix0 += gridDim.x * 128) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 128 * KK; i += blockDim.x) {
-      const int lp = i / KK, k = i - lp * KK;
-      const long long pix = pix0 + lp;
+    for (int i = threadIdx.x; i < 128 * KP; i += blockDim.x) {
+      const int lp = i / KP, k = i - lp * KP;
+      const int pix = pix0 + lp;
       float v = 0.f;
-      if (pix < P) {
+      if (pix < P && k < KK) {
         const int t = k / CIN, c = k - t * CIN;
-        const int ww = static_cast<int>(pix % W), hh = static_cast<int>((pix / W) % H);
-        const long long b = pix / ((long long)W * H);
+        const int b = pix / HW, r = pix - b * HW;
+        const int hh = r / W, ww = r - hh * W;
         const int ih = hh + t / 3 - 1, iw = ww + t % 3 - 1;
         if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[((b * CIN + c) * H + ih) * W + iw];
       }
       s_patch[i] = v;
     }
     for (int i = threadIdx.x; i < 128 * Cout; i += blockDim.x) {
-      const long long pix = pix0 + i / Cout;
-      s_dy[i] = pix < P ? to_f32(dy[pix * Cout + (i % Cout)]) : 0.f;
+      const int pix = pix0 + i / Cout;
+      s_dy[i] = pix < P ? to_f32(dy[(long long)pix * Cout + (i % Cout)]) : 0.f;
     }
     __syncthreads();
+    if (active) {
+      for (int lp = slice; lp < 128; lp += slices) {
+        const float4 d = *reinterpret_cast<const float4*>(s_dy + lp * Cout + cg * 4);
+        const float* pr = s_patch + lp * KP + kg * KG;
 #pragma unroll
-    for (int j = 0; j < MAXO; ++j) {
-      const int o = threadIdx.x + j * 256;
-      if (o < n_out) {
-        const int co = o / KK, k = o - co * KK;
-        float a = acc[j];
-#pragma unroll 8
-        for (int lp = 0; lp < 128; ++lp) a = fmaf(s_dy[lp * Cout + co], s_patch[lp * KK + k], a);
-        acc[j] = a;
+        for (int j = 0; j < KG; ++j) {
+          const float pv = pr[j];
+          acc[0][j] = fmaf(d.x, pv, acc[0][j]);
+          acc[1][j] = fmaf(d.y, pv, acc[1][j]);
+          acc[2][j] = fmaf(d.z, pv, acc[2][j]);
+          acc[3][j] = fmaf(d.w, pv, acc[3][j]);
+        }
       }
     }
   }
+  if (active) {
 #pragma unroll
-  for (int j = 0; j < MAXO; ++j) {
-    const int o = threadIdx.x + j * 256;
-    if (o < n_out) atomicAdd(dw + o, acc[j]);
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int j = 0; j < KG; ++j) atomicAdd(s_out + (cg * 4 + a) * KP + kg * KG + j, acc[a][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout * KP; i += blockDim.x) {
+    const int co = i / KP, k = i - co * KP;
+    if (k < KK) atomicAdd(dw + co * KK + k, s_out[i]);
   }
 }
 
@@ -1344,10 +1368,11 @@ int slb_conv3x3_small_fwd(const float* x, const float* w, const float* bias, voi
 }  // extern "C"
 template <typename T>
 static int small_wgrad_t(const float* x, const void* dy, float* dw, int B, int Cin, int H, int W, int Cout, cudaStream_t st) {
-  if (Cout * 9 * Cin > 2048) return -3;
-  const size_t smem = (size_t)(128 * 9 * Cin + 128 * Cout) * sizeof(float);
+  if (Cout % 4 || Cout > 64 || (long long)B * H * W > (1LL << 30)) return -3;
+  const int kp = 4 * ((9 * Cin + 3) / 4);
+  const size_t smem = (size_t)(128 * kp + 128 * Cout + Cout * kp) * sizeof(float);
   const long long chunks = ((long long)B * H * W + 127) / 128;
-  const int grid = static_cast<int>(chunks < 296 ? chunks : 296);   // 2+ CTAs per SM: the staging phases of one hide behind the FMAs of the other
+  const int grid = static_cast<int>(chunks < 296 ? chunks : 296);   // 2 CTAs per SM: the staging phase of one hides behind the FMAs of the other
   const T* d = reinterpret_cast<const T*>(dy);
   if (Cin == 3) {
     static bool done3 = false;

@@ -48,7 +48,7 @@ def preload(device=None) -> None:
         return
     with torch.cuda.device(d):
         bad = (lib().slb_preload_gemm() + lib().slb_preload_fused() + lib().slb_preload_elementwise()
-               + lib().slb_preload_transformer() + lib().slb_preload_allreduce())
+               + lib().slb_preload_transformer() + lib().slb_preload_allreduce() + lib().slb_preload_ticket())
     if bad:
         raise NativeError(f"{bad} kernels failed to load (wrong GPU architecture? this library is sm_100a only)")
     _preloaded.add(d)
@@ -443,6 +443,25 @@ def set_flag(flag_ptr: int, value: int = 0, seq=None, hint_ptr: int = 0):
 
 def counter_inc(ctr):
     _check(lib().slb_counter_inc(_p(ctr), _stream()), "counter_inc")
+
+
+def store_u32(ptr: int, value: int):
+    """Stream-ordered ``*ptr = value`` (sets the sequence counter a following graph replay publishes from)."""
+    _check(lib().slb_store_u32(c_void_p(ptr), c_uint32(value), _stream()), "store_u32")
+
+
+def ticket_ring_bytes(entries: int) -> int:
+    return int(lib().slb_ticket_ring_bytes(c_int(entries)))
+
+
+def ticket_publish(ring_ptr: int, entries: int, origin: int, it: int, gseq_ctr, batch: int):
+    _check(lib().slb_ticket_publish(c_void_p(ring_ptr), c_int(entries), c_uint32(origin), c_uint32(it), _p(gseq_ctr),
+                                    c_uint32(batch), _stream()), "ticket_publish")
+
+
+def ticket_claim(ring_ptr: int, entries: int, total: int, max_spins: int, out_host_ptr: int):
+    _check(lib().slb_ticket_claim(c_void_p(ring_ptr), c_int(entries), c_uint32(total), c_uint64(max_spins),
+                                  c_void_p(out_host_ptr), _stream()), "ticket_claim")
 
 
 def memcpy_async(dst_ptr: int, src_ptr: int, nbytes: int):

@@ -144,6 +144,10 @@ def run_api(args, roles=None, cfg=None) -> dict:
     for t in threads:
         t.join(args.timeout)
     wall = time.perf_counter() - t0
+    for cli in clients:                      # background checkpoint uploads of the last round: finish before the broker goes
+        th = cli.__dict__.get("_ckpt_thread")
+        if th is not None:
+            th.join(60.0)
     ok = not errors and not any(t.is_alive() for t in threads)
     flag = torch.tensor([float(ok)], device=dev)
     if dist is not None:
@@ -169,8 +173,10 @@ def run_api(args, roles=None, cfg=None) -> dict:
     steady = per_round[1:] or per_round
     best = min(steady, key=lambda r: r["wall_ms"])
     ckpt = os.path.exists(os.path.join(workdir, "VGG16_CIFAR10.pth"))
+    from ..checkpoint import load_meta
+    ckpt_round = load_meta(os.path.join(workdir, "VGG16_CIFAR10.pth")).get("round") if ckpt else None
     return {"scenario": name, "cut_layers": cfg.cluster_cut_layers if cfg.cluster_mode else cfg.no_cluster_cut_layers,
             "non_iid_rate": cfg.non_iid_rate, "path": "native broker daemon + Server + DeviceRpcClient FSMs (REGISTER/START/READY/SYN/NOTIFY/PAUSE/UPDATE), device data plane",
             "clients": list(cfg.clients), "microbatches_per_client_per_round": K, "rounds": per_round, "steady_round": best,
-            "checkpoint_written": ckpt, "total_wall_s": wall,
+            "checkpoint_written": ckpt, "checkpoint_round": ckpt_round, "total_wall_s": wall,
             "h2d_bytes_per_step": n_first * (args.batch * 3 * 32 * 32 * 4 + args.batch * 8), "d2h_bytes_per_step": n_first * 16}

@@ -12,6 +12,13 @@ with the downstream stage multiplexing its lanes on one executor (fan-in).  If a
 divide its predecessor, or the stage has no native plan, the client keeps the host data plane —
 a *topology* fallback (logged), never a kernel fallback.
 
+Competing consumers (``b200.dynamic-consumers: true``, or automatically when the last stage does not divide its
+predecessor, e.g. clients [4, 3]): the edge into the last stage becomes a *ticket ring* (``parallel/ticket.py``).  Producers
+keep each microbatch in their own outbox and append a ticket; every last-stage replica claims the next ticket whenever it
+has fewer than ``b200.claim-ahead`` programs in flight, copies the payload in over NVLink and returns the gradient to the
+ticket's origin — the reference's shared ``intermediate_queue`` + ``trace`` routing (src/train/VGG16.py:40-53,143-154)
+without a broker hop, and a slow replica simply claims fewer tickets.
+
 A trailing partial batch of the loader (``num-sample`` not a multiple of the batch size) is not dropped: it runs
 through a second program set compiled for its size on the *same* mailboxes (prefix views of the slots, shared sequence
 counters), so microbatch counts — the FedAvg weights, src/train/VGG16.py:109 — match the reference's.
@@ -49,6 +56,9 @@ class DeviceRpcClient(RpcClient):
                 self.dstage = self.dstages[self._lane_info[0][0]]
                 for st in self.dstages.values():
                     st._posted = {"F": 0, "B": 0, "L": 0}
+                ring = getattr(self, "_ring", None)
+                if ring is not None and ring.base is not None:
+                    ring.reset()                             # I own the edge's ticket ring: a fresh queue for this round
             else:
                 self._wired_key = None
                 self._wire(msg)
@@ -83,16 +93,27 @@ class DeviceRpcClient(RpcClient):
         members: Dict[int, list] = msg["peers"]["members"]
         ids = {s: [cid for cid, _ in members[s]] for s in members}
         n = {s: len(ids[s]) for s in ids}
-        for s in range(2, self.num_layers + 1):
+        L = self.num_layers
+        # the edge into the last stage is dynamic (ticket ring) on request, or when static lanes cannot cover it
+        self._dynamic = L >= 2 and n.get(L, 0) > 0 and (bool(self.opts.get("dynamic-consumers", False)) or n[L - 1] % n[L] != 0)
+        for s in range(2, L + 1):
+            if s == L and self._dynamic:
+                continue
             if n[s] == 0 or n[s - 1] % n[s] != 0:
                 raise RuntimeError(f"replica counts {[n[k] for k in sorted(n)]}: stage {s} does not divide stage {s - 1}")
+        self._stage_ids = ids
         me = ids[self.layer_id].index(str(self.client_id))
         lanes = []
         for lane in range(n[1]):
+            if self._dynamic and self.layer_id == L:         # a competing consumer serves whichever lane it claims
+                lanes.append((lane, ids[L - 1][lane % n[L - 1]], None))
+                continue
             if lane % n[self.layer_id] != me:
                 continue
             up = ids[self.layer_id - 1][lane % n[self.layer_id - 1]] if self.layer_id > 1 else None
             down = ids[self.layer_id + 1][lane % n[self.layer_id + 1]] if self.layer_id < self.num_layers else None
+            if self._dynamic and self.layer_id == L - 1:
+                down = None                                  # no fixed partner: the outbox + ticket ring take its place
             lanes.append((lane, up, down))
         return lanes
 
@@ -121,22 +142,53 @@ class DeviceRpcClient(RpcClient):
             mb, hdl = cache[key]
             mb.base[spec.flags_off: spec.flags_off + 4 * spec.depth].zero_()      # fresh sequence numbers for fresh stages
             return mb, hdl
+        L = self.num_layers
+        dyn_consumer = self._dynamic and self.layer_id == L
+        dyn_producer = self._dynamic and self.layer_id == L - 1
+        consumers = self._stage_ids[L] if self._dynamic else []
+        fwd_out: Dict[int, Mailbox] = {}
+        grad_out: Dict[int, Mailbox] = {}
+        self._outboxes: Dict[int, Mailbox] = {}
+        self._ring = None
+        need = 0
         for lane, up, down in lanes:
-            if up is not None:                                     # I consume this lane's activations
+            if dyn_consumer:                                       # local inbox: filled by my own copy-in from the origin's outbox
+                c, h, w = ex.in_shape
+                fwd_in[lane], _ = own("inbox", lane, MailboxSpec(depth, B, (B, h, w, c), itemsize=isz))
+                need += 2                                          # the origin's outbox + its gradient mailbox
+            elif up is not None:                                   # I consume this lane's activations
                 c, h, w = ex.in_shape
                 spec_in = MailboxSpec(depth, B, (B, h, w, c), itemsize=isz)
                 fwd_in[lane], hdl = own("act", lane, spec_in)
                 self.channel.publish_obj(f"ipc_{up}", {"kind": "act", "lane": lane, "handle": hdl,
                                                        "shape": spec_in.payload_shape})
-            if down is not None:                                   # I consume the gradients of this lane's output
+                need += 1
+            if dyn_producer:                                       # outbox + gradient mailbox, offered to every consumer
+                c, h, w = ex.out_shape
+                spec_out = MailboxSpec(depth, B, (B, h, w, c), itemsize=isz)
+                fwd_out[lane], h_out = own("outbox", lane, spec_out)
+                grad_in[lane], h_grad = own("grad", lane, spec_out)
+                for cid in consumers:
+                    self.channel.publish_obj(f"ipc_{cid}", {"kind": "outbox", "lane": lane, "handle": h_out, "shape": spec_out.payload_shape})
+                    self.channel.publish_obj(f"ipc_{cid}", {"kind": "grad", "lane": lane, "handle": h_grad, "shape": spec_out.payload_shape})
+            elif down is not None:                                 # I consume the gradients of this lane's output
                 c, h, w = ex.out_shape
                 spec_out = MailboxSpec(depth, B, (B, h, w, c), itemsize=isz)
                 grad_in[lane], hdl = own("grad", lane, spec_out)
                 self.channel.publish_obj(f"ipc_{down}", {"kind": "grad", "lane": lane, "handle": hdl,
                                                          "shape": spec_out.payload_shape})
-        need = sum(int(up is not None) + int(down is not None) for _, up, down in lanes)
-        fwd_out: Dict[int, Mailbox] = {}
-        grad_out: Dict[int, Mailbox] = {}
+                need += 1
+        if self._dynamic and self.layer_id >= L - 1:
+            from .ticket import TicketRing
+            if dyn_consumer and consumers[0] == str(self.client_id):   # the edge's first consumer hosts the ring
+                if "ring" not in cache:
+                    cache["ring"] = TicketRing.allocate(dev)
+                self._ring = cache["ring"]
+                self._ring.reset()
+                for cid in self._stage_ids[L - 1] + consumers[1:]:
+                    self.channel.publish_obj(f"ipc_{cid}", {"kind": "ring", "handle": self._ring.handle})
+            else:
+                need += 1
         t0 = time.monotonic()
         while need:
             m = self.channel.get_obj(my_q, 0.25)
@@ -144,10 +196,17 @@ class DeviceRpcClient(RpcClient):
                 if time.monotonic() - t0 > self.watchdog:
                     raise TimeoutError("peer never posted its IPC handle")
                 continue
+            if m["kind"] == "ring":
+                from .ticket import TicketRing
+                self._ring = TicketRing.open(m["handle"], dev)
+                need -= 1
+                continue
             spec = MailboxSpec(depth, B, tuple(m["shape"]), itemsize=isz)
             mb = Mailbox.open_peer(spec, m["handle"], dev)
             if m["kind"] == "act":                                 # downstream's activation ring: I produce into it
                 fwd_out[m["lane"]] = mb
+            elif m["kind"] == "outbox":                            # an origin's outbox: I copy claimed microbatches out of it
+                self._outboxes[m["lane"]] = mb
             else:                                                  # upstream's gradient ring
                 grad_out[m["lane"]] = mb
             need -= 1
@@ -159,6 +218,9 @@ class DeviceRpcClient(RpcClient):
             self.dstages[lane] = DeviceStage(ex, B, depth, fwd_in=fwd_in.get(lane), grad_in=grad_in.get(lane),
                                              fwd_out=fwd_out.get(lane), grad_out=grad_out.get(lane),
                                              slot_offset=k * depth if multi else 0, bind_inputs=not multi)
+        if dyn_consumer:
+            from .mailbox import EdgeCounters
+            self._in_seq = {lane: EdgeCounters(depth, dev) for lane, _, _ in lanes}      # copy-in publishes of my inboxes
         self._lane_info = lanes
         self.dstage = self.dstages[lanes[0][0]]
         self._edges = (fwd_in, grad_in, fwd_out, grad_out, multi, depth)
@@ -197,6 +259,69 @@ class DeviceRpcClient(RpcClient):
             self._tails[int(m["lane"])] = int(m.get("tail", 0))
         return counts
 
+    def progress(self) -> int:
+        # while the device loop runs, host counters stand still (the host only enqueues, then blocks in a stream synchronize);
+        # the device-side waits are bounded by their own spin limits, so "busy on the device" counts as moving
+        if self.__dict__.get("_device_busy"):
+            return time.monotonic_ns() // 1_000_000
+        return super().progress() + int(self.__dict__.get("_device_steps", 0))
+
+    def _announce(self, down, lane: int, batches: int, tail: int) -> None:
+        """Batch count of a lane to whoever consumes it: the fixed partner, or every competing consumer."""
+        targets = [down] if down is not None else (self._stage_ids[self.num_layers] if self._dynamic else [])
+        for cid in targets:
+            self.channel.publish_obj(f"plan_{cid}", {"lane": lane, "batches": batches, "tail": tail})
+
+    def _offer(self, st: DeviceStage, lane: int, it: int) -> None:
+        """Producer side of the ticket ring: microbatch ``it`` of ``lane`` sits in my outbox — queue a ticket for it."""
+        if self._dynamic and self.layer_id == self.num_layers - 1:
+            with torch.cuda.stream(st.stream):
+                self._ring.publish(lane, it, st.exp_grad.at(it % st.depth), st.B)
+
+    def _run_competing_consumer(self, lanes, counts, tails, log_loss) -> int:
+        """Last stage behind a ticket ring: claim → copy the origin's outbox slot in → L program → gradient to the origin."""
+        from ..ops import native as N
+        depth = self.dstage.depth
+        total = sum(counts.values()) + sum(1 for l in tails if tails[l])
+        ahead = max(1, int(self.opts.get("claim-ahead", 2)))
+        slow = float((self.opts.get("debug-slow-ms") or {}).get(self.rank, 0.0)) if isinstance(self.opts.get("debug-slow-ms"), dict) else 0.0
+        done: List[torch.cuda.Event] = []
+        mine = 0
+        self.claimed: List[tuple] = []
+        while True:
+            if len(done) >= ahead:
+                done[len(done) - ahead].synchronize()            # a busy replica does not hoard tickets
+            got = self._ring.claim(total, max_spins=self.dstage.wait_spins)
+            if got is None:
+                break
+            _, lane, it, gseq, b = got
+            st = self.dstages[lane] if b == self.dstage.B else self._tail_stage(lane, b)
+            slot = it % depth
+            src, box = self._outboxes[lane], st.fwd_in
+            nbytes = b * self._payload_bytes_per_sample(src)
+            with torch.cuda.stream(st.stream):
+                N.memcpy_async(box.payload[slot].data_ptr(), src.payload[slot].data_ptr(), nbytes)
+                N.memcpy_async(box.labels[slot].data_ptr(), src.labels[slot].data_ptr(), b * 8)
+                N.set_flag(box.flag_ptr(slot), 0, seq=self._in_seq[lane].at(slot))
+                N.store_u32(st.seq_grad.at(slot).data_ptr(), (gseq - 1) & 0xFFFFFFFF)
+                if slow > 0:
+                    torch.cuda._sleep(int(slow * 1.9e6))         # test hook: an artificially slow replica
+            st.last(it)
+            log_loss(st)
+            ev = torch.cuda.Event()
+            ev.record(st.stream)
+            done.append(ev)
+            self.claimed.append((lane, it))
+            mine += 1
+        return mine
+
+    @staticmethod
+    def _payload_bytes_per_sample(mb: Mailbox) -> int:
+        n = mb.spec.itemsize
+        for d in mb.spec.payload_shape[1:]:
+            n *= d
+        return n
+
     def run_stage(self):
         if self.dstage is None:
             return super().run_stage()
@@ -204,7 +329,9 @@ class DeviceRpcClient(RpcClient):
         B = self.dstage.B
         ex = self.executor
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self._device_busy = True
         ev0.record(self.dstage.stream)
+        self.timing["at_run_stage"] = time.monotonic()          # at_*: CLOCK_MONOTONIC stamps (one box: comparable across processes)
         # the reference prints the loss of every microbatch (src/train/VGG16.py:168, a host sync per step); here every step
         # copies it to pinned host memory asynchronously and the round reports the mean
         loss_log: List[torch.Tensor] = []
@@ -243,7 +370,7 @@ class DeviceRpcClient(RpcClient):
                         tail = batch
                 n, tb = len(full), (int((tail[0] if not isinstance(tail, dict) else tail["input_ids"]).shape[0]) if tail is not None else 0)
                 source = full + ([tail] if tail is not None else [])
-            self.channel.publish_obj(f"plan_{down}", {"lane": lane, "batches": n, "tail": tb})
+            self._announce(down, lane, n, tb)
             total = n + (1 if tb else 0)
             stage_of = lambda it: st if it < n else self._tail_stage(lane, tb)
             it = it_b = 0
@@ -267,6 +394,7 @@ class DeviceRpcClient(RpcClient):
                 stage_of(it).stage_input(it, x, y)
                 t2 = pc()
                 stage_of(it).forward(it)
+                self._offer(stage_of(it), lane, it)
                 it += 1
                 t_prev = pc()
                 if prof is not None:
@@ -286,7 +414,7 @@ class DeviceRpcClient(RpcClient):
             tails = self._tails
             if not self.is_last:
                 for lane, _, down in lanes:
-                    self.channel.publish_obj(f"plan_{down}", {"lane": lane, "batches": counts[lane], "tail": tails.get(lane, 0)})
+                    self._announce(down, lane, counts[lane], tails.get(lane, 0))
             depth = self.dstage.depth
             n_of = {lane: counts[lane] + (1 if tails.get(lane, 0) else 0) for lane, _, _ in lanes}
             most = max(n_of.values()) if n_of else 0
@@ -295,7 +423,8 @@ class DeviceRpcClient(RpcClient):
                 return self.dstages[lane] if it < counts[lane] else self._tail_stage(lane, tails[lane])
             # lanes are interleaved microbatch by microbatch (round-robin over the upstream replicas)
             t_l = time.perf_counter()
-            for it in range(most + (0 if self.is_last else depth)):
+            dyn_last = self._dynamic and self.is_last
+            for it in range(0 if dyn_last else most + (0 if self.is_last else depth)):
                 for lane, _, _ in lanes:
                     n = n_of[lane]
                     if self.is_last:
@@ -307,12 +436,16 @@ class DeviceRpcClient(RpcClient):
                             stage_of(lane, it - depth).backward(it - depth)
                         if it < n:
                             stage_of(lane, it).forward(it)
-            total = sum(n_of.values())
+                            self._offer(stage_of(lane, it), lane, it)
+            total = self._run_competing_consumer(lanes, counts, tails, log_loss) if dyn_last else sum(n_of.values())
             self.timing["launch_downstream"] = (time.perf_counter() - t_l) * 1e3
         ev1.record(self.dstage.stream)
         t_s = time.perf_counter()
         self.dstage.stream.synchronize()
         self.timing["final_sync"] = (time.perf_counter() - t_s) * 1e3
+        self.timing["at_device_done"] = time.monotonic()
+        self._device_busy = False
+        self._device_steps = int(self.__dict__.get("_device_steps", 0)) + int(total)
         self.last_device_ms = ev0.elapsed_time(ev1)
         t_c = time.perf_counter()
         self.last_loss = (sum(float(h[0]) for h in loss_log) / len(loss_log)) if loss_log else None
@@ -322,7 +455,9 @@ class DeviceRpcClient(RpcClient):
         if self.is_first:
             self.send_to_server(M.notify(self.client_id, self.layer_id, self.cluster))
         t_p = time.perf_counter()
+        self.timing["at_notify"] = time.monotonic()
         self.trainer._wait_pause()
+        self.timing["at_pause"] = time.monotonic()
         self.timing["wait_pause"] = (time.perf_counter() - t_p) * 1e3
         return (not ex.nan_detected()), total
 
@@ -358,13 +493,14 @@ class DeviceRpcClient(RpcClient):
         leader = bool(mine) and mine[0] == me and int(self.cluster or 0) == first_cluster
         want = leader and send and done and bool(self.start_msg.get("save_parameters", True))
         rnd = int(self.start_msg.get("round", self.rounds_done + 1))
+        self.timing["at_update"] = time.monotonic()
         extra = dict(resident=True, device_ms=getattr(self, "last_device_ms", None), loss=getattr(self, "last_loss", None),
                      timing=dict(self.timing))
         if want and self.start_msg.get("async_checkpoint"):
             # the checkpoint copy leaves the round's critical path: snapshot on the device now (the next round may already
             # be training when the bytes cross PCIe), UPDATE without a payload, CHECKPOINT from a background thread
             t_s = time.perf_counter()
-            snap = {k: v.detach().clone() for k, v in ex.state_dict().items()}
+            snap = ex.state_dict()                           # detached device clones in the reference's key order
             extra["timing"]["snapshot"] = (time.perf_counter() - t_s) * 1e3
             self.send_to_server(M.update(self.client_id, self.layer_id, bool(result) and done, size, self.cluster, None,
                                          checkpoint_follows=rnd, **extra))
@@ -385,6 +521,6 @@ class DeviceRpcClient(RpcClient):
                 prev.join()                                   # rounds arrive in order
             with torch.cuda.device(self.executor.device):
                 host = {k: v.to("cpu") for k, v in snap.items()}
-            ch.publish_obj(M.RPC_QUEUE, M.checkpoint(self.client_id, self.layer_id, self.cluster, rnd, host))
+            ch.publish_obj(M.CKPT_QUEUE, M.checkpoint(self.client_id, self.layer_id, self.cluster, rnd, host))
         self._ckpt_thread = threading.Thread(target=ship, name=f"slb200-ckpt-upload-{rnd}")     # non-daemon: finishes before exit
         self._ckpt_thread.start()

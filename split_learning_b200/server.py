@@ -34,6 +34,12 @@ from .planning import auto_threshold, clustering_algorithm, partition, partition
 from .transport import Channel
 
 
+import contextlib
+import threading
+
+_NO_LOCK = contextlib.nullcontext()
+
+
 class Server:
     ALGORITHM = "main"
 
@@ -89,6 +95,15 @@ class Server:
         """Serve ``rpc_queue`` until training is finished (blocking)."""
         last = time.monotonic()
         limit = idle_timeout if idle_timeout is not None else max(self.watchdog * 4, 600.0)
+        self._start_checkpoint_receiver()
+        try:
+            self._serve(last, limit)
+        finally:
+            self._ckpt_stop.set()
+            if self._ckpt_rx is not threading.current_thread():
+                self._ckpt_rx.join(5.0)
+
+    def _serve(self, last: float, limit: float) -> None:
         while not self.done:
             m = self.ch.get_obj(M.RPC_QUEUE, 0.1)
             now = time.monotonic()
@@ -103,20 +118,45 @@ class Server:
             self.on_request(m)
         self._finish_checkpoints()
 
+    def _start_checkpoint_receiver(self) -> None:
+        """CHECKPOINT messages arrive on their own queue and are taken by their own thread (own channel): receiving a
+        134 MB body takes tens of milliseconds, during which the control loop must stay free for NOTIFY / UPDATE."""
+        import threading
+        self._ckpt_lock = threading.Lock()
+        self._ckpt_stop = threading.Event()
+        ch = self.ch.clone()
+        ch.queue_declare(M.CKPT_QUEUE)
+
+        def loop():
+            while not self._ckpt_stop.is_set():
+                try:
+                    m = ch.get_obj(M.CKPT_QUEUE, 0.2)
+                except Exception as e:              # noqa — broker gone: the run is over
+                    self.logger.log_warning(f"checkpoint receiver stopped: {e}")
+                    return
+                if m is not None and m.get("action") == M.CHECKPOINT:
+                    self.on_checkpoint(m)
+        self._ckpt_rx = threading.Thread(target=loop, daemon=True, name="slb200-ckpt-receiver")
+        self._ckpt_rx.start()
+
     def _finish_checkpoints(self, timeout: float = 180.0) -> None:
         """Training is over; stage leaders may still be shipping the last rounds' parameters for the checkpoint."""
         deadline = time.monotonic() + timeout
         while self.__dict__.get("_ckpt_pending") and time.monotonic() < deadline:
-            m = self.ch.get_obj(M.RPC_QUEUE, 0.25)
-            if m is not None and m.get("action") == M.CHECKPOINT:
-                self.on_checkpoint(m)
+            time.sleep(0.01)
+        if self.__dict__.get("_ckpt_pending"):
+            self.logger.log_warning(f"checkpoint parts of rounds {sorted(self._ckpt_pending)} never arrived")
+        if self.__dict__.get("_ckpt_stop") is not None:
+            self._ckpt_stop.set()
+            self._ckpt_rx.join(5.0)
         self.drain_checkpoints()
 
     def _beacon(self, now: float) -> None:
         """Relay liveness to every client and check that every beaconing client is still there."""
         self._last_beacon = now
+        total = self.__dict__.get("_handled", 0) + sum(int(v) for v in self.__dict__.get("progress_of", {}).values())
         for c in self.clients:
-            self.send_to_response(c.client_id, M.heartbeat())
+            self.send_to_response(c.client_id, M.heartbeat(progress=total))
         dead = [cid for cid, t in self.last_seen.items() if now - t > max(self.watchdog, 3 * self.heartbeat)]
         if dead and not self.done:
             self.logger.log_error(f"clients silent for {self.watchdog}s: {dead}; stopping the run")
@@ -126,8 +166,12 @@ class Server:
     def on_request(self, message: dict) -> None:
         action = message["action"]
         if action == M.HEARTBEAT:
-            self.last_seen[str(message.get("client_id"))] = time.monotonic()
+            cid = str(message.get("client_id"))
+            self.last_seen[cid] = time.monotonic()
+            if message.get("progress") is not None:
+                self.__dict__.setdefault("progress_of", {})[cid] = int(message["progress"])
             return
+        self._handled = self.__dict__.get("_handled", 0) + 1          # control traffic is progress too
         handler = {M.REGISTER: self.on_register, M.NOTIFY: self.on_notify, M.UPDATE: self.on_update,
                    M.READY: self.on_ready, M.CHECKPOINT: self.on_checkpoint}.get(action)
         if handler is None:
@@ -369,7 +413,10 @@ class Server:
         self._resident_votes = getattr(self, "_resident_votes", [])
         self._resident_votes.append(bool(message.get("resident", False)))
         if message.get("checkpoint_follows"):
-            self.__dict__.setdefault("_ckpt_pending", set()).add(int(message["checkpoint_follows"]))
+            with self.__dict__.get("_ckpt_lock") or _NO_LOCK:
+                rnd = int(message["checkpoint_follows"])
+                if rnd not in self.__dict__.setdefault("_ckpt_done", set()):
+                    self.__dict__.setdefault("_ckpt_pending", set()).add(rnd)
         if message.get("device_ms") is not None:
             self._device_ms = getattr(self, "_device_ms", []) + [float(message["device_ms"])]
         if layer_id == 1:
@@ -379,6 +426,8 @@ class Server:
         if message.get("timing"):
             acc = self.__dict__.setdefault("_client_timing", {})
             for k, v in message["timing"].items():
+                if k.startswith("at_"):                     # absolute stamps -> ms since the round began, latest client
+                    v = (float(v) - self._round_t0) * 1e3
                 acc[k] = max(acc.get(k, 0.0), float(v))
         if self.save_parameters and self.round_result and sd is not None:
             if has_nan(sd):
@@ -445,15 +494,17 @@ class Server:
         once every stage of the (first) cluster has arrived — the next round is not held up by a 134 MB upload + torch.save."""
         import threading
         rnd = int(message["round"])
-        parts = self.__dict__.setdefault("_ckpt_parts", {}).setdefault(rnd, {})
-        parts[int(message["layer_id"])] = message["parameters"]
-        if len(parts) < self.num_stages:
-            return
-        full: Dict[str, torch.Tensor] = {}
-        for s in sorted(parts):
-            full.update(parts[s])
-        del self._ckpt_parts[rnd]
-        self.__dict__.setdefault("_ckpt_pending", set()).discard(rnd)
+        with self.__dict__.get("_ckpt_lock") or _NO_LOCK:
+            parts = self.__dict__.setdefault("_ckpt_parts", {}).setdefault(rnd, {})
+            parts[int(message["layer_id"])] = message["parameters"]
+            if len(parts) < self.num_stages:
+                return
+            full: Dict[str, torch.Tensor] = {}
+            for s in sorted(parts):
+                full.update(parts[s])
+            del self._ckpt_parts[rnd]
+            self.__dict__.setdefault("_ckpt_done", set()).add(rnd)
+            self.__dict__.setdefault("_ckpt_pending", set()).discard(rnd)
         path = checkpoint_path(self.model_name, self.data_name, self.workdir)
 
         def write():

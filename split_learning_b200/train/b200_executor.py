@@ -223,6 +223,7 @@ class B200Executor(StageExecutor):
         torch.cuda.set_device(self.device)
         N.preload(self.device)
         self.model_cls = type(model)
+        self._sd_keys = list(model.state_dict().keys())          # checkpoint key order of this stage (reference layout)
         self.start_layer, self.end_layer = model.start_layer, model.end_layer
         self.model_name = model_name
         self.is_first, self.is_last = is_first, is_last
@@ -360,9 +361,8 @@ class B200Executor(StageExecutor):
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         torch.cuda.synchronize(self.device)
-        tmpl = self.model_cls(self.start_layer, self.end_layer).state_dict()
         out = {}
-        for key in tmpl:
+        for key in self._sd_keys:
             if key in self.entries:
                 t = self.view(self.P, key).detach().clone()
                 if t.dim() == 4:

@@ -60,7 +60,12 @@ class StageTrainer:
             return False
         if m.get("action") == M.HEARTBEAT:       # aged by its send time: a backlog of old beacons proves nothing
             age = max(0.0, time.time() - float(m.get("t", time.time())))
-            self.alive_at = max(self.alive_at, time.monotonic() - age)
+            prog = m.get("progress")
+            if prog is None or prog != self.__dict__.get("_seen_progress"):
+                # the server is alive AND somebody (a peer, the server, me) has done work since the last beacon; beacons
+                # over a system that has stopped moving do not extend a wait
+                self._seen_progress = prog
+                self.alive_at = max(self.alive_at, time.monotonic() - age)
             return False
         if m.get("action") == M.PAUSE:
             self.pause_msg = m

@@ -118,15 +118,16 @@ def test_broker_comm_allgather_and_barrier():
 
 
 def test_device_plane_lane_mapping():
-    """Lane i (first-stage client i) is served at stage s by member i % n_s; non-dividing topologies are refused
-    (-> host data plane)."""
+    """Lane i (first-stage client i) is served at stage s by member i % n_s.  A last stage that does not divide its
+    predecessor (or ``dynamic-consumers``) turns the last edge into a ticket ring: every last-stage replica may serve every
+    lane, producers have no fixed partner.  A non-dividing *middle* stage is refused (-> host data plane)."""
     import pytest
     from split_learning_b200.parallel.device_client import DeviceRpcClient
 
-    def lanes(counts, layer, member):
+    def lanes(counts, layer, member, **opts):
         members = {s + 1: [(f"c{s + 1}_{j}", 0) for j in range(n)] for s, n in enumerate(counts)}
         c = DeviceRpcClient.__new__(DeviceRpcClient)
-        c.client_id, c.layer_id, c.num_layers = f"c{layer}_{member}", layer, len(counts)
+        c.client_id, c.layer_id, c.num_layers, c.opts = f"c{layer}_{member}", layer, len(counts), opts
         return c._lanes({"peers": {"members": members}})
 
     assert lanes([4, 2, 1], 1, 3) == [(3, None, "c2_1")]
@@ -134,10 +135,14 @@ def test_device_plane_lane_mapping():
     assert [l for l, _, _ in lanes([4, 2, 1], 3, 0)] == [0, 1, 2, 3]
     assert lanes([4, 2, 1], 3, 0)[2] == (2, "c2_0", None)
     assert lanes([2, 2], 2, 1) == [(1, "c1_1", None)]
+    # competing consumers: [3, 2] cannot be cut into static lanes -> both last-stage replicas serve all three lanes
+    assert lanes([3, 2], 1, 2) == [(2, None, None)]
+    assert lanes([3, 2], 2, 1) == [(0, "c1_0", None), (1, "c1_1", None), (2, "c1_2", None)]
+    assert lanes([1, 2], 2, 0) == [(0, "c1_0", None)]
+    assert lanes([4, 2], 2, 0, **{"dynamic-consumers": True}) == [(l, f"c1_{l}", None) for l in range(4)]
+    assert lanes([4, 2, 2], 2, 1, **{"dynamic-consumers": True}) == [(1, "c1_1", None), (3, "c1_3", None)]
     with pytest.raises(RuntimeError):
-        lanes([3, 2], 1, 0)
-    with pytest.raises(RuntimeError):
-        lanes([1, 2], 2, 0)
+        lanes([3, 2, 1], 1, 0)
 
 
 @pytest.mark.parametrize("kind", ["native", "python"])

@@ -503,3 +503,43 @@ def test_baseline_scenarios_on_device_plane(tmp_path, monkeypatch, name):
         assert [len([c for c in cl if c.layer_id == s]) for s in (1, 2, 3)] == [2, 1, 1]
         sizes = sorted(len(c.train_loader.dataset) for c in cl if c.layer_id == 1)
         assert sizes[0] > 0
+
+
+@pytest.mark.parametrize("clients,slow", [((3, 2), False), ((3, 2), True), ((2, 2), False)])
+def test_competing_consumers_ticket_ring(tmp_path, monkeypatch, clients, slow):
+    """Dynamic competing consumers on the device plane (reference: every stage-2 replica ``basic_get``s one shared queue,
+    src/train/VGG16.py:143-154; the gradient returns to ``trace[-1]``, :40-53): [3, 2] cannot be cut into static lanes, so the
+    last edge is a ticket ring.  Every microbatch is claimed by exactly one replica, gradients reach their origin (the round
+    completes and every first-stage client steps), and an artificially slow replica ends up with less work."""
+    import yaml
+    monkeypatch.setenv("SLB200_WAIT_SPINS", str(1 << 24))
+    from split_learning_b200.checkpoint import load_checkpoint
+    from split_learning_b200.config import normalize
+    from split_learning_b200.runner import run_inproc
+    raw = yaml.safe_load(open("config.yaml"))
+    raw["server"].update({"clients": list(clients), "global-round": 2, "validation": False})
+    raw["server"]["data-distribution"]["num-sample"] = 400 if slow else 208        # 208 = 6 x 32 + a trailing 16
+    raw["server"]["manual"]["no-cluster"]["cut-layers"] = [7]
+    raw["server"]["manual"]["cluster"] = {"num-cluster": 1, "cut-layers": [[7]], "infor-cluster": [list(clients)]}
+    raw["log_path"] = str(tmp_path)
+    raw["learning"].update({"batch-size": 32, "control-count": 2, "learning-rate": 0.01})
+    raw["b200"] = {"synthetic-data": True, "data-plane": "device", "watchdog-seconds": 120, "dynamic-consumers": True, "claim-ahead": 1}
+    n1 = clients[0]
+    if slow:
+        raw["b200"]["debug-slow-ms"] = {n1: 4.0}              # REGISTER rank n1 = the first last-stage replica
+    srv = run_inproc(normalize(raw), devices=["cuda:0"], workdir=str(tmp_path), timeout=600)
+    assert [h["ok"] for h in srv.history] == [True, True]
+    cl = srv.clients_objs
+    assert all(c.dstage is not None and c._dynamic for c in cl)
+    last = [c for c in cl if c.layer_id == 2]
+    per_lane = 400 // 32 + (1 if 400 % 32 else 0) if slow else 7
+    everything = sorted((lane, it) for lane in range(n1) for it in range(per_lane))
+    assert sorted(t for c in last for t in c.claimed) == everything, "every microbatch exactly once, none lost"
+    assert all(len(c.claimed) > 0 for c in last)
+    if slow:
+        n_slow, n_fast = len(last[0].claimed), len(last[1].claimed)
+        assert last[0].rank == n1 and n_fast > 1.5 * n_slow, (n_slow, n_fast)     # work migrated to the free replica
+    sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    assert len(sd) == 97 and all(torch.isfinite(v.float()).all() for v in sd.values())
+    first = [c for c in cl if c.layer_id == 1]
+    assert all(c.rounds_done == 2 for c in first)

@@ -1,6 +1,9 @@
 """Isolated kernel timings + roofline fractions (CUDA events, warm-up, L2 flush between iterations).
 
-    python tools/profile_kernels.py [--only NAME] [--iters 20] [--out gpurun_out/kernels.json]
+    python tools/profile_kernels.py [--precision tf32|bf16] [--only NAME] [--iters 20] [--out gpurun_out/kernels.json]
+
+``--precision tf32`` (default, the engine's default): fp32 tensors, tcgen05 kind::tf32 convolutions (compute roofline =
+half of the measured bf16 tensor throughput), fp32 CUDA-core Linear with the SGD update fused into the weight-gradient pass.
 
 Roofline denominators: MEASURED_PEAKS.json (hbm_gbs, bf16_tflops burst).  For the fused cut kernels the target time is
 max(FLOPs / peak, link bytes / 770 GB/s) as the profiling recipe prescribes.  Under ``ncu`` use ``--only`` + ``--iters 1``.
@@ -54,8 +57,19 @@ def timeit(fn, iters, setup=None):
     return ts[len(ts) // 2], ts[0]
 
 
+PREC = "tf32"
+
+
+def ADT():
+    return torch.float32 if PREC == "tf32" else torch.bfloat16
+
+
+def ISZ():
+    return 4 if PREC == "tf32" else 2
+
+
 def bf(x):
-    return x.to(torch.bfloat16)
+    return x.to(ADT())
 
 
 def conv_case(B, H, W, Cin, Cout):
@@ -75,13 +89,13 @@ def case(fn):
 
 def _conv_fwd(B, H, W, Cin, Cout, iters):
     x, w, bias = conv_case(B, H, W, Cin, Cout)
-    y = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    y = torch.empty(B, H, W, Cout, device="cuda", dtype=ADT())
     s1, s2 = torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
     bn_, ks = N.conv_tiling(B * H * W, Cout, Cin)
     acc = torch.zeros(B * H * W, Cout, device="cuda") if ks > 1 else None
     med, best = timeit(lambda: N.conv3x3_fwd(x, w, y, bias, s1, s2, acc=acc), iters, (lambda: acc.zero_()) if acc is not None else None)
     flops = 2.0 * B * H * W * Cout * 9 * Cin
-    byts = x.numel() * 2 + w.numel() * 2 + y.numel() * 2
+    byts = (x.numel() + w.numel() + y.numel()) * ISZ()
     return {"us": med, "best_us": best, "flops": flops, "bytes": byts, "tiling": [bn_, ks]}
 
 
@@ -127,7 +141,7 @@ def conv4_wgrad(iters):
     dy = bf(torch.randn(B, H, W, Cout, device="cuda"))
     dw = torch.zeros(Cout, 3, 3, Cin, device="cuda")
     med, best = timeit(lambda: N.conv3x3_wgrad(x, dy, dw), iters)
-    return {"us": med, "best_us": best, "flops": 2.0 * B * H * W * Cout * 9 * Cin, "bytes": x.numel() * 2 + dy.numel() * 2 + dw.numel() * 4}
+    return {"us": med, "best_us": best, "flops": 2.0 * B * H * W * Cout * 9 * Cin, "bytes": (x.numel() + dy.numel()) * ISZ() + dw.numel() * 4}
 
 
 @case
@@ -137,7 +151,7 @@ def conv28_wgrad(iters):
     dy = bf(torch.randn(B, H, W, Cout, device="cuda"))
     dw = torch.zeros(Cout, 3, 3, Cin, device="cuda")
     med, best = timeit(lambda: N.conv3x3_wgrad(x, dy, dw), iters)
-    return {"us": med, "best_us": best, "flops": 2.0 * B * H * W * Cout * 9 * Cin, "bytes": x.numel() * 2 + dy.numel() * 2 + dw.numel() * 4}
+    return {"us": med, "best_us": best, "flops": 2.0 * B * H * W * Cout * 9 * Cin, "bytes": (x.numel() + dy.numel()) * ISZ() + dw.numel() * 4}
 
 
 @case
@@ -146,10 +160,10 @@ def conv8_dgrad_cut_head(iters):
     B, H, W, Cin, Cout = 32, 16, 16, 64, 128
     x, w, _ = conv_case(B, H, W, Cin, Cout)
     dy = bf(torch.randn(B, H, W, Cout, device="cuda"))
-    dx = torch.empty(B, H, W, Cin, device="cuda", dtype=torch.bfloat16)
+    dx = torch.empty(B, H, W, Cin, device="cuda", dtype=ADT())
     med, best = timeit(lambda: N.conv3x3_dgrad(dy, w, dx), iters)
-    return {"us": med, "best_us": best, "flops": 2.0 * B * H * W * Cout * 9 * Cin, "bytes": dy.numel() * 2 + w.numel() * 2 + dx.numel() * 2,
-            "link_bytes": dx.numel() * 2}
+    return {"us": med, "best_us": best, "flops": 2.0 * B * H * W * Cout * 9 * Cin, "bytes": (dy.numel() + w.numel() + dx.numel()) * ISZ(),
+            "link_bytes": dx.numel() * ISZ()}
 
 
 def _fused(B, H, W, Cin, Cout, relu, pool, iters):
@@ -160,7 +174,7 @@ def _fused(B, H, W, Cin, Cout, relu, pool, iters):
     sm, si = torch.empty(Cout, device="cuda"), torch.empty(Cout, device="cuda")
     s = torch.zeros(2 * Cout, device="cuda")
     OH, OW = (H // 2, W // 2) if pool else (H, W)
-    out = torch.zeros(B, OH, OW, Cout, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(B, OH, OW, Cout, device="cuda", dtype=ADT())
     bar = torch.zeros(4, device="cuda", dtype=torch.int32)
     flag = torch.zeros(4, device="cuda", dtype=torch.int32)
 
@@ -169,8 +183,8 @@ def _fused(B, H, W, Cin, Cout, relu, pool, iters):
         N.conv_bn_act_p2p(x, w, bias, gamma, beta, rm, rv, nbt, sm, si, s[:Cout], s[Cout:], None, out, relu, pool, bar,
                           flag=flag[0:1], seq=flag[1:2])
     med, best = timeit(run, iters)
-    return {"us": med, "best_us": best, "flops": 2.0 * B * H * W * Cout * 9 * Cin, "bytes": x.numel() * 2 + w.numel() * 2 + out.numel() * 2,
-            "link_bytes": out.numel() * 2}
+    return {"us": med, "best_us": best, "flops": 2.0 * B * H * W * Cout * 9 * Cin, "bytes": (x.numel() + w.numel() + out.numel()) * ISZ(),
+            "link_bytes": out.numel() * ISZ()}
 
 
 @case
@@ -186,6 +200,36 @@ def fused_cut14(iters):
 @case
 def fused_cut7_b128(iters):
     return _fused(128, 32, 32, 64, 64, 1, 1, iters)
+
+
+@case
+def linear50_fwd_f32(iters):
+    """fp32 Linear 4096 -> 4096 at batch 32 (parity mode): IEEE fp32 FMAs on CUDA cores, weight streamed once."""
+    x = torch.randn(32, 4096, device="cuda")
+    w = torch.randn(4096, 4096, device="cuda") * 0.01
+    acc = torch.zeros(32, 4096, device="cuda")
+    med, best = timeit(lambda: N.linear_fwd_f32(x, w, acc), iters, lambda: acc.zero_())
+    return {"us": med, "best_us": best, "flops": 2.0 * 32 * 4096 * 4096, "bytes": w.numel() * 4 + x.numel() * 4 + acc.numel() * 4, "fp32_cuda_cores": True}
+
+
+@case
+def linear50_dgrad_f32(iters):
+    dz = torch.randn(32, 4096, device="cuda")
+    w = torch.randn(4096, 4096, device="cuda") * 0.01
+    dacc = torch.zeros(32, 4096, device="cuda")
+    med, best = timeit(lambda: N.linear_dgrad_f32(dz, w, dacc), iters, lambda: dacc.zero_())
+    return {"us": med, "best_us": best, "flops": 2.0 * 32 * 4096 * 4096, "bytes": w.numel() * 4 + dz.numel() * 4 + dacc.numel() * 4, "fp32_cuda_cores": True}
+
+
+@case
+def linear50_wgrad_sgd_f32(iters):
+    """dW = dz^T x with the SGD-momentum update applied in the same pass: reads P, M once, writes P, M once; no G buffer."""
+    x = torch.randn(32, 4096, device="cuda")
+    dz = torch.randn(32, 4096, device="cuda")
+    P, Mo = torch.randn(4096, 4096, device="cuda") * 0.01, torch.zeros(4096, 4096, device="cuda")
+    bp, bm, bg = torch.zeros(4096, device="cuda"), torch.zeros(4096, device="cuda"), torch.zeros(4096, device="cuda")
+    med, best = timeit(lambda: N.linear_wgrad_f32(dz, x, sgd=(P, Mo, bp, bm, bg, 5e-4, 0.5)), iters)
+    return {"us": med, "best_us": best, "flops": 2.0 * 32 * 4096 * 4096, "bytes": P.numel() * 16 + (x.numel() + dz.numel()) * 4, "fp32_cuda_cores": True}
 
 
 @case
@@ -224,9 +268,9 @@ def bn_relu_pool_fwd_conv4(iters):
     rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
     nbt = torch.zeros((), device="cuda", dtype=torch.int64)
     sm, si = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
-    out = torch.empty(B, H // 2, W // 2, C, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(B, H // 2, W // 2, C, device="cuda", dtype=ADT())
     med, best = timeit(lambda: N.bn_relu_pool_fwd(y, s1, s2, gamma, beta, rm, rv, nbt, sm, si, out, H, W, True, True), iters)
-    return {"us": med, "best_us": best, "flops": 0.0, "bytes": y.numel() * 2 + out.numel() * 2}
+    return {"us": med, "best_us": best, "flops": 0.0, "bytes": (y.numel() + out.numel()) * ISZ()}
 
 
 @case
@@ -242,15 +286,26 @@ def fedavg_4src_local(iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16"])
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernels.json"))
     a = ap.parse_args()
-    res = {"peaks": PEAKS, "gpu": torch.cuda.get_device_name(0), "kernels": {}}
+    global PREC
+    PREC = a.precision
+    res = {"peaks": PEAKS, "precision": PREC, "gpu": torch.cuda.get_device_name(0), "kernels": {}}
+    fp32_cuda_tflops = 148 * 128 * 2 * 1.965e9 / 1e12          # FFMA peak of the CUDA cores (148 SMs x 128 lanes, 1965 MHz)
     for name, fn in CASES.items():
         if a.only and a.only != name:
             continue
+        bf16_only = name in ("linear50_fwd", "linear50_wgrad")
+        f32_only = name.endswith("_f32")
+        if (PREC == "tf32" and bf16_only) or (PREC == "bf16" and f32_only):
+            continue
         r = fn(a.iters)
-        t_c = r["flops"] / (PEAKS["bf16_tflops"] * 1e12) * 1e6
+        tensor_peak = PEAKS["bf16_tflops"] * (0.5 if PREC == "tf32" else 1.0)
+        peak = fp32_cuda_tflops if r.get("fp32_cuda_cores") else tensor_peak
+        r["compute_peak_tflops"] = peak
+        t_c = r["flops"] / (peak * 1e12) * 1e6
         t_m = r["bytes"] / (PEAKS["hbm_gbs"] * 1e9) * 1e6
         t_l = r.get("link_bytes", 0) / (NVLINK_GBS * 1e9) * 1e6
         roof = max(t_c, t_m, t_l)
