@@ -4,8 +4,9 @@
 //
 //   producer (after the pass that filled its outbox slot):   t = atom.add.sys(tail);  entry[t % R] = {origin, it, gseq, b};
 //                                                            fence.sys; st.release.sys(entry.seq, t + 1)
-//   consumer (any replica, before it enqueues a program):    t = atom.add.sys(head);  t >= total -> "round drained";
-//                                                            spin ld.acquire.sys(entry.seq) == t + 1;  read the entry
+//   consumer (any replica, before it enqueues a program):    t = head; t >= total -> "round drained"; t >= tail -> "empty";
+//                                                            atom.cas.sys(head, t, t + 1); ld.acquire.sys(entry.seq) == t + 1;
+//                                                            read the entry
 //
 // A ticket is claimed by exactly one replica (the atomic), in FIFO order, and names the origin (whose outbox slot holds the
 // payload and whose gradient mailbox receives dX) — the reference's `trace[-1]`.  The claim result goes to mapped pinned
@@ -34,17 +35,26 @@ __global__ void ticket_publish_kernel(uint32_t* ring, int ring_entries, uint32_t
 }
 
 // out (mapped pinned host memory, 8 x u32): {status, ticket, origin, it, gseq, batch, 0, 0}
-//   status 1 = claimed, 2 = drained (ticket >= total), 3 = timeout / aborted
+//   status 1 = claimed, 2 = drained (all `total` tickets handed out), 3 = timeout / aborted, 4 = nothing published yet
+// The claim never parks on the device: a ticket is taken (CAS on head) only when tail says one has been allocated, so the
+// only spin is the short window between a producer's atom.add on tail and its release of the entry.  "Nothing yet" goes
+// back to the host, which polls — a long-lived spinner would occupy an SM slot and, on a GPU shared by many streams
+// (several clients in one process), can sit in front of the very kernels that would publish the ticket it waits for.
 __global__ void ticket_claim_kernel(uint32_t* ring, int ring_entries, uint32_t total, unsigned long long max_spins,
                                     volatile uint32_t* out) {
   pdl_wait();
-  const uint32_t t = atomicAdd_system(ring + 1, 1u);
+  uint32_t t;
+  for (;;) {
+    t = ld_acquire_sys(ring + 1);
+    if (t >= total) { out[1] = t; out[0] = 2u; __threadfence_system(); return; }
+    if (t >= ld_acquire_sys(ring + 0)) { out[1] = t; out[0] = 4u; __threadfence_system(); return; }
+    if (atomicCAS_system(ring + 1, t, t + 1u) == t) break;
+  }
   out[1] = t;
-  if (t >= total) { out[0] = 2u; __threadfence_system(); return; }
   const uint32_t* e = ring + TK_HDR + static_cast<size_t>(t % ring_entries) * TK_ENTRY;
   unsigned long long spins = 0;
   while (ld_acquire_sys(e + 0) != t + 1u) {
-    __nanosleep(200);
+    __nanosleep(100);
     if (++spins > max_spins || ld_acquire_sys(ring + 2) != 0u) { out[0] = 3u; __threadfence_system(); return; }
   }
   out[2] = e[1]; out[3] = e[2]; out[4] = e[3]; out[5] = e[4];

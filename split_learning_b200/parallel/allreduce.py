@@ -101,10 +101,12 @@ class DeviceFedAvg:
     ``TorchDistComm`` / ``BrokerComm`` from parallel/fedavg.py, or any object with ``all_gather_object``); ``run`` is a
     pure device operation."""
 
-    def __init__(self, ex, uid: str, cluster: int, comm, spin_limit: int = 1 << 28):
+    def __init__(self, ex, uid: str, cluster: int, comm, spin_limit: Optional[int] = None):
         self.ex, self.uid, self.cluster, self.comm = ex, str(uid), int(cluster), comm
         self.device = ex.device
-        self.spin_limit = spin_limit
+        import os
+        # a participant that died before the round end must not park the survivors for minutes: same bound as the mailbox waits
+        self.spin_limit = int(spin_limit if spin_limit is not None else os.environ.get("SLB200_WAIT_SPINS", str(1 << 28)))
         raw, self.sync_handle, self.sync_ptr = alloc_exportable(4096, self.device)
         self.sync = raw.view(torch.int32)
         self.round = 0

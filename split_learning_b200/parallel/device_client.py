@@ -288,10 +288,13 @@ class DeviceRpcClient(RpcClient):
         done: List[torch.cuda.Event] = []
         mine = 0
         self.claimed: List[tuple] = []
+        for lane, b in tails.items():                        # compile the trailing-batch programs before the first claim,
+            if b:                                            # not while an origin is already waiting for its gradient
+                self._tail_stage(lane, b)
         while True:
             if len(done) >= ahead:
                 done[len(done) - ahead].synchronize()            # a busy replica does not hoard tickets
-            got = self._ring.claim(total, max_spins=self.dstage.wait_spins)
+            got = self._ring.claim(total, timeout=self.watchdog)
             if got is None:
                 break
             _, lane, it, gseq, b = got

@@ -52,23 +52,36 @@ class TicketRing:
         N.ticket_publish(self.ptr, self.entries, origin, it, gseq_ctr, batch)
 
     # ---- consumer -------------------------------------------------------------------------
-    def claim(self, total: int, max_spins: int = 1 << 28) -> Optional[Tuple[int, int, int, int, int]]:
-        """Blocks until this replica owns the next ticket: (ticket, origin, it, gseq, batch), or None when all ``total``
-        tickets of the round have been handed out.  Runs on a private stream so it never queues behind training work."""
+    def claim(self, total: int, max_spins: int = 1 << 22, timeout: float = 120.0,
+              alive=None) -> Optional[Tuple[int, int, int, int, int]]:
+        """Blocks (on the host) until this replica owns the next ticket: (ticket, origin, it, gseq, batch), or None when all
+        ``total`` tickets of the round have been handed out.  Each attempt is one tiny kernel on a private stream that never
+        waits for a ticket to appear; while the ring is empty the host backs off (20 us .. 1 ms).  ``alive``: optional
+        callable polled while waiting — returning False aborts (the run was stopped)."""
+        import time
         if self._out is None:
             with torch.cuda.device(self.device):
                 self._out = torch.zeros(8, dtype=torch.int32).pin_memory()
                 self._claim_stream = torch.cuda.Stream(device=self.device)
-        self._out.zero_()
-        with torch.cuda.stream(self._claim_stream):
-            N.ticket_claim(self.ptr, self.entries, total, max_spins, self._out.data_ptr())
-        self._claim_stream.synchronize()
-        status, ticket, origin, it, gseq, batch = (int(v) & 0xFFFFFFFF for v in self._out[:6].tolist())
-        if status == 2:
-            return None
-        if status != 1:
-            raise TimeoutError(f"ticket ring: ticket {ticket} was never published (producer dead?)")
-        return ticket, origin, it, gseq, batch
+        t0 = time.monotonic()
+        pause = 2e-5
+        while True:
+            self._out.zero_()
+            with torch.cuda.stream(self._claim_stream):
+                N.ticket_claim(self.ptr, self.entries, total, max_spins, self._out.data_ptr())
+            self._claim_stream.synchronize()
+            status, ticket, origin, it, gseq, batch = (int(v) & 0xFFFFFFFF for v in self._out[:6].tolist())
+            if status == 1:
+                return ticket, origin, it, gseq, batch
+            if status == 2:
+                return None
+            if status == 4:                                   # nothing published yet
+                if time.monotonic() - t0 > timeout or (alive is not None and not alive()):
+                    raise TimeoutError(f"ticket ring: no ticket for {timeout:.0f}s (producers dead?)")
+                time.sleep(pause)
+                pause = min(pause * 1.5, 1e-3)
+                continue
+            raise TimeoutError(f"ticket ring: ticket {ticket} was allocated but never published (producer dead?)")
 
     def abort(self) -> None:
         """Owner only: wake every spinning claim (a role failed)."""
