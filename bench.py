@@ -258,7 +258,11 @@ def main():
         out = ref_main(args, transport="nccl" if args.impl == "reference-nccl" else "broker")
     elif args.scenario:
         from split_learning_b200.parallel.api_bench import run_api
+        sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+        sampler.start()
+        t0 = time.perf_counter()
         api = run_api(args)
+        clocks = sampler.stop(t0, time.perf_counter())
         out = None
         if api:
             r = api.get("steady_round") or {}
@@ -271,7 +275,7 @@ def main():
                               "control_count": args.depth},
                    "e2e": {"value": r.get("images_per_s_device"), "round_wall_ms": r.get("wall_ms"),
                            "round_overhead_ms": r.get("overhead_ms"), "images_per_s_whole_round": r.get("images_per_s_round")},
-                   "api": api}
+                   "clocks": clocks, "api": api}
     else:
         out = run_ours(args)
         if not args.no_api and not args.cuts and (args.gpus == 1 or args.placement == "ring"):

@@ -19,8 +19,10 @@ def checkpoint_path(model_name: str, data_name: str, directory: str = ".") -> st
 
 
 def save_checkpoint(state_dict: Dict[str, torch.Tensor], path: str, meta: Optional[dict] = None) -> None:
+    import threading
     cpu = {k: v.detach().to("cpu") for k, v in state_dict.items()}
-    tmp = path + ".tmp"
+    # unique temporary name: two writer threads (asynchronous checkpoints of consecutive rounds) must not share one
+    tmp = f"{path}.tmp.{os.getpid()}.{threading.get_ident()}"
     torch.save(cpu, tmp)
     os.replace(tmp, path)               # atomic: a crash never leaves a torn checkpoint
     if meta is not None:

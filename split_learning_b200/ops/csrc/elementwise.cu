@@ -364,6 +364,85 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams<T> 
   }
 }
 
+// Single-launch BatchNorm backward for small feature maps (P <= 4096 pixels: the 8x8 / 4x4 / 2x2 layers of VGG at
+// microbatch 32).  BatchNorm statistics are per channel, so a block that owns 8 channels and walks *all* pixels needs no
+// cross-block reduction at all: pass 1 (dgamma, dbeta) -> block reduction -> pass 2 (dy), one launch instead of the
+// reduce + apply pair (whose second kernel re-reads what the first just read, after a kernel boundary).  The re-read of
+// pass 2 hits L1/L2.  Threads read 32-byte sectors (8 fp32 channels) — full sector efficiency.
+template <bool POOL, typename T>
+__global__ void __launch_bounds__(256) bn_bwd_chan_kernel(const BnBwdParams<T> p) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int NP = POOL ? 4 : 1;
+  const int g = blockIdx.x;                         // channel group of 8
+  float sc[8], sh[8], mean[8], istd[8], ag[8], ab[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    mean[j] = p.save_mean[c];
+    istd[j] = p.save_invstd[c];
+    sc[j] = p.gamma[c] * istd[j];
+    sh[j] = p.beta[c] - mean[j] * sc[j];
+    ag[j] = ab[j] = 0.f;
+  }
+  const int outP = POOL ? p.P >> 2 : p.P;
+  for (int op = threadIdx.x; op < outP; op += blockDim.x) {
+    float yv[NP][8], dz[NP][8];
+    long long ip[NP];
+    bn_dz<POOL, T>(p, op, g, sc, sh, yv, dz, ip);
+#pragma unroll
+    for (int q = 0; q < NP; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ab[j] += dz[q][j];
+        ag[j] += dz[q][j] * (yv[q][j] - mean[j]) * istd[j];
+      }
+  }
+  __shared__ float s_part[8][16];                   // [warp][dgamma 8 | dbeta 8]
+  __shared__ float s_tot[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ag[j] += __shfl_xor_sync(0xffffffffu, ag[j], o);
+      ab[j] += __shfl_xor_sync(0xffffffffu, ab[j], o);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_part[warp][j] = ag[j]; s_part[warp][8 + j] = ab[j]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += s_part[w][threadIdx.x];
+    s_tot[threadIdx.x] = t;
+    float* dst = threadIdx.x < 8 ? p.dgamma + g * 8 + threadIdx.x : p.dbeta + g * 8 + (threadIdx.x - 8);
+    *dst += t;                                      // this block is the only writer of its channels (buffers pre-zeroed / accumulated)
+  }
+  __syncthreads();
+  const float invP = 1.f / static_cast<float>(p.P);
+  float k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { k2[j] = s_tot[j] * invP; k1[j] = s_tot[8 + j] * invP; }
+  for (int op = threadIdx.x; op < outP; op += blockDim.x) {
+    float yv[NP][8], dz[NP][8];
+    long long ip[NP];
+    bn_dz<POOL, T>(p, op, g, sc, sh, yv, dz, ip);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = (yv[q][j] - mean[j]) * istd[j];
+        r[j] = sc[j] * (dz[q][j] - k1[j] - xhat * k2[j]);
+      }
+      store8(p.dy + ip[q] * p.C + g * 8, r);
+    }
+  }
+}
+
 // Single-launch BatchNorm backward: reduce (dgamma, dbeta) -> software grid barrier -> apply.  Every block of the grid
 // is co-resident (<= 296 blocks of 256 threads, a few KB of smem: 8 fit per SM), so the barrier cannot dead-lock; kernels
 // of other streams that may share the SMs always terminate on their own.  grid_bar: [0] arrivals (monotonic),
@@ -788,6 +867,22 @@ __global__ void dropout_bwd_kernel(const float* dacc, const uint8_t* mask, T* dx
 // (16 FLOP per weight byte): the kernels below read every weight exactly once with 16-byte coalesced loads and keep the
 // whole batch tile in registers / shared memory.
 
+// Packed fp32 FMA (FFMA2 on sm_100: two IEEE round-to-nearest fp32 FMAs per instruction, same results as two fmaf) — the
+// 3-register FFMA issues every second cycle per scheduler, so the scalar versions of these kernels sat at ~2x their
+// 37 TFLOP/s bound; pairing two batch rows per instruction halves the issue slots.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // acc[b][n] (+)= sum_{k in slice} x[b][k] * w[n][k]            grid (ceil(N/32), ceil(K/kc), ceil(B/32)), 256 threads
 // warp = (feature group of 8) x (batch half of 16); lanes stride K in float4 steps; partial sums are reduced across the
 // warp with the register butterfly and added to `acc` (zeroed by the caller) with one atomic per (b, n) per slice.
@@ -795,17 +890,19 @@ __global__ void __launch_bounds__(256) linear_fwd_f32_kernel(const float* __rest
                                                             float* acc, int B, int N, int K, int ldx, int ldw, int lda, int kc) {
   pdl_trigger();
   pdl_wait();
-  __shared__ __align__(16) float s_x[32 * 128];                 // [b][128 k] of the current step
+  // x of the current step, transposed for the packed FMAs: [j = k % 4][lane = k / 4][b], lane stride padded to 36 floats
+  // (16-byte loads of 4 consecutive batch rows by the 32 lanes of a warp hit 8 distinct bank groups per phase)
+  __shared__ __align__(16) float s_x[4 * 32 * 36];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int fg = warp >> 1, bh = warp & 1;
   const int n0 = blockIdx.x * 32 + fg * 8;
   const int k_begin = blockIdx.y * kc, k_end = min(K, k_begin + kc);
   const int b0 = blockIdx.z * 32;
-  float a[4][32];
+  f32x2 ac2[8][8];                                               // [feature][batch pair of this warp's half]
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int f = 0; f < 8; ++f)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) a[q][j] = 0.f;
+    for (int bp = 0; bp < 8; ++bp) ac2[f][bp] = 0ull;
   const int steps = (k_end - k_begin + 127) / 128;
   float4 xr[4], wr[8];
   auto fetch = [&](int step) {
@@ -826,8 +923,11 @@ __global__ void __launch_bounds__(256) linear_fwd_f32_kernel(const float* __rest
     __syncthreads();                                             // previous step's readers are done with s_x
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int e = threadIdx.x + i * 256;
-      *reinterpret_cast<float4*>(s_x + (e >> 5) * 128 + (e & 31) * 4) = xr[i];
+      const int e = threadIdx.x + i * 256, b = e >> 5, c4 = e & 31;
+      s_x[(0 * 32 + c4) * 36 + b] = xr[i].x;
+      s_x[(1 * 32 + c4) * 36 + b] = xr[i].y;
+      s_x[(2 * 32 + c4) * 36 + b] = xr[i].z;
+      s_x[(3 * 32 + c4) * 36 + b] = xr[i].w;
     }
     float4 wc[8];
 #pragma unroll
@@ -835,16 +935,29 @@ __global__ void __launch_bounds__(256) linear_fwd_f32_kernel(const float* __rest
     __syncthreads();
     if (step + 1 < steps) fetch(step + 1);                       // next step's global loads fly during the FMAs
 #pragma unroll
-    for (int b = 0; b < 16; ++b) {
-      const float4 xv = *reinterpret_cast<const float4*>(s_x + (bh * 16 + b) * 128 + 4 * lane);
+    for (int j = 0; j < 4; ++j) {
+      f32x2 xp[8];
+      const float* row = s_x + (j * 32 + lane) * 36 + bh * 16;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(row + q * 4);
+        xp[2 * q] = v.x;
+        xp[2 * q + 1] = v.y;
+      }
 #pragma unroll
       for (int f = 0; f < 8; ++f) {
-        float t = a[f >> 1][(f & 1) * 16 + b];
-        t = fmaf(wc[f].x, xv.x, t); t = fmaf(wc[f].y, xv.y, t); t = fmaf(wc[f].z, xv.z, t); t = fmaf(wc[f].w, xv.w, t);
-        a[f >> 1][(f & 1) * 16 + b] = t;
+        const float wv = j == 0 ? wc[f].x : (j == 1 ? wc[f].y : (j == 2 ? wc[f].z : wc[f].w));
+        const f32x2 wp = pack2(wv, wv);
+#pragma unroll
+        for (int bp = 0; bp < 8; ++bp) ac2[f][bp] = ffma2(wp, xp[bp], ac2[f][bp]);
       }
     }
   }
+  float a[4][32];
+#pragma unroll
+  for (int f = 0; f < 8; ++f)
+#pragma unroll
+    for (int bp = 0; bp < 8; ++bp) unpack2(ac2[f][bp], a[f >> 1][(f & 1) * 16 + 2 * bp], a[f >> 1][(f & 1) * 16 + 2 * bp + 1]);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float v = warp_col_reduce32e(a[q]);                    // lane j: sum over lanes of a[q][j]
@@ -870,9 +983,9 @@ __global__ void __launch_bounds__(128) linear_dgrad_f32_kernel(const float* __re
   }
   __syncthreads();
   if (k0 >= K) return;
-  float a[32][4];
+  f32x2 acc[16][4];                                              // [batch pair][k]: (row 2bp, row 2bp+1)
 #pragma unroll
-  for (int b = 0; b < 32; ++b) { a[b][0] = a[b][1] = a[b][2] = a[b][3] = 0.f; }
+  for (int bp = 0; bp < 16; ++bp) { acc[bp][0] = acc[bp][1] = acc[bp][2] = acc[bp][3] = 0ull; }
   const float* wp = w + (long long)n_begin * ldw + k0;
   int nn = 0;
   for (; nn + 4 <= n_cnt; nn += 4) {
@@ -881,29 +994,32 @@ __global__ void __launch_bounds__(128) linear_dgrad_f32_kernel(const float* __re
     for (int u = 0; u < 4; ++u) wv[u] = __ldcs(reinterpret_cast<const float4*>(wp + (long long)(nn + u) * ldw));
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+      const f32x2 w0 = pack2(wv[u].x, wv[u].x), w1 = pack2(wv[u].y, wv[u].y), w2 = pack2(wv[u].z, wv[u].z), w3 = pack2(wv[u].w, wv[u].w);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 d = *reinterpret_cast<const float4*>(s_dz + (nn + u) * 32 + q * 4);
-        const float dd[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          a[q * 4 + t][0] = fmaf(dd[t], wv[u].x, a[q * 4 + t][0]);
-          a[q * 4 + t][1] = fmaf(dd[t], wv[u].y, a[q * 4 + t][1]);
-          a[q * 4 + t][2] = fmaf(dd[t], wv[u].z, a[q * 4 + t][2]);
-          a[q * 4 + t][3] = fmaf(dd[t], wv[u].w, a[q * 4 + t][3]);
-        }
+        const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(s_dz + (nn + u) * 32 + q * 4);   // rows 4q..4q+3 (warp broadcast)
+        acc[2 * q][0] = ffma2(d.x, w0, acc[2 * q][0]); acc[2 * q][1] = ffma2(d.x, w1, acc[2 * q][1]);
+        acc[2 * q][2] = ffma2(d.x, w2, acc[2 * q][2]); acc[2 * q][3] = ffma2(d.x, w3, acc[2 * q][3]);
+        acc[2 * q + 1][0] = ffma2(d.y, w0, acc[2 * q + 1][0]); acc[2 * q + 1][1] = ffma2(d.y, w1, acc[2 * q + 1][1]);
+        acc[2 * q + 1][2] = ffma2(d.y, w2, acc[2 * q + 1][2]); acc[2 * q + 1][3] = ffma2(d.y, w3, acc[2 * q + 1][3]);
       }
     }
   }
   for (; nn < n_cnt; ++nn) {
     const float4 wv = __ldcs(reinterpret_cast<const float4*>(wp + (long long)nn * ldw));
+    const f32x2 w0 = pack2(wv.x, wv.x), w1 = pack2(wv.y, wv.y), w2 = pack2(wv.z, wv.z), w3 = pack2(wv.w, wv.w);
 #pragma unroll
-    for (int b = 0; b < 32; ++b) {
-      const float d = s_dz[nn * 32 + b];
-      a[b][0] = fmaf(d, wv.x, a[b][0]); a[b][1] = fmaf(d, wv.y, a[b][1]);
-      a[b][2] = fmaf(d, wv.z, a[b][2]); a[b][3] = fmaf(d, wv.w, a[b][3]);
+    for (int bp = 0; bp < 16; ++bp) {
+      const f32x2 d = *reinterpret_cast<const f32x2*>(s_dz + nn * 32 + 2 * bp);
+      acc[bp][0] = ffma2(d, w0, acc[bp][0]); acc[bp][1] = ffma2(d, w1, acc[bp][1]);
+      acc[bp][2] = ffma2(d, w2, acc[bp][2]); acc[bp][3] = ffma2(d, w3, acc[bp][3]);
     }
   }
+  float a[32][4];
+#pragma unroll
+  for (int bp = 0; bp < 16; ++bp)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) unpack2(acc[bp][k], a[2 * bp][k], a[2 * bp + 1][k]);
 #pragma unroll
   for (int b = 0; b < 32; ++b)
     if (b0 + b < B)
@@ -940,10 +1056,13 @@ __global__ void __launch_bounds__(128) linear_wgrad_f32_kernel(const float* __re
   }
   __syncthreads();
   if (k0 >= K) return;
-  float4 xv[32];
+  f32x2 xp[16][4];                                               // [batch pair][k] = (x[2bp][k], x[2bp+1][k])
 #pragma unroll
-  for (int b = 0; b < 32; ++b)
-    xv[b] = (b0 + b < B) ? __ldg(reinterpret_cast<const float4*>(x + (long long)(b0 + b) * ldx + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int bp = 0; bp < 16; ++bp) {
+    const float4 e = (b0 + 2 * bp < B) ? __ldg(reinterpret_cast<const float4*>(x + (long long)(b0 + 2 * bp) * ldx + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 o = (b0 + 2 * bp + 1 < B) ? __ldg(reinterpret_cast<const float4*>(x + (long long)(b0 + 2 * bp + 1) * ldx + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    xp[bp][0] = pack2(e.x, o.x); xp[bp][1] = pack2(e.y, o.y); xp[bp][2] = pack2(e.z, o.z); xp[bp][3] = pack2(e.w, o.w);
+  }
   const long long base = (long long)n_begin * ld + k0;
   float4 pc = make_float4(0.f, 0.f, 0.f, 0.f), mc = pc;
   if (mode == 2 && n_cnt > 0) { pc = *reinterpret_cast<const float4*>(P + base); mc = *reinterpret_cast<const float4*>(M + base); }
@@ -955,16 +1074,23 @@ __global__ void __launch_bounds__(128) linear_wgrad_f32_kernel(const float* __re
       if (mode == 2) { pn = *reinterpret_cast<const float4*>(P + off + ld); mn = *reinterpret_cast<const float4*>(M + off + ld); }
       if (mode == 1) pn = *reinterpret_cast<const float4*>(G + off + ld);
     }
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    f32x2 g2[4] = {0ull, 0ull, 0ull, 0ull};                        // (sum over even rows, sum over odd rows) per k
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 d = *reinterpret_cast<const float4*>(s_dz + nn * 32 + q * 4);
-      const float dd[4] = {d.x, d.y, d.z, d.w};
+      const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(s_dz + nn * 32 + q * 4);      // (d[4q], d[4q+1]), (d[4q+2], d[4q+3])
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        g.x = fmaf(dd[t], xv[q * 4 + t].x, g.x); g.y = fmaf(dd[t], xv[q * 4 + t].y, g.y);
-        g.z = fmaf(dd[t], xv[q * 4 + t].z, g.z); g.w = fmaf(dd[t], xv[q * 4 + t].w, g.w);
+      for (int k = 0; k < 4; ++k) {
+        g2[k] = ffma2(d.x, xp[2 * q][k], g2[k]);
+        g2[k] = ffma2(d.y, xp[2 * q + 1][k], g2[k]);
       }
+    }
+    float4 g;
+    {
+      float lo, hi;
+      unpack2(g2[0], lo, hi); g.x = __fadd_rn(lo, hi);
+      unpack2(g2[1], lo, hi); g.y = __fadd_rn(lo, hi);
+      unpack2(g2[2], lo, hi); g.z = __fadd_rn(lo, hi);
+      unpack2(g2[3], lo, hi); g.w = __fadd_rn(lo, hi);
     }
     if (mode == 2) {
       mc.x = __fadd_rn(__fmul_rn(mu, mc.x), g.x); mc.y = __fadd_rn(__fmul_rn(mu, mc.y), g.y);      // same rounding
@@ -1186,6 +1312,7 @@ int slb_preload_elementwise() {
   { auto k = bn_bwd_reduce_kernel<true, T>; SLB_PRELOAD(k); } { auto k = bn_bwd_reduce_kernel<false, T>; SLB_PRELOAD(k); } \
   { auto k = bn_bwd_apply_kernel<true, T>; SLB_PRELOAD(k); } { auto k = bn_bwd_apply_kernel<false, T>; SLB_PRELOAD(k); } \
   { auto k = bn_bwd_fused_kernel<true, T>; SLB_PRELOAD(k); } { auto k = bn_bwd_fused_kernel<false, T>; SLB_PRELOAD(k); } \
+  { auto k = bn_bwd_chan_kernel<true, T>; SLB_PRELOAD(k); } { auto k = bn_bwd_chan_kernel<false, T>; SLB_PRELOAD(k); } \
   { auto k = col_stats_kernel<T>; SLB_PRELOAD(k); } { auto k = conv_finalize_kernel<T>; SLB_PRELOAD(k); } \
   { auto k = conv3x3_small_fwd_kernel<3, 64, T>; SLB_PRELOAD(k); } { auto k = conv3x3_small_fwd_kernel<1, 64, T>; SLB_PRELOAD(k); } \
   { auto k = conv3x3_small_fwd_kernel<3, 32, T>; SLB_PRELOAD(k); } { auto k = conv3x3_small_fwd_kernel<1, 32, T>; SLB_PRELOAD(k); } \
@@ -1270,6 +1397,14 @@ int slb_bn_relu_pool_fwd(const void* y, const float* sum, const float* sumsq, co
 }
 
 }  // extern "C"
+static int bn_bwd_chan_max_p() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SLB200_BN_BWD_CHAN_MAX_P");
+    v = e ? atoi(e) : 4096;
+  }
+  return v;
+}
 template <typename T>
 static int bn_bwd_t(const void* dout, const void* y, const float* gamma, const float* beta, const float* save_mean,
                     const float* save_invstd, float* dgamma, float* dbeta, void* dy, int P, int C, int H, int W, int relu,
@@ -1300,6 +1435,12 @@ static int bn_bwd_t(const void* dout, const void* y, const float* gamma, const f
     const int g2 = grid < cap[pool ? 1 : 0] ? grid : cap[pool ? 1 : 0];
     if (pool) launch_k(bn_bwd_fused_kernel<true, T>, g2, block, 2 * C * sizeof(float), st, p, grid_bar);
     else      launch_k(bn_bwd_fused_kernel<false, T>, g2, block, 2 * C * sizeof(float), st, p, grid_bar);
+    return last_err();
+  }
+  if (!identity && !skip_reduce && P <= bn_bwd_chan_max_p()) {       // small maps: channel-owned blocks, one launch
+    const int thr = outP >= 256 ? 256 : (outP >= 128 ? 128 : 64);
+    if (pool) launch_k(bn_bwd_chan_kernel<true, T>, C / 8, thr, 0, st, p);
+    else      launch_k(bn_bwd_chan_kernel<false, T>, C / 8, thr, 0, st, p);
     return last_err();
   }
   if (pool) {

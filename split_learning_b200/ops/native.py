@@ -300,6 +300,9 @@ def bn_relu_pool_fwd(y, col_sum, col_sumsq, gamma, beta, running_mean, running_v
                                       _dt(y), _stream()), "bn_relu_pool_fwd")
 
 
+BN_BWD_CHAN_MAX_P = int(os.environ.get("SLB200_BN_BWD_CHAN_MAX_P", "4096"))
+
+
 def bn_relu_pool_bwd(dout, y, gamma, beta, save_mean, save_invstd, dgamma, dbeta, dy, H, W, relu, pool, identity=False,
                      grid_bar=None, reduced=False):
     """``grid_bar`` (3+ zeroed int32 owned by the call site) selects the single-launch reduce->barrier->apply kernel.
@@ -307,10 +310,11 @@ def bn_relu_pool_bwd(dout, y, gamma, beta, save_mean, save_invstd, dgamma, dbeta
     P, C = y.shape[0] * y.shape[1] * y.shape[2], y.shape[3]
     if reduced:
         identity, grid_bar = 2, None
+    chan = (not identity) and grid_bar is None and P <= BN_BWD_CHAN_MAX_P      # one channel-owned launch (small maps)
     _check(lib().slb_bn_relu_pool_bwd(_p(dout), _p(y), _p(gamma), _p(beta), _p(save_mean), _p(save_invstd), _p(dgamma),
                                       _p(dbeta), _p(dy), c_int(P), c_int(C), c_int(H), c_int(W), c_int(int(relu)),
                                       c_int(int(pool)), c_int(int(identity)), _p(grid_bar), _dt(y), _stream()), "bn_relu_pool_bwd",
-           1 if (identity or grid_bar is not None) else 2)
+           1 if (identity or grid_bar is not None or chan) else 2)
 
 
 def col_stats(y2d, col_sum, col_sumsq=None):

@@ -424,6 +424,9 @@ class Server:
         if message.get("loss") is not None:
             self._losses = getattr(self, "_losses", []) + [float(message["loss"])]
         if message.get("timing"):
+            per = {k: ((float(v) - self._round_t0) * 1e3 if k.startswith("at_") else float(v)) for k, v in message["timing"].items()}
+            per["layer_id"] = layer_id
+            self.__dict__.setdefault("_client_timings", []).append(per)
             acc = self.__dict__.setdefault("_client_timing", {})
             for k, v in message["timing"].items():
                 if k.startswith("at_"):                     # absolute stamps -> ms since the round began, latest client
@@ -459,7 +462,8 @@ class Server:
         metrics["phases_ms"] = dict(self._phase)
         if self.__dict__.get("_client_timing"):
             metrics["client_timing_ms"] = dict(self._client_timing)       # max over clients, per client-side phase
-            self._client_timing = {}
+            metrics["client_timings"] = list(self.__dict__.get("_client_timings", []))
+            self._client_timing, self._client_timings = {}, []
         if self.save_parameters and self.round_result:
             for k in range(len(self.topology.clusters)):
                 self.avg_all_parameters(k)
@@ -508,7 +512,11 @@ class Server:
         path = checkpoint_path(self.model_name, self.data_name, self.workdir)
 
         def write():
-            save_checkpoint(full, path, meta={"round": rnd})
+            with self.__dict__.setdefault("_ckpt_write_lock", threading.Lock()):     # one writer at a time, never back in time
+                if rnd < self.__dict__.get("_ckpt_written", 0):
+                    return
+                save_checkpoint(full, path, meta={"round": rnd})
+                self._ckpt_written = rnd
             self.logger.log_info(f"checkpoint of round {rnd} written ({len(full)} entries)")
         t = threading.Thread(target=write, daemon=True, name=f"slb200-ckpt-{rnd}")
         self.__dict__.setdefault("_ckpt_threads", []).append(t)
