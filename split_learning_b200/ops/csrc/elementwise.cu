@@ -870,6 +870,16 @@ __global__ void dropout_bwd_kernel(const float* dacc, const uint8_t* mask, T* dx
 // Packed fp32 FMA (FFMA2 on sm_100: two IEEE round-to-nearest fp32 FMAs per instruction, same results as two fmaf) — the
 // 3-register FFMA issues every second cycle per scheduler, so the scalar versions of these kernels sat at ~2x their
 // 37 TFLOP/s bound; pairing two batch rows per instruction halves the issue slots.
+// Ampere-style asynchronous copies (LDGSTS): the weight stream of the fp32 Linear kernels is staged through a ring of
+// shared-memory stages so that several steps of HBM traffic are in flight per SM without holding registers (ncu on the
+// register-prefetch version: 22 % of the stall samples on the first use of the prefetched weights, DRAM at 13 % of peak).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
   f32x2 r;
@@ -890,9 +900,11 @@ __global__ void __launch_bounds__(256) linear_fwd_f32_kernel(const float* __rest
                                                             float* acc, int B, int N, int K, int ldx, int ldw, int lda, int kc) {
   pdl_trigger();
   pdl_wait();
+  constexpr int ST = 4;                                          // weight stages in flight (16 KB each)
   // x of the current step, transposed for the packed FMAs: [j = k % 4][lane = k / 4][b], lane stride padded to 36 floats
   // (16-byte loads of 4 consecutive batch rows by the 32 lanes of a warp hit 8 distinct bank groups per phase)
   __shared__ __align__(16) float s_x[4 * 32 * 36];
+  extern __shared__ __align__(16) float s_w[];                   // [ST][32 features][128 k]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int fg = warp >> 1, bh = warp & 1;
   const int n0 = blockIdx.x * 32 + fg * 8;
@@ -904,8 +916,8 @@ __global__ void __launch_bounds__(256) linear_fwd_f32_kernel(const float* __rest
 #pragma unroll
     for (int bp = 0; bp < 8; ++bp) ac2[f][bp] = 0ull;
   const int steps = (k_end - k_begin + 127) / 128;
-  float4 xr[4], wr[8];
-  auto fetch = [&](int step) {
+  float4 xr[4];
+  auto fetch_x = [&](int step) {
     const int kb = k_begin + step * 128;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -913,14 +925,27 @@ __global__ void __launch_bounds__(256) linear_fwd_f32_kernel(const float* __rest
       xr[i] = (b0 + b < B && kb + c < k_end) ? __ldg(reinterpret_cast<const float4*>(x + (long long)(b0 + b) * ldx + kb + c))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-#pragma unroll
-    for (int f = 0; f < 8; ++f)
-      wr[f] = (n0 + f < N && kb + 4 * lane < k_end) ? __ldcs(reinterpret_cast<const float4*>(w + (long long)(n0 + f) * ldw + kb + 4 * lane))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  if (steps > 0) fetch(0);
+  auto issue_w = [&](int step) {                                 // 32 rows x 128 k = 1024 float4: four per thread
+    if (step < steps) {
+      const int kb = k_begin + step * 128;
+      float* dst = s_w + (step % ST) * 32 * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = threadIdx.x + i * 256, r = e >> 5, c = (e & 31) * 4;
+        const int n = blockIdx.x * 32 + r;
+        if (n < N && kb + c < k_end) cp_async16(dst + r * 128 + c, w + (long long)n * ldw + kb + c);
+        else *reinterpret_cast<float4*>(dst + r * 128 + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    cp_async_commit();                                           // one group per step, also when empty: uniform counting
+  };
+#pragma unroll
+  for (int s0 = 0; s0 < ST - 1; ++s0) issue_w(s0);
+  if (steps > 0) fetch_x(0);
   for (int step = 0; step < steps; ++step) {
-    __syncthreads();                                             // previous step's readers are done with s_x
+    cp_async_wait<ST - 2>();                                     // this thread's copies of stage `step` have landed
+    __syncthreads();                                             // ... everybody's have; previous step's readers are done
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = threadIdx.x + i * 256, b = e >> 5, c4 = e & 31;
@@ -929,11 +954,13 @@ __global__ void __launch_bounds__(256) linear_fwd_f32_kernel(const float* __rest
       s_x[(2 * 32 + c4) * 36 + b] = xr[i].z;
       s_x[(3 * 32 + c4) * 36 + b] = xr[i].w;
     }
+    issue_w(step + ST - 1);                                      // refills the stage that was read during step - 1
     float4 wc[8];
+    const float* ws = s_w + ((step % ST) * 32 + fg * 8) * 128 + 4 * lane;
 #pragma unroll
-    for (int f = 0; f < 8; ++f) wc[f] = wr[f];
+    for (int f = 0; f < 8; ++f) wc[f] = *reinterpret_cast<const float4*>(ws + f * 128);
     __syncthreads();
-    if (step + 1 < steps) fetch(step + 1);                       // next step's global loads fly during the FMAs
+    if (step + 1 < steps) fetch_x(step + 1);                     // x is L2-resident: one step of register prefetch suffices
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       f32x2 xp[8];
@@ -953,6 +980,7 @@ __global__ void __launch_bounds__(256) linear_fwd_f32_kernel(const float* __rest
       }
     }
   }
+  cp_async_wait<0>();
   float a[4][32];
 #pragma unroll
   for (int f = 0; f < 8; ++f)
@@ -986,12 +1014,32 @@ __global__ void __launch_bounds__(128) linear_dgrad_f32_kernel(const float* __re
   f32x2 acc[16][4];                                              // [batch pair][k]: (row 2bp, row 2bp+1)
 #pragma unroll
   for (int bp = 0; bp < 16; ++bp) { acc[bp][0] = acc[bp][1] = acc[bp][2] = acc[bp][3] = 0ull; }
+  // weights: every thread streams its own 16-byte column segment of the rows n through a private ring in shared memory
+  // (DST stages of 4 rows): DST * 64 bytes in flight per thread instead of one 4-row register group
+  constexpr int DST = 6;
+  float* s_ring = s_dz + nc * 32;                                // [DST][4 rows][blockDim.x] float4
   const float* wp = w + (long long)n_begin * ldw + k0;
-  int nn = 0;
-  for (; nn + 4 <= n_cnt; nn += 4) {
+  const int groups = (n_cnt + 3) / 4;
+  auto issue = [&](int g) {
+    if (g < groups) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float* dst = s_ring + (((g % DST) * 4 + u) * blockDim.x + threadIdx.x) * 4;
+        if (g * 4 + u < n_cnt) cp_async16(dst, wp + (long long)(g * 4 + u) * ldw);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int g = 0; g < DST - 1; ++g) issue(g);
+  for (int g = 0; g < groups; ++g) {
+    cp_async_wait<DST - 2>();                                    // my own copies of group g have landed (nobody else reads them)
     float4 wv[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) wv[u] = __ldcs(reinterpret_cast<const float4*>(wp + (long long)(nn + u) * ldw));
+    for (int u = 0; u < 4; ++u) wv[u] = *reinterpret_cast<const float4*>(s_ring + (((g % DST) * 4 + u) * blockDim.x + threadIdx.x) * 4);
+    issue(g + DST - 1);                                          // the slot of group g - 1: its values are in registers / consumed
+    const int nn = g * 4;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const f32x2 w0 = pack2(wv[u].x, wv[u].x), w1 = pack2(wv[u].y, wv[u].y), w2 = pack2(wv[u].z, wv[u].z), w3 = pack2(wv[u].w, wv[u].w);
@@ -1005,16 +1053,7 @@ __global__ void __launch_bounds__(128) linear_dgrad_f32_kernel(const float* __re
       }
     }
   }
-  for (; nn < n_cnt; ++nn) {
-    const float4 wv = __ldcs(reinterpret_cast<const float4*>(wp + (long long)nn * ldw));
-    const f32x2 w0 = pack2(wv.x, wv.x), w1 = pack2(wv.y, wv.y), w2 = pack2(wv.z, wv.z), w3 = pack2(wv.w, wv.w);
-#pragma unroll
-    for (int bp = 0; bp < 16; ++bp) {
-      const f32x2 d = *reinterpret_cast<const f32x2*>(s_dz + nn * 32 + 2 * bp);
-      acc[bp][0] = ffma2(d, w0, acc[bp][0]); acc[bp][1] = ffma2(d, w1, acc[bp][1]);
-      acc[bp][2] = ffma2(d, w2, acc[bp][2]); acc[bp][3] = ffma2(d, w3, acc[bp][3]);
-    }
-  }
+  cp_async_wait<0>();
   float a[32][4];
 #pragma unroll
   for (int bp = 0; bp < 16; ++bp)
@@ -1578,7 +1617,9 @@ int slb_linear_fwd_f32(const float* x, const float* w, float* acc, int B, int N,
   int kc = 1024;
   while (kc > 128 && fgroups * ((K + kc - 1) / kc) < 296) kc >>= 1;
   dim3 grid(fgroups, (K + kc - 1) / kc, (B + 31) / 32);
-  launch_k(linear_fwd_f32_kernel, grid, dim3(256), 0, st, x, w, acc, B, N, K, ldx, ldw, lda, kc);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(linear_fwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32 * 128 * 4); attr = true; }
+  launch_k(linear_fwd_f32_kernel, grid, dim3(256), (size_t)4 * 32 * 128 * sizeof(float), st, x, w, acc, B, N, K, ldx, ldw, lda, kc);
   return last_err();
 }
 int slb_linear_dgrad_f32(const float* dz, const float* w, float* dacc, int B, int N, int K, int lddz, int ldw, int ldd,
@@ -1589,7 +1630,10 @@ int slb_linear_dgrad_f32(const float* dz, const float* w, float* dacc, int B, in
   int nc = 256;
   while (nc > 32 && ktiles * ((N + nc - 1) / nc) < 296) nc >>= 1;
   dim3 grid(ktiles, (N + nc - 1) / nc, (B + 31) / 32);
-  launch_k(linear_dgrad_f32_kernel, grid, dim3(threads), (size_t)nc * 32 * sizeof(float), st, dz, w, dacc, B, N, K, lddz, ldw, ldd, nc);
+  const size_t smem = (size_t)nc * 32 * sizeof(float) + (size_t)6 * 4 * threads * 16;      // dz slice + per-thread weight ring
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(linear_dgrad_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+  launch_k(linear_dgrad_f32_kernel, grid, dim3(threads), smem, st, dz, w, dacc, B, N, K, lddz, ldw, ldd, nc);
   return last_err();
 }
 // mode 0: G = g, 1: G += g, 2: fused SGD-momentum on (P, M) [+ bias rows].  Batches > 32 are looped here (mode 2 needs B <= 32).
