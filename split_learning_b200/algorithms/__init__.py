@@ -22,6 +22,11 @@ def client_class(name: str = "main", opts=None):
             from ..parallel.device_client import DeviceRpcClient
             return DeviceRpcClient
         return RpcClient
+    if (opts and str(opts.get("data-plane", "host")).lower() == "device" and opts.get("device-variants", False)
+            and name in ("vanilla_sl", "cluster_fsl")):
+        # EXPERIMENTAL, opt-in (b200.device-variants: true): not yet verified on hardware — see parallel/device_variants.py
+        from ..parallel.device_variants import DEVICE_CLIENTS      # sequential variants over the ticket ring
+        return DEVICE_CLIENTS[name]
     from . import variants
     return variants.CLIENTS[name]
 

@@ -22,6 +22,21 @@ int slb_malloc(void** out, long long bytes) {
 }
 int slb_free(void* p) { return -static_cast<int>(cudaFree(p)); }
 
+// A stream of our own (non-blocking).  torch.cuda.Stream() hands out 32 pooled streams per device round-robin, so in a
+// process that creates more than 32 (several clients in one process, long test sessions) two *live* stage streams can be
+// the same CUDA stream — and a mailbox wait of one stage then sits in front of the kernel of the other that would publish
+// that flag.  high != 0: greatest priority of the device.
+int slb_stream_create(void** out, int high) {
+  int least = 0, greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  cudaStream_t s;
+  cudaError_t e = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high ? greatest : least);
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  *out = s;
+  return 0;
+}
+int slb_stream_destroy(void* s) { return -static_cast<int>(cudaStreamDestroy(static_cast<cudaStream_t>(s))); }
+
 int slb_ipc_get_handle(void* p, uint8_t* out64) {
   cudaIpcMemHandle_t h;
   cudaError_t e = cudaIpcGetMemHandle(&h, p);

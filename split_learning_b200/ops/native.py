@@ -449,6 +449,15 @@ def counter_inc(ctr):
     _check(lib().slb_counter_inc(_p(ctr), _stream()), "counter_inc")
 
 
+def new_stream(device, priority: int = 0):
+    """A dedicated non-blocking CUDA stream wrapped for torch (``torch.cuda.ExternalStream``) — not one of torch's 32 pooled
+    streams, which alias once a process has created more than 32 (see ``slb_stream_create``)."""
+    out = c_void_p()
+    with torch.cuda.device(device):
+        _check(lib().slb_stream_create(ctypes.byref(out), c_int(1 if priority < 0 else 0)), "stream_create", 0)
+    return torch.cuda.ExternalStream(out.value, device=device)
+
+
 def store_u32(ptr: int, value: int):
     """Stream-ordered ``*ptr = value`` (sets the sequence counter a following graph replay publishes from)."""
     _check(lib().slb_store_u32(c_void_p(ptr), c_uint32(value), _stream()), "store_u32")

@@ -107,7 +107,9 @@ class MailboxSpec:
         return self.header_off + 256
 
 
-_SAME_PROCESS = {}          # IPC handle -> (raw pointer, HostGate), for partners that live in this very process
+_SAME_PROCESS = {}          # IPC handle -> (raw pointer, owner Mailbox), for partners that live in this very process
+_GATE_LOCK = __import__("threading").Lock()   # several same-process peers may open one mailbox at the same time (competing
+#                                               consumers): exactly one HostGate per mailbox, or posts get lost
 
 
 class HostGate:
@@ -244,9 +246,11 @@ class Mailbox:
     def open_peer(spec: MailboxSpec, handle: bytes, device) -> "Mailbox":
         if handle in _SAME_PROCESS:            # cudaIpcOpenMemHandle refuses handles exported by the same process
             raw, owner_mb = _SAME_PROCESS[handle]
-            if owner_mb.gate is None:
-                owner_mb.gate = HostGate()
-            return Mailbox(spec, None, owner=False, raw_ptr=raw, gate=owner_mb.gate)
+            with _GATE_LOCK:
+                if owner_mb.gate is None:
+                    owner_mb.gate = HostGate()
+                gate = owner_mb.gate
+            return Mailbox(spec, None, owner=False, raw_ptr=raw, gate=gate)
         return Mailbox(spec, None, owner=False, raw_ptr=open_exported(handle, device))     # one mapping per handle and process
 
 

@@ -43,7 +43,7 @@ class TicketRing:
         """Owner only, between rounds (every participant is parked between UPDATE and the next SYN)."""
         assert self.base is not None, "only the owner resets the ring"
         self.base.zero_()
-        torch.cuda.synchronize(self.device)
+        torch.cuda.current_stream(self.device).synchronize()
 
     # ---- producer -------------------------------------------------------------------------
     def publish(self, origin: int, it: int, gseq_ctr: Optional[torch.Tensor], batch: int) -> None:
@@ -53,16 +53,19 @@ class TicketRing:
 
     # ---- consumer -------------------------------------------------------------------------
     def claim(self, total: int, max_spins: int = 1 << 22, timeout: float = 120.0,
-              alive=None) -> Optional[Tuple[int, int, int, int, int]]:
+              alive=None, stop=None) -> Optional[Tuple[int, int, int, int, int]]:
         """Blocks (on the host) until this replica owns the next ticket: (ticket, origin, it, gseq, batch), or None when all
         ``total`` tickets of the round have been handed out.  Each attempt is one tiny kernel on a private stream that never
         waits for a ticket to appear; while the ring is empty the host backs off (20 us .. 1 ms).  ``alive``: optional
-        callable polled while waiting — returning False aborts (the run was stopped)."""
+        callable polled while waiting — returning False aborts (the run was stopped).  ``stop``: optional callable for
+        producers whose number of tickets is not known up front (sequential variants: ``total`` = 2^32 - 1): once it
+        returns True *and* the ring is empty, the queue is drained (the caller saw PAUSE: every producer has finished and
+        published all its tickets)."""
         import time
         if self._out is None:
             with torch.cuda.device(self.device):
                 self._out = torch.zeros(8, dtype=torch.int32).pin_memory()
-                self._claim_stream = torch.cuda.Stream(device=self.device)
+                self._claim_stream = N.new_stream(self.device)
         t0 = time.monotonic()
         pause = 2e-5
         while True:
@@ -76,6 +79,8 @@ class TicketRing:
             if status == 2:
                 return None
             if status == 4:                                   # nothing published yet
+                if stop is not None and stop():
+                    return None
                 if time.monotonic() - t0 > timeout or (alive is not None and not alive()):
                     raise TimeoutError(f"ticket ring: no ticket for {timeout:.0f}s (producers dead?)")
                 time.sleep(pause)

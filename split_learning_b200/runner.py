@@ -87,14 +87,22 @@ def run_variant(cfg: Config, client_specs: Sequence[dict], workdir: str = ".", t
                 traceback.print_exc()
                 errors.append(e)
                 server.done = True
+                try:                            # a failed role must not leave the others waiting out their watchdogs
+                    from . import messages as M
+                    for c in list(server.clients):
+                        server.send_to_response(c.client_id, M.stop("run aborted"))
+                except Exception:
+                    pass
         return run
     threads = [threading.Thread(target=guard(lambda: server.start(idle_timeout=timeout)), daemon=True)]
+    clients = []
     for r, spec in enumerate(client_specs):
         spec = dict(spec)
         layer_id = spec.pop("layer_id")
         cluster = spec.pop("cluster", -1)
         dev = devices[r % len(devices)] if devices else "cpu"
         cli = client_class(algo, cfg.b200)(str(uuid.uuid4()), layer_id, broker, device=dev, b200_opts=cfg.b200, rank=r)
+        clients.append(cli)
 
         def body(cli=cli, cluster=cluster, spec=spec):
             cli.register(dict(DEFAULT_PROFILE), cluster, **spec)
@@ -108,4 +116,5 @@ def run_variant(cfg: Config, client_specs: Sequence[dict], workdir: str = ".", t
         raise errors[0]
     if any(t.is_alive() for t in threads):
         raise TimeoutError("run_variant: roles still alive after timeout")
+    server.clients_objs = clients
     return server

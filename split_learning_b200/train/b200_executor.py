@@ -259,7 +259,7 @@ class B200Executor(StageExecutor):
         # 36.5 k) — equal priorities let the hardware interleave best.
         prio = os.environ.get("SLB200_STAGE_PRIO", "none")
         self.stream_priority = -1 if ((prio == "last" and is_last) or (prio == "first" and is_first)) else 0
-        self.stream = torch.cuda.Stream(device=self.device, priority=self.stream_priority)
+        self.stream = N.new_stream(self.device, self.stream_priority)
         # device data plane hooks (set by parallel.mailbox): where the stage output / input gradient go
         self.out_target = None
         self.grad_target = None
@@ -357,10 +357,15 @@ class B200Executor(StageExecutor):
                         st[k].copy_(sd[f"layer{bn}.{k}"].to(self.device))
             if self.PB is not None:
                 self.PB.copy_(self.P)
-        torch.cuda.synchronize(self.device)
+        # stream-level, never device-wide: a device synchronize would also wait for kernels of *other* clients sharing the
+        # GPU — including flag waits only this thread's next launch can release — and is not permitted while a sibling
+        # thread captures a CUDA graph
+        torch.cuda.current_stream(self.device).synchronize()
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
-        torch.cuda.synchronize(self.device)
+        if getattr(self, "stream", None) is not None:
+            self.stream.synchronize()                    # the stage's own work (side streams are joined into it per pass)
+        torch.cuda.current_stream(self.device).synchronize()
         out = {}
         for key in self._sd_keys:
             if key in self.entries:
@@ -551,7 +556,7 @@ class _Plan:
         self.gnorm = torch.zeros(4, device=dev)                                 # clip-grad-norm: sum of squared gradients
         # weight-gradient kernels run on a forked stream: they only feed the optimizer, so they overlap with the
         # dY -> dX critical path of the layers below (captured as parallel branches of the CUDA graph)
-        self.side = torch.cuda.Stream(device=dev, priority=ex.stream_priority)
+        self.side = N.new_stream(dev, ex.stream_priority)
         self.graphs: Dict[Tuple[str, int], torch.cuda.CUDAGraph] = {}
         self._warm = False
 

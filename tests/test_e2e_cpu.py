@@ -174,3 +174,68 @@ def test_dead_client_becomes_an_error_not_a_deadlock(tmp_path, monkeypatch):
     with pytest.raises((RuntimeError, TimeoutError)):
         run_inproc(normalize(raw), workdir=str(tmp_path), timeout=60)
     assert time.monotonic() - t0 < 60
+
+
+def test_async_checkpoint_protocol_resident_rounds(tmp_path):
+    """The device plane's round end, replayed with scripted clients on the CPU: UPDATEs without parameters (``resident``,
+    ``checkpoint_follows``), the stage state-dicts arriving later as CHECKPOINT messages on their own queue (out of order,
+    the older round last) — the server must not wait for them inside the round, must write exactly the newest round, and
+    must not send parameters in the next START."""
+    import threading
+    import time
+    from split_learning_b200 import messages as M
+    from split_learning_b200.checkpoint import load_meta
+    from split_learning_b200.server import Server
+    from split_learning_b200.transport import InProcBroker
+    raw = _raw(tmp_path, rounds=2)
+    raw["server"]["validation"] = False
+    cfg = normalize(raw)
+    br = InProcBroker()
+    srv = Server(cfg, br, workdir=str(tmp_path))
+    th = threading.Thread(target=lambda: srv.start(idle_timeout=60), daemon=True)
+    th.start()
+    full = VGG16_CIFAR10().state_dict()
+    parts = {1: {k: v for k, v in full.items() if int(k.split(".")[0][5:]) <= 7},
+             2: {k: v for k, v in full.items() if int(k.split(".")[0][5:]) > 7}}
+    ids = {1: "c-one", 2: "c-two"}
+    for lid, cid in ids.items():
+        br.publish_obj(M.RPC_QUEUE, M.register(cid, lid, {"speed": 1.0}, -1, rank=lid - 1))
+
+    def expect(cid, action, timeout=30):
+        t0 = time.monotonic()
+        while time.monotonic() - t0 < timeout:
+            m = br.get_obj(M.reply_queue(cid), 0.5)
+            if m is not None and m.get("action") != M.HEARTBEAT:
+                assert m["action"] == action, (m["action"], action)
+                return m
+        raise AssertionError(f"{cid}: no {action}")
+    starts = []
+    for rnd in (1, 2):
+        for lid, cid in ids.items():
+            starts.append(expect(cid, M.START))
+            br.publish_obj(M.RPC_QUEUE, M.ready(cid, lid))
+        for cid in ids.values():
+            expect(cid, M.SYN)
+        br.publish_obj(M.RPC_QUEUE, M.notify(ids[1], 1, 0))
+        for cid in ids.values():
+            expect(cid, M.PAUSE)
+        for lid, cid in ids.items():
+            br.publish_obj(M.RPC_QUEUE, M.update(cid, lid, True, 4, 0, None, resident=True, checkpoint_follows=rnd,
+                                                 device_ms=12.5, loss=2.0, timing={"fedavg": 0.4, "at_update": time.monotonic()}))
+    for cid in ids.values():
+        expect(cid, M.STOP)
+    assert starts[0]["parameters"] is None and all(s["parameters"] is None and s["resident"] for s in starts[2:])
+    # round 2's parts arrive first, round 1's afterwards: the stale round must not overwrite the newer checkpoint
+    tag = lambda sd, v: {k: (t.clone().float().fill_(v) if t.is_floating_point() else t.clone()) for k, t in sd.items()}
+    for rnd in (2, 1):
+        for lid, cid in ids.items():
+            br.publish_obj(M.CKPT_QUEUE, M.checkpoint(cid, lid, 0, rnd, tag(parts[lid], float(rnd))))
+        time.sleep(0.3)
+    th.join(30)
+    assert not th.is_alive(), "server must finish once every announced checkpoint part has arrived"
+    sd = load_checkpoint(str(tmp_path / "VGG16_CIFAR10.pth"))
+    assert len(sd) == 97 and float(sd["layer1.weight"].flatten()[0]) == 2.0 and float(sd["layer50.weight"].flatten()[0]) == 2.0
+    assert load_meta(str(tmp_path / "VGG16_CIFAR10.pth")).get("round") == 2
+    assert [h["ok"] for h in srv.history] == [True, True]
+    assert srv.history[0]["device_ms"] == 12.5 and "updates_in" in srv.history[0]["phases_ms"]
+    assert srv.history[1]["first_stage_microbatches"] == 4
