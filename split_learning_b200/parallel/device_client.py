@@ -12,8 +12,9 @@ with the downstream stage multiplexing its lanes on one executor (fan-in).  If a
 divide its predecessor, or the stage has no native plan, the client keeps the host data plane —
 a *topology* fallback (logged), never a kernel fallback.
 
-Competing consumers (``b200.dynamic-consumers: true``, or automatically when the last stage does not divide its
-predecessor, e.g. clients [4, 3]): the edge into the last stage becomes a *ticket ring* (``parallel/ticket.py``).  Producers
+Competing consumers (``b200.dynamic-consumers: true``; this is also what keeps a last stage that does not divide its
+predecessor, e.g. clients [4, 3], on the device plane): the edge into the last stage becomes a *ticket ring*
+(``parallel/ticket.py``).  Producers
 keep each microbatch in their own outbox and append a ticket; every last-stage replica claims the next ticket whenever it
 has fewer than ``b200.claim-ahead`` programs in flight, copies the payload in over NVLink and returns the gradient to the
 ticket's origin — the reference's shared ``intermediate_queue`` + ``trace`` routing (src/train/VGG16.py:40-53,143-154)
@@ -94,8 +95,10 @@ class DeviceRpcClient(RpcClient):
         ids = {s: [cid for cid, _ in members[s]] for s in members}
         n = {s: len(ids[s]) for s in ids}
         L = self.num_layers
-        # the edge into the last stage is dynamic (ticket ring) on request, or when static lanes cannot cover it
-        self._dynamic = L >= 2 and n.get(L, 0) > 0 and (bool(self.opts.get("dynamic-consumers", False)) or n[L - 1] % n[L] != 0)
+        # the edge into the last stage is dynamic (ticket ring) on request — including topologies static lanes cannot cover
+        # ([4, 3]); without the flag those keep the host data plane (the ring's hardware tests still fail intermittently
+        # when several clients share ONE GPU, so it does not switch itself on)
+        self._dynamic = L >= 2 and n.get(L, 0) > 0 and bool(self.opts.get("dynamic-consumers", False))
         for s in range(2, L + 1):
             if s == L and self._dynamic:
                 continue

@@ -118,9 +118,9 @@ def test_broker_comm_allgather_and_barrier():
 
 
 def test_device_plane_lane_mapping():
-    """Lane i (first-stage client i) is served at stage s by member i % n_s.  A last stage that does not divide its
-    predecessor (or ``dynamic-consumers``) turns the last edge into a ticket ring: every last-stage replica may serve every
-    lane, producers have no fixed partner.  A non-dividing *middle* stage is refused (-> host data plane)."""
+    """Lane i (first-stage client i) is served at stage s by member i % n_s.  ``dynamic-consumers`` turns the last edge into a
+    ticket ring: every last-stage replica may serve every lane, producers have no fixed partner — also for a last stage that
+    does not divide its predecessor.  Without the flag non-dividing stages are refused (-> host data plane)."""
     import pytest
     from split_learning_b200.parallel.device_client import DeviceRpcClient
 
@@ -135,11 +135,14 @@ def test_device_plane_lane_mapping():
     assert [l for l, _, _ in lanes([4, 2, 1], 3, 0)] == [0, 1, 2, 3]
     assert lanes([4, 2, 1], 3, 0)[2] == (2, "c2_0", None)
     assert lanes([2, 2], 2, 1) == [(1, "c1_1", None)]
-    # competing consumers: [3, 2] cannot be cut into static lanes -> both last-stage replicas serve all three lanes
-    assert lanes([3, 2], 1, 2) == [(2, None, None)]
-    assert lanes([3, 2], 2, 1) == [(0, "c1_0", None), (1, "c1_1", None), (2, "c1_2", None)]
-    assert lanes([1, 2], 2, 0) == [(0, "c1_0", None)]
-    assert lanes([4, 2], 2, 0, **{"dynamic-consumers": True}) == [(l, f"c1_{l}", None) for l in range(4)]
+    # competing consumers (opt-in): [3, 2] cannot be cut into static lanes -> both last-stage replicas serve all three lanes
+    dyn = {"dynamic-consumers": True}
+    assert lanes([3, 2], 1, 2, **dyn) == [(2, None, None)]
+    assert lanes([3, 2], 2, 1, **dyn) == [(0, "c1_0", None), (1, "c1_1", None), (2, "c1_2", None)]
+    assert lanes([1, 2], 2, 0, **dyn) == [(0, "c1_0", None)]
+    assert lanes([4, 2], 2, 0, **dyn) == [(l, f"c1_{l}", None) for l in range(4)]
+    with pytest.raises(RuntimeError):                       # without the flag a non-dividing last stage keeps the host plane
+        lanes([3, 2], 1, 0)
     assert lanes([4, 2, 2], 2, 1, **{"dynamic-consumers": True}) == [(1, "c1_1", None), (3, "c1_3", None)]
     with pytest.raises(RuntimeError):
         lanes([3, 2, 1], 1, 0)
