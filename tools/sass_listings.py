@@ -20,8 +20,16 @@ KERNELS = {
     "fedavg_allreduce": "_ZN3slb23fedavg_allreduce_kernelENS_8ArParamsE",
     "linear_wgrad_sgd_f32": "_ZN3slb23linear_wgrad_f32_kernelEPKfS1_PfS2_S2_S2_S2_S2_iiiiiiiiiff",
     "sgd_momentum": "_ZN3slb19sgd_momentum_kernelEP6float4S1_S1_P5uint2xffi",
+    "attn_fwd": "_ZN3slb15attn_fwd_kernelE14CUtensorMap_stS0_S0_NS_10AttnParamsE",
+    "attn_bwd": "_ZN3slb15attn_bwd_kernelE14CUtensorMap_stS0_S0_S0_NS_10AttnParamsE",
+    "linear_fwd_f32_ffma2_ldgsts": "_ZN3slb21linear_fwd_f32_kernelEPKfS1_Pfiiiiiii",
+    "linear_dgrad_f32_ffma2_ldgsts": "_ZN3slb23linear_dgrad_f32_kernelEPKfS1_Pfiiiiiii",
+    "ticket_publish": "_ZN3slb21ticket_publish_kernelEPjijjPKjj",
+    "ticket_claim": "_ZN3slb19ticket_claim_kernelEPjijyPVj",
+    "zero_wait_flag_acquire": "_ZN3slb16zero_wait_kernelEP6float4xPKjPjyPi",
+    "litmus_pingpong": "_ZN3slb22litmus_pingpong_kernelEPjS0_PKjS2_ijiyS0_",
 }
-MARK = re.compile(r"UTC[A-Z]*MMA|UTMALDG|UTCBAR|LDTM|UTCATOMSWS|RED\.|REDG|ST\.E\.STRONG\.SYS|LD\.E\.STRONG\.SYS|SYNCS|MEMBAR|ACQBULK|UTMAPF|ERRBAR|CCTL")
+MARK = re.compile(r"UTC[A-Z]*MMA|UTMALDG|UTCBAR|LDTM|UTCATOMSWS|RED\.|REDG|ST\.E\.STRONG\.SYS|LD\.E\.STRONG\.SYS|SYNCS|MEMBAR|ACQBULK|UTMAPF|ERRBAR|CCTL|FFMA2|LDGSTS|ATOM")
 
 
 def listing(mangled):
