@@ -141,8 +141,9 @@ def run_api(args, roles=None, cfg=None) -> dict:
     t0 = time.perf_counter()
     for t in threads:
         t.start()
+    limit = min(float(args.timeout), float(os.environ.get("SLB200_API_BENCH_TIMEOUT", "420")))      # for the whole public-API run
     for t in threads:
-        t.join(args.timeout)
+        t.join(max(1.0, limit - (time.perf_counter() - t0)))
     wall = time.perf_counter() - t0
     for cli in clients:                      # background checkpoint uploads of the last round: finish before the broker goes
         th = cli.__dict__.get("_ckpt_thread")

@@ -74,3 +74,40 @@ def test_shipped_example_configs_normalise():
         algos.add(cfg.b200.get("algorithm", "main"))
         assert sum(cfg.clients) >= 2
     assert algos == {"main", "vanilla_sl", "cluster_fsl", "dcsl", "flex", "2ls"}
+
+
+def test_fedavg_allreduce_segments_two_clusters_cut_7_and_14():
+    """The device FedAvg all-reduce (``parallel/allreduce.py``) cuts the model into segments = maximal key ranges held by the
+    same set of replicas.  BASELINE config #4 (cluster 0 cut at 7, cluster 1 cut at 14): layers 1-7 live in both first
+    stages, 8-14 in stage 2 of cluster 0 and stage 1 of cluster 1, 15-52 in both last stages — for parameters, BN running
+    statistics and the integer counters alike — and every replica derives the same list from (model, layers) alone."""
+    from split_learning_b200.models import VGG16_CIFAR10
+    from split_learning_b200.parallel.allreduce import KINDS, Member, build_segments, model_key_order
+    from split_learning_b200.train.b200_executor import flat_layouts
+    spans = [(0, 7, 0), (7, 52, 0), (0, 14, 1), (14, 52, 1)]                 # (start, end, cluster)
+    members = sorted((Member(f"m{i}", cl, a, b, {}, {}) for i, (a, b, cl) in enumerate(spans)), key=lambda m: m.uid)
+    layouts = [flat_layouts(VGG16_CIFAR10, m.start_layer, m.end_layer) for m in members]
+    order = model_key_order(VGG16_CIFAR10)
+    segs = build_segments(members, layouts, order)
+    assert [s.index for s in segs] == list(range(len(segs)))
+    by_kind = {k: [s for s in segs if s.kind == k] for k in KINDS}
+    for kind in KINDS:
+        assert [s.holders for s in by_kind[kind]] == [[0, 2], [1, 2], [1, 3]], kind
+    p = by_kind["P"]
+    assert p[0].first_key == "layer1.weight" and p[1].first_key == "layer8.weight" and p[2].first_key == "layer15.weight"
+    # a segment starts where the holder's own flat layout puts its first key, and the three segments tile every stage buffer
+    for s in segs:
+        for q, off in zip(s.holders, s.offs):
+            assert off == layouts[q][s.kind][s.first_key][0]
+    for q in range(4):
+        for kind in KINDS:
+            mine = sorted((s.offs[s.holders.index(q)], s.n) for s in by_kind[kind] if q in s.holders)
+            total = sum(n for _, n in layouts[q][kind].values())
+            assert mine[0][0] == 0 and all(a + n == b for (a, n), (b, _) in zip(mine, mine[1:])) and sum(n for _, n in mine) == total
+    # every parameter of the model is covered exactly once per kind
+    covered = sum(s.n for s in p if 0 in s.holders) + sum(s.n for s in p if 1 in s.holders)
+    full = flat_layouts(VGG16_CIFAR10, 0, VGG16_CIFAR10.num_layers())
+    assert covered == sum(n for _, n in full["P"].values())
+    # one cluster, one replica per stage: a single segment per kind and holder — the degenerate case the main tests use
+    solo = build_segments(members[:2], layouts[:2], order)
+    assert [(s.kind, s.holders) for s in solo] == [(k, [q]) for k in KINDS for q in (0, 1)]
