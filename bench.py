@@ -292,6 +292,7 @@ def main():
                 out["e2e"] = {"value": r["images_per_s_device"], "unit": "images/s", "path": api["path"],
                               "ms_per_step": r["device_ms"] / api["microbatches_per_client_per_round"],
                               "h2d_bytes_per_step": api["h2d_bytes_per_step"], "d2h_bytes_per_step": api["d2h_bytes_per_step"],
+                              "steps_per_round": api["microbatches_per_client_per_round"], "rounds": len(api.get("rounds", [])),
                               "round_wall_ms": r["wall_ms"], "round_overhead_ms": r["overhead_ms"],
                               "images_per_s_whole_round": r["images_per_s_round"], "train_loss": r["train_loss"]}
                 out["api"] = api

@@ -98,7 +98,11 @@ def run_api(args, roles=None, cfg=None) -> dict:
         import torch.distributed as dist
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device(dev))
-    K = args.steps - args.steps % 5 or 5                 # microbatches per client and round (IID split over 10 labels)
+    # microbatches per client and round (IID split over 10 labels -> a multiple of 5).  A round is a user-level unit of work:
+    # it is never shorter than 100 microbatches here, so that a short ``--steps`` (the kernel-pipeline loop times exactly
+    # that many) does not turn the end-to-end number into a measurement of the round's pipeline fill and drain.
+    K = max(int(args.steps), int(os.environ.get("SLB200_API_MIN_STEPS", "100")))
+    K = K - K % 5 or 5
     rounds = int(getattr(args, "rounds", 3))
     port = 29800 + (int(os.environ.get("MASTER_PORT", "0")) % 150)
     workdir = tempfile.mkdtemp(prefix="slb200_api_")
