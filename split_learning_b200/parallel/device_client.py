@@ -67,6 +67,12 @@ class DeviceRpcClient(RpcClient):
         except Exception as e:          # topology not supported on the device plane → host plane
             print_with_color(f"[device plane] falling back to host data plane: {e}", "yellow")
             self.dstage = None
+        # competing consumers: the host gates of the mailboxes I own count per round (same-process partners only; see
+        # mailbox.HostGate.reset).  Static lanes keep the free-running later rounds: all their programs exist after round 1.
+        for entry in (self.__dict__.get("_mailbox_cache", {}).values() if self.__dict__.get("_dynamic") else ()):
+            mb = entry[0] if isinstance(entry, tuple) else None
+            if mb is not None and getattr(mb, "gate", None) is not None:
+                mb.gate.reset()
         self.timing["on_start"] = (time.perf_counter() - t_start) * 1e3
         for m in sent:
             self.send_to_server(m)

@@ -128,6 +128,15 @@ class HostGate:
             self._n += 1
             self._cv.notify_all()
 
+    def reset(self) -> None:
+        """New round (owner side, while every role is parked between UPDATE and SYN): waits count from zero again.  Without
+        it the previous round's posts satisfy every wait of the next round at once and the gate stops gating — harmless
+        while every program of the round is already captured, but with competing consumers a replica may have to capture a
+        (lane, slot) program it has not served before, i.e. instantiate a CUDA graph while the producer's wait kernel for
+        exactly that program is already spinning on the shared GPU."""
+        with self._cv:
+            self._n = 0
+
     def wait(self, count: int, timeout: float = 120.0) -> None:
         with self._cv:
             if not self._cv.wait_for(lambda: self._n >= count, timeout):
