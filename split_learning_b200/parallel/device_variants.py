@@ -157,7 +157,15 @@ class SequentialDeviceClient(DeviceRpcClient, SequentialClient):
         ahead = max(1, int(self.opts.get("claim-ahead", 2)))
         done: List[torch.cuda.Event] = []
         self.claimed: List[tuple] = []
-        paused = lambda: self.trainer._poll_pause(0.0)       # PAUSE (or STOP) is kept in trainer.pause_msg once seen
+        def paused() -> bool:
+            # idle moment of the claim loop: wire lanes whose client has come up in the meantime (its START arrives mid-round)
+            # before its first ticket — opening its gradient mailbox is also what creates the host gate a same-process
+            # producer waits on before it enqueues a backward pass
+            self._drain_handles(0.0)
+            for lane, _, _ in self._lane_info:
+                if lane not in self.dstages and ("outbox", lane) in self._handles and ("grad", lane) in self._handles:
+                    self._ensure_lane(lane)
+            return self.trainer._poll_pause(0.0)             # PAUSE (or STOP) is kept in trainer.pause_msg once seen
         while True:
             if len(done) >= ahead:
                 done[len(done) - ahead].synchronize()
