@@ -66,11 +66,15 @@ class BatchedTensorLoader:
     page-locked staging slot instead of ``batch_size`` ``__getitem__`` calls + ``default_collate`` (≈0.3 ms per CIFAR
     microbatch with ``torch.utils.data.DataLoader``, which is the whole device time of a first-stage step on a B200).
     Same iteration contract as ``DataLoader(ds, batch_size, shuffle, drop_last=False)``: a fresh permutation per epoch, the
-    short batch last.  ``pin=True`` yields views of a ring of pinned slots, one per microbatch of an epoch — a slot is
-    rewritten one epoch later, after the consumer's H2D copies of the previous epoch have completed."""
+    short batch last.  ``pin=True`` yields pinned slots, one per microbatch of an epoch (epochs of up to
+    ``MAX_PINNED_BATCHES`` microbatches; longer ones yield pageable tensors) — a slot is rewritten one epoch later, after the
+    consumer's H2D copies of the previous epoch have completed."""
+
+    MAX_PINNED_BATCHES = 512          # beyond this the consumer stages through its own bounded pinned ring instead
 
     def __init__(self, dataset, batch_size: int, shuffle: bool = True, pin: bool = False, seed: int = 0):
-        self.dataset, self.batch_size, self.shuffle, self.pin = dataset, int(batch_size), shuffle, pin
+        self.dataset, self.batch_size, self.shuffle = dataset, int(batch_size), shuffle
+        self.pin = bool(pin) and (len(dataset) + int(batch_size) - 1) // int(batch_size) <= self.MAX_PINNED_BATCHES
         self.drop_last = False
         self._gen = torch.Generator().manual_seed(seed + 1)
         self._slots: dict = {}

@@ -77,19 +77,34 @@ class DeviceRpcClient(RpcClient):
         for m in sent:
             self.send_to_server(m)
 
+    PIN_RING = 32
+
     def _pinned(self, it: int, x: torch.Tensor, y: torch.Tensor):
-        """Pinned staging slot ``it`` of this client's input pool (allocated once, re-used by every round: all H2D copies of
-        a round have completed when the round's stream synchronize returns)."""
+        """Page-locked staging for a microbatch that is not pinned yet: a ring of ``PIN_RING`` slots (bounded, whatever the
+        length of the epoch).  A slot is reused only after the H2D copy that read it has completed (event recorded by
+        ``_pin_mark`` right after the copy was enqueued).  Loaders that already yield pinned tensors pass through."""
+        self._pin_last = None
         if x.is_cuda or (x.is_pinned() and y.is_pinned() and x.dtype == torch.float32 and y.dtype == torch.long):
             return x, y
         pool = self.__dict__.setdefault("_pin_pool", {})
-        key = (it, tuple(x.shape))
+        key = (it % self.PIN_RING, tuple(x.shape))
         if key not in pool:
-            pool[key] = (torch.empty(x.shape, dtype=torch.float32).pin_memory(), torch.empty(y.shape, dtype=torch.long).pin_memory())
-        px, py = pool[key]
+            pool[key] = [torch.empty(x.shape, dtype=torch.float32).pin_memory(), torch.empty(y.shape, dtype=torch.long).pin_memory(), None]
+        px, py, ev = pool[key]
+        if ev is not None:
+            ev.synchronize()                                 # PIN_RING microbatches ago: long done
         px.copy_(x)
         py.copy_(y)
+        self._pin_last = key
         return px, py
+
+    def _pin_mark(self, stream) -> None:
+        key = self.__dict__.get("_pin_last")
+        if key is not None:
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            self._pin_pool[key][2] = ev
+            self._pin_last = None
 
     # ------------------------------------------------------------------
     def _lanes(self, msg: dict):
@@ -404,6 +419,7 @@ class DeviceRpcClient(RpcClient):
                     it_b += 1
                 t1 = pc()
                 stage_of(it).stage_input(it, x, y)
+                self._pin_mark(stage_of(it).stream)
                 t2 = pc()
                 stage_of(it).forward(it)
                 self._offer(stage_of(it), lane, it)
