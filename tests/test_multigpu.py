@@ -63,3 +63,17 @@ def test_ring_bench_selfcheck_and_litmus():
     assert out["selfcheck"]["ok"], out["selfcheck"]
     assert out["litmus"]["ok"], out["litmus"]
     assert out["fedavg_round"]["max_abs_err_vs_nccl_mean"] < 1e-5 and out["fedavg_round"]["aggregated"]
+
+
+@pytest.mark.skipif(_ngpu() < 4, reason="needs 4 GPUs")
+@pytest.mark.parametrize("scenario,clients", [("split", [2, 2]), ("clusters", [2, 2]), ("three-stage", [2, 1, 1])])
+def test_baseline_scenarios_through_public_api_four_gpus(scenario, clients):
+    """BASELINE.json configs #3 / #4 / #5 scaled to four GPUs, one client per GPU, through the public API
+    (``bench.py --scenario``): server + client FSMs over the broker, device data plane, device FedAvg all-reduce (also across
+    clusters cut at 7 and at 14), asynchronous checkpoint — every round must finish and report device-timed throughput."""
+    r = _torchrun(4, ["bench.py", "--gpus", "4", "--steps", "20", "--warmup", "5", "--scenario", scenario])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["config"]["clients"] == clients and out["value"] > 0
+    assert all(rd["ok"] for rd in out["api"]["rounds"]) and out["api"]["checkpoint_written"]
+    assert out["e2e"]["round_overhead_ms"] is not None and out["e2e"]["round_overhead_ms"] < 200
