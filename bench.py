@@ -52,7 +52,7 @@ def parse():
                     help="run ONLY the public-API path on a named BASELINE.json configuration, one client per GPU: split = [N/2, N/2] "
                          "cut 7 (#2/#3), clusters = two clusters cut 7 / 14 (#4), three-stage = cuts [5, 10], non-IID 0.5 (#5)")
     ap.add_argument("--no-api", action="store_true", help="skip the run through the public API (server + client FSMs over the broker)")
-    ap.add_argument("--rounds", type=int, default=3, help="public-API run: global rounds (the first one pays graph capture and wiring)")
+    ap.add_argument("--rounds", type=int, default=4, help="public-API run: global rounds (the first one pays graph capture and wiring)")
     ap.add_argument("--no-selfcheck", action="store_true", help="skip the cross-GPU vs single-GPU loss-trajectory check")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--timeout", type=float, default=1500.0)
