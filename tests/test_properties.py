@@ -106,3 +106,57 @@ def test_label_allocation_shapes_and_budgets(clients, labels, samples, seed):
     for name in ("flex", "2ls"):
         m = preset_matrix(name, clients, labels)
         assert m.shape == (clients, labels) and np.allclose(m.sum(1), 1.0) and (m >= 0).all()
+
+
+# ------------------------------------------------------------------------------------------------ wire codec
+_leaf = st.one_of(st.none(), st.booleans(), st.integers(-2**40, 2**40), st.floats(allow_nan=False, width=32), st.text(max_size=12),
+                  st.binary(max_size=24))
+_tensor = st.tuples(st.sampled_from(["float32", "float16", "int64", "uint8", "bool"]),
+                    st.lists(st.integers(0, 5), min_size=0, max_size=3)).map(
+    lambda a: (torch.arange(int(np.prod(a[1])) if a[1] else 1).reshape(a[1] if a[1] else ()) % 2).to(getattr(torch, a[0])))
+_tree = st.recursive(st.one_of(_leaf, _tensor), lambda kids: st.one_of(st.lists(kids, max_size=4), st.tuples(kids, kids),
+                                                                      st.dictionaries(st.text(max_size=6), kids, max_size=4)),
+                     max_leaves=12)
+
+
+def _same(a, b):
+    if isinstance(a, torch.Tensor):
+        return isinstance(b, torch.Tensor) and a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)
+    if isinstance(a, dict):
+        return isinstance(b, dict) and a.keys() == b.keys() and all(_same(a[k], b[k]) for k in a)
+    if isinstance(a, (list, tuple)):
+        return type(a) is type(b) and len(a) == len(b) and all(_same(x, y) for x, y in zip(a, b))
+    if isinstance(a, float):
+        return isinstance(b, float) and (a == b)
+    return a == b and type(a) is type(b)
+
+
+@FAST
+@given(_tree)
+def test_codec_round_trips_arbitrary_message_trees(obj):
+    """Whatever a control-plane message carries (nested containers, scalars, tensors of any dtype / rank incl. empty ones): both
+    wire forms — the plain pickle and the segmented form with out-of-band tensor memory — decode to an equal object."""
+    from split_learning_b200.transport import codec
+    assert _same(codec.loads(codec.dumps(obj)), obj)
+    assert _same(codec.loads(bytearray(b"".join(codec.dump_segments(obj)))), obj)
+    assert _same(codec.loads(bytes(b"".join(codec.dump_segments(obj)))), obj)
+
+
+@FAST
+@given(st.sampled_from(["os.system", "subprocess.Popen", "builtins.eval", "builtins.exec", "builtins.__import__", "posix.system",
+                        "shutil.rmtree", "torch.load", "pickle.loads", "importlib.import_module"]), st.text(max_size=10))
+def test_codec_refuses_every_foreign_global(target, arg):
+    """The restricted unpickler resolves a fixed allow-list; any other global — whatever its arguments — is refused before it is
+    called."""
+    import pickle
+    from split_learning_b200.transport import codec
+    mod, name = target.rsplit(".", 1)
+    payload = b"\x80\x04c" + mod.encode() + b"\n" + name.encode() + b"\n" + pickle.dumps((arg,), protocol=2)[2:-1] + b"R."
+    try:                                            # the payload is a well-formed pickle: stock pickle would call the global
+        assert pickle.loads(b"\x80\x04cbuiltins\nlen\n" + pickle.dumps((arg,), protocol=2)[2:-1] + b"R.") == len(arg)
+    except Exception as err:                        # noqa
+        raise AssertionError(f"test payload malformed: {err}")
+    import pytest
+    with pytest.raises(Exception) as e:
+        codec.loads(payload)
+    assert isinstance(e.value, codec.UnsafePayload), e.value
