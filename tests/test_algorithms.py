@@ -153,3 +153,37 @@ def test_validation_gate_and_heartbeat_pump():
     ok_strict, _ = get_val("KWT", "SPEECHCOMMANDS", bad, strict=True, device="cpu", synthetic=True)
     assert ok_main and math.isnan(m_main["val_loss"]) and not ok_strict
     assert get_val("NOPE", "CIFAR10", {}, device="cpu") == (False, {})
+
+
+def test_batched_tensor_loader_contract():
+    """``BatchedTensorLoader`` = ``DataLoader(ds, batch_size, shuffle, drop_last=False)`` for an in-memory dataset: every sample
+    exactly once per epoch, the short batch last, a new permutation every epoch, per-client seeds, exact per-label counts;
+    pinned staging is capped (long epochs yield pageable tensors and the consumer stages through its own bounded ring)."""
+    from split_learning_b200.data.loaders import BatchedTensorLoader, SyntheticDataset, data_loader
+    counts = [7, 0, 13, 5, 0, 0, 9, 1, 0, 3]
+    ds = SyntheticDataset("CIFAR10", counts, seed=3)
+    assert len(ds) == sum(counts) and torch.bincount(ds.labels, minlength=10).tolist() == counts
+    ld = BatchedTensorLoader(ds, 8, shuffle=True, pin=False, seed=3)
+    assert len(ld) == 5 and ld.batch_size == 8 and ld.drop_last is False
+    epochs = []
+    for _ in range(2):
+        xs, ys, sizes = [], [], []
+        for x, y in ld:
+            assert x.shape[1:] == (3, 32, 32) and x.dtype == torch.float32 and y.dtype == torch.long
+            xs.append(x), ys.append(y), sizes.append(x.shape[0])
+        assert sizes == [8, 8, 8, 8, 6]                                   # the short batch comes last
+        x, y = torch.cat(xs), torch.cat(ys)
+        assert torch.bincount(y, minlength=10).tolist() == counts            # every sample once
+        key = x.flatten(1).sum(1)
+        assert torch.allclose(key.sort().values, ds.data.flatten(1).sum(1).sort().values)
+        epochs.append(y)
+    assert not torch.equal(epochs[0], epochs[1])                              # reshuffled
+    fixed = BatchedTensorLoader(ds, 8, shuffle=False)
+    assert torch.equal(torch.cat([y for _, y in fixed]), ds.labels)
+    # different clients draw different samples; validation never re-draws the training stream
+    a = data_loader("CIFAR10", 8, counts, train=True, synthetic=True, seed=1).dataset.data
+    b = data_loader("CIFAR10", 8, counts, train=True, synthetic=True, seed=2).dataset.data
+    v = data_loader("CIFAR10", 8, counts, train=False, synthetic=True, seed=1).dataset.data
+    assert not torch.equal(a, b) and not torch.equal(a[: len(v)], v[: len(a)])
+    long_epoch = BatchedTensorLoader(SyntheticDataset("MNIST", [60] * 10, seed=0), 1, pin=True)
+    assert len(long_epoch) == 600 > BatchedTensorLoader.MAX_PINNED_BATCHES and long_epoch.pin is False
